@@ -1,0 +1,168 @@
+/* pyves_b200 -- C ABI of the B200-native biased-Langevin VES hot path.
+ *
+ * One opaque handle = one ensemble of independent walkers on one GPU.  Every entry point
+ * returns 0 on success or a negative PYVES_E* code; nothing throws across the boundary;
+ * pyves_last_error() returns the message of the last failure on that handle (or the last
+ * handle-less failure when h == NULL).  All array arguments are CALLER-OWNED and are not
+ * retained past the call, except the state that pyves_set_state() copies in and the bias
+ * parameters that pyves_set_bias_*() copy to the device.  A handle is not thread-safe;
+ * distinct handles are independent.  Work is enqueued on the cudaStream_t passed as
+ * `stream` (NULL = legacy default stream).  "on_host" selects host pointers (the library
+ * stages through device memory and synchronises the stream) or device pointers.
+ *
+ * Element type of `void*` state/energy/force arrays is the handle's precision
+ * (float for PYVES_F32, double for PYVES_F64); moment / histogram outputs are always double.
+ *
+ * Each declaration cites the reference interface (apallath/pyves) it replaces.
+ */
+#ifndef PYVES_B200_H
+#define PYVES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pyves_ctx pyves_t;
+
+#define PYVES_ABI_VERSION 1
+
+/* error codes */
+#define PYVES_OK 0
+#define PYVES_EINVAL (-1)   /* bad argument (Python shim raises ValueError) */
+#define PYVES_ECUDA (-2)    /* CUDA runtime failure, sticky (RuntimeError) */
+#define PYVES_ESTATE (-3)   /* call sequence error, e.g. stepping before set_integrator */
+#define PYVES_ENOMEM (-4)
+#define PYVES_EUNSUPPORTED (-5) /* NotImplementedError */
+
+/* precision of state and force arithmetic */
+#define PYVES_F32 0
+#define PYVES_F64 1
+
+/* integration scheme: ves/langevin_dynamics.py:49-51 builds openmm.LangevinIntegrator */
+#define PYVES_SCHEME_OPENMM_LANGEVIN 0 /* v <- a v + b F/m + c xi/sqrt(m); x <- x + dt v */
+#define PYVES_SCHEME_MIDDLE 1          /* openmm.LangevinMiddleIntegrator (BAOAB-like), optional */
+
+/* potential kinds: ves/potentials.py.  params (doubles):
+ *   SLIP_BOND_2D  : force_x force_y y_0 y_scale y_shift xy_0 xy_scale          (:166,183)
+ *   CATCH_BOND_2D : the 7 above + gx_0 gx_scale gy_0 gy_scale                  (:199,229)
+ *   SZABO_BEREZHKOVSKII : x0 omega2 Omega2 Delta                               (:241-254)
+ *   others take none.  z always feels 1000 z^2 (:105); 1D kinds add 1000 y^2 (:32).     */
+#define PYVES_POT_SINGLE_WELL_1D 0
+#define PYVES_POT_DOUBLE_WELL_1D 1
+#define PYVES_POT_SINGLE_WELL_2D 2
+#define PYVES_POT_DOUBLE_WELL_2D 3
+#define PYVES_POT_SLIP_BOND_2D 4
+#define PYVES_POT_CATCH_BOND_2D 5
+#define PYVES_POT_SZABO_BEREZHKOVSKII 6
+#define PYVES_POT_MULLER_BROWN 7
+
+/* bias kinds */
+#define PYVES_BIAS_NONE 0
+#define PYVES_BIAS_LEGENDRE_1D 1 /* ves/basis.py:16-156  LegendreBasis1D */
+#define PYVES_BIAS_LEGENDRE_2D 2 /* tensor product, new (BASELINE.json configs[1]) */
+#define PYVES_BIAS_MLP_1D 3      /* ves/basis.py:159-232 NNBasis1D */
+#define PYVES_BIAS_PATHCV 4      /* ves/basis.py:386-548 LegendreBasis2DPathCV */
+#define PYVES_BIAS_HARMONIC 5    /* ves/bias.py:97-133   HarmonicBias_SingleParticle_1D */
+
+#define PYVES_ACT_RELU 0
+#define PYVES_ACT_TANH 1
+
+#define PYVES_MAX_DEGREE 63   /* Legendre degree per axis */
+#define PYVES_MAX_PATH 256    /* images on a path CV */
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* replaces SingleParticleSimulation.__init__ (ves/langevin_dynamics.py:21-83): System +
+ * Context creation.  dims = 2 (z dropped; it is decoupled) or 3.  `seed` keys the Philox
+ * stream (setRandomNumberSeed, :52-53). */
+int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_t seed, int precision);
+int pyves_destroy(pyves_t* h);
+const char* pyves_last_error(const pyves_t* h);
+int pyves_abi_version(void);
+
+/* ---- configuration ------------------------------------------------------------------- */
+/* LangevinIntegrator(temp, friction, timestep) + addParticle(mass), :34-51.  kT in kJ/mol,
+ * friction in 1/ps, dt in ps, mass in Da. */
+int pyves_set_integrator(pyves_t* h, double mass, double kT, double friction, double dt, int scheme);
+/* system.addForce(potential), :44-47 (CustomExternalForce from ves/potentials.py) */
+int pyves_set_potential(pyves_t* h, int kind, const double* params, int nparams);
+/* global id of local walker 0 (walker sharding across GPUs); Philox counters use global ids */
+int pyves_set_walker_offset(pyves_t* h, int64_t gid0);
+int pyves_set_step_counter(pyves_t* h, int64_t step);
+int pyves_get_step_counter(const pyves_t* h, int64_t* step);
+
+/* system.addForce(bias.force) + context.reinitialize, :143-145,155-159,167-169; the
+ * TorchForce(model_loc) round trip of ves/bias.py:52-58 becomes a parameter upload. */
+int pyves_set_bias_none(pyves_t* h);
+/* axis 0 = x, 1 = y; w[degree+1] */
+int pyves_set_bias_legendre1d(pyves_t* h, int axis, int degree, double lo, double hi, const double* w);
+/* minmax = {xlo, xhi, ylo, yhi}; w row-major [deg_x+1][deg_y+1] */
+int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* minmax, const double* w);
+/* theta in torch parameters() order: W0[h0,1] b0[h0] W1[h1,h0] b1[h1] ... Wout[1,hL] bout[1] */
+int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act,
+                       const double* theta);
+int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, const double* y_i, double lam,
+                          const double* w, double phi);
+int pyves_set_bias_harmonic(pyves_t* h, int axis, double k, double s0);
+/* number of basis functions (Legendre) or parameters (MLP) of the current bias */
+int pyves_basis_size(const pyves_t* h, int64_t* K);
+
+/* ---- walker state: SoA, pos[dims][n], vel[dims][n] ---------------------------------- */
+/* context.setPositions / setState (:69-76) */
+int pyves_set_state(pyves_t* h, const void* pos, const void* vel, int on_host, void* stream);
+/* context.getState(getPositions, getVelocities) (:201,208) */
+int pyves_get_state(pyves_t* h, void* pos, void* vel, int on_host, void* stream);
+/* ves/config_creation.py:56-68 for every walker: up to ntrials uniform draws in
+ * box = {xmin,xmax,ymin,ymax}, accept the first with exp(-beta U) >= 0.5; z = 0.
+ * n_failed (host) receives the number of walkers that were never accepted. */
+int pyves_init_positions_mc(pyves_t* h, const double* box, double beta, int ntrials, int64_t* n_failed, void* stream);
+/* context.setVelocitiesToTemperature (:70-74): v = sqrt(kT/m) N(0,1) */
+int pyves_init_velocities(pyves_t* h, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* integrator.step(nsteps) (:188) for every walker: potential force + bias force + noise +
+ * update, state held in registers for the whole launch.  injected_noise: NULL = Philox, or
+ * a device array [nsteps][dims][n] of N(0,1) draws (parity tests). */
+int pyves_step(pyves_t* h, int64_t nsteps, const void* injected_noise, void* stream);
+/* same, recording positions of walkers [0, n_rec) before every `every`-th step (frame t is
+ * written before step t, as :180-188 does) into traj_out (device) [n_frames][dims][n_rec],
+ * n_frames = ceil(nsteps / every). */
+int pyves_step_record(pyves_t* h, int64_t nsteps, int64_t every, int64_t n_rec, void* traj_out,
+                      const void* injected_noise, void* stream);
+
+/* TorchForce evaluation (ves/bias.py:58; LegendreBasis1D.forward ves/basis.py:123-156):
+ * bias energy E[n] and force F[n][ncols] (= -dE/dpos) at caller positions pos[n][ncols]
+ * (row-major like the reference's [N,3] tensors; ncols 1..3, missing columns read as 0).
+ * E or F may be NULL. */
+int pyves_eval_bias(pyves_t* h, const void* pos, int64_t n, int ncols, void* E, void* F, int on_host, void* stream);
+/* potential energy U + V_bias and kinetic energy per walker of the handle's state
+ * (context.getState(getEnergy=True), :227-228) */
+int pyves_energies(pyves_t* h, void* PE, void* KE, int on_host, void* stream);
+
+/* The two Python loops of VESBias_SingleParticle_1D.update (ves/bias.py:219-233) and the
+ * ensemble averages of textbook VES: sum_w, sum_w f_k, optionally sum_w f_k f_l, with
+ * f = dV/dparam (basis functions for Legendre, parameter gradient for the MLP).
+ * pos == NULL: the handle's walkers; else caller rows pos[n][ncols].  row_weights == NULL:
+ * w = 1.  sum_wff may be NULL.  Outputs are double: sum_w[1], sum_wf[K], sum_wff[K*K]. */
+int pyves_moments(pyves_t* h, const void* pos, int64_t n, int ncols, const void* row_weights, double* sum_w,
+                  double* sum_wf, double* sum_wff, int on_host, void* stream);
+
+/* ves/visualization.py:475 histogram of positions (pos == NULL: the handle's walkers).
+ * ndim 1: axis picks the column; ndim 2: (x, y).  range = {lo0, hi0, lo1, hi1};
+ * counts[nbins0 * nbins1] (row-major, x outer) is ACCUMULATED into (zero it first). */
+int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim, int axis, const double* range,
+                    const int* nbins, const void* row_weights, double* counts, int on_host, void* stream);
+
+/* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general kernel) */
+int pyves_set_tuning(pyves_t* h, int variant);
+
+/* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */
+int pyves_fp32_fma_peak(int device, double* tflops);
+/* kernels launched by this library since load (bench.py's gpu_launches evidence) */
+int64_t pyves_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

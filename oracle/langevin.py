@@ -34,7 +34,7 @@ def constants(mass=1.0, temp=300.0, friction=20.0, timestep_fs=10.0):
     a = math.exp(-friction * dt)
     b = (1.0 - a) / friction if friction != 0.0 else dt
     c = math.sqrt(kT * (1.0 - a * a))
-    return dict(mass=mass, kT=kT, dt=dt, a=a, b=b, c=c,
+    return dict(mass=mass, kT=kT, dt=dt, friction=friction, a=a, b=b, c=c,
                 b_over_m=b / mass, c_over_sqrtm=c / math.sqrt(mass),
                 sigma_v=math.sqrt(kT / mass))
 

@@ -1,0 +1,8 @@
+"""pyves_b200 -- B200-native biased-Langevin VES hot path behind the API of apallath/pyves.
+
+The compute path is the CUDA library ``csrc/libpyves_b200.so`` (C ABI in
+``include/pyves_b200.h``), reached through ``pyves_b200._lib``; the modules ``basis``, ``bias``,
+``target``, ``potentials``, ``langevin_dynamics`` and ``config_creation`` mirror the reference's
+``ves.*`` modules.  There is no CPU fallback.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,375 @@
+"""ctypes binding of the C ABI in ``include/pyves_b200.h`` (``csrc/libpyves_b200.so``).
+
+There is no CPU fallback: if the shared library is missing, ``load()`` raises, and every compute
+entry point needs a CUDA device.  ``Ensemble`` is a thin object wrapper around one handle.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpyves_b200.so")
+
+F32, F64 = 0, 1
+SCHEME_OPENMM_LANGEVIN, SCHEME_MIDDLE = 0, 1
+SCHEMES = {"openmm_langevin": SCHEME_OPENMM_LANGEVIN, "middle": SCHEME_MIDDLE}
+(POT_SINGLE_WELL_1D, POT_DOUBLE_WELL_1D, POT_SINGLE_WELL_2D, POT_DOUBLE_WELL_2D, POT_SLIP_BOND_2D,
+ POT_CATCH_BOND_2D, POT_SZABO_BEREZHKOVSKII, POT_MULLER_BROWN) = range(8)
+BIAS_NONE, BIAS_LEGENDRE_1D, BIAS_LEGENDRE_2D, BIAS_MLP_1D, BIAS_PATHCV, BIAS_HARMONIC = range(6)
+ACT_RELU, ACT_TANH = 0, 1
+MAX_DEGREE = 63
+
+EINVAL, ECUDA, ESTATE, ENOMEM, EUNSUPPORTED = -1, -2, -3, -4, -5
+
+_c = ctypes
+_vp, _i, _i64, _u64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_double
+_dp = _c.POINTER(_c.c_double)
+_ip = _c.POINTER(_c.c_int)
+
+# name -> (restype, argtypes); every symbol include/pyves_b200.h declares
+SIGNATURES = {
+    "pyves_create": (_i, [_c.POINTER(_vp), _i, _i64, _i, _u64, _i]),
+    "pyves_destroy": (_i, [_vp]),
+    "pyves_last_error": (_c.c_char_p, [_vp]),
+    "pyves_abi_version": (_i, []),
+    "pyves_set_integrator": (_i, [_vp, _d, _d, _d, _d, _i]),
+    "pyves_set_potential": (_i, [_vp, _i, _dp, _i]),
+    "pyves_set_walker_offset": (_i, [_vp, _i64]),
+    "pyves_set_step_counter": (_i, [_vp, _i64]),
+    "pyves_get_step_counter": (_i, [_vp, _c.POINTER(_i64)]),
+    "pyves_set_bias_none": (_i, [_vp]),
+    "pyves_set_bias_legendre1d": (_i, [_vp, _i, _i, _d, _d, _dp]),
+    "pyves_set_bias_legendre2d": (_i, [_vp, _i, _i, _dp, _dp]),
+    "pyves_set_bias_mlp": (_i, [_vp, _i, _d, _d, _i, _ip, _i, _dp]),
+    "pyves_set_bias_pathcv": (_i, [_vp, _i, _i, _dp, _dp, _d, _dp, _d]),
+    "pyves_set_bias_harmonic": (_i, [_vp, _i, _d, _d]),
+    "pyves_basis_size": (_i, [_vp, _c.POINTER(_i64)]),
+    "pyves_set_state": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pyves_get_state": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pyves_init_positions_mc": (_i, [_vp, _dp, _d, _i, _c.POINTER(_i64), _vp]),
+    "pyves_init_velocities": (_i, [_vp, _vp]),
+    "pyves_step": (_i, [_vp, _i64, _vp, _vp]),
+    "pyves_step_record": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "pyves_eval_bias": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
+    "pyves_energies": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pyves_moments": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
+    "pyves_set_tuning": (_i, [_vp, _i]),
+    "pyves_fp32_fma_peak": (_i, [_i, _dp]),
+    "pyves_launch_count": (_i64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "pyves_b200: %s is missing; build it with `python pyves_b200/csrc/build.py` "
+                "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _darr(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return a, a.ctypes.data_as(_dp)
+
+
+def _raise(code, handle):
+    msg = load().pyves_last_error(handle)
+    msg = msg.decode() if msg else "pyves_b200 error %d" % code
+    if code == EINVAL:
+        raise ValueError(msg)
+    if code == EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    if code == ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def launch_count():
+    return int(load().pyves_launch_count())
+
+
+def fp32_fma_peak(device=0):
+    out = _d(0.0)
+    rc = load().pyves_fp32_fma_peak(device, ctypes.byref(out))
+    if rc:
+        _raise(rc, None)
+    return out.value
+
+
+def _ptr(t):
+    """Raw address of a torch tensor / numpy array / None / int."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Ensemble:
+    """One ensemble of walkers on one GPU (one ``pyves_t`` handle)."""
+
+    def __init__(self, n_walkers, dims=2, seed=0, precision="fp32", device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyves_b200 needs a CUDA device; there is no CPU fallback")
+        self.lib = load()
+        self.n = int(n_walkers)
+        self.dims = int(dims)
+        self.precision = {"fp32": F32, "fp64": F64, F32: F32, F64: F64}[precision]
+        self.device = int(device)
+        self.torch_dtype = torch.float64 if self.precision == F64 else torch.float32
+        self.np_dtype = np.float64 if self.precision == F64 else np.float32
+        self.h = _vp()
+        rc = self.lib.pyves_create(ctypes.byref(self.h), self.device, self.n, self.dims, int(seed) & (2 ** 64 - 1),
+                                   self.precision)
+        if rc:
+            self.h = _vp()
+            _raise(rc, None)
+
+    # -------------------------------------------------------------------------------------- plumbing
+    def _ck(self, rc):
+        if rc:
+            _raise(rc, self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pyves_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return _stream(self.device)
+
+    def _check(self, t, shape=None, dtype=None):
+        """A caller tensor must be contiguous, on this device, of the handle's dtype."""
+        import torch
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device:
+            raise ValueError("expected a CUDA tensor on device %d" % self.device)
+        if not t.is_contiguous():
+            raise ValueError("expected a contiguous tensor")
+        if t.dtype != (dtype or self.torch_dtype):
+            raise ValueError("expected dtype %s" % (dtype or self.torch_dtype))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
+        return t
+
+    # ---------------------------------------------------------------------------------- configuration
+    def set_integrator(self, mass, kT, friction, dt, scheme="openmm_langevin"):
+        self._ck(self.lib.pyves_set_integrator(self.h, mass, kT, friction, dt, SCHEMES.get(scheme, scheme)))
+
+    def set_potential(self, kind, params=()):
+        a, p = _darr(params)
+        self._ck(self.lib.pyves_set_potential(self.h, kind, p if a.size else None, a.size))
+
+    def set_walker_offset(self, gid0):
+        self._ck(self.lib.pyves_set_walker_offset(self.h, gid0))
+
+    @property
+    def step_counter(self):
+        out = _i64(0)
+        self._ck(self.lib.pyves_get_step_counter(self.h, ctypes.byref(out)))
+        return out.value
+
+    @step_counter.setter
+    def step_counter(self, v):
+        self._ck(self.lib.pyves_set_step_counter(self.h, v))
+
+    def set_tuning(self, variant):
+        self._ck(self.lib.pyves_set_tuning(self.h, variant))
+
+    def set_bias_none(self):
+        self._ck(self.lib.pyves_set_bias_none(self.h))
+
+    def set_bias_legendre1d(self, axis, degree, lo, hi, w):
+        a, p = _darr(w)
+        if a.size != degree + 1:
+            raise ValueError("weights must have degree + 1 entries")
+        self._ck(self.lib.pyves_set_bias_legendre1d(self.h, axis, degree, lo, hi, p))
+
+    def set_bias_legendre2d(self, deg_x, deg_y, minmax, w):
+        a, p = _darr(w)
+        if a.size != (deg_x + 1) * (deg_y + 1):
+            raise ValueError("weights must have (deg_x + 1) * (deg_y + 1) entries")
+        m, mp = _darr(minmax)
+        self._ck(self.lib.pyves_set_bias_legendre2d(self.h, deg_x, deg_y, mp, p))
+
+    def set_bias_mlp(self, axis, lo, hi, sizes, act, theta):
+        a, p = _darr(theta)
+        s = np.ascontiguousarray(np.asarray(sizes, dtype=np.int32))
+        dims = [1] + [int(v) for v in s] + [1]
+        if len(s) and a.size != sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)):
+            raise ValueError("parameter vector does not match the layer sizes")
+        self._ck(self.lib.pyves_set_bias_mlp(self.h, axis, lo, hi, len(s), s.ctypes.data_as(_ip), act, p))
+
+    def set_bias_pathcv(self, degree, x_i, y_i, lam, w, phi=0.0):
+        xa, xp = _darr(x_i)
+        ya, yp = _darr(y_i)
+        wa, wp = _darr(w)
+        if xa.size != ya.size:
+            raise ValueError("x_i and y_i must have the same length")
+        if wa.size != degree + 1:
+            raise ValueError("weights must have degree + 1 entries")
+        self._ck(self.lib.pyves_set_bias_pathcv(self.h, degree, xa.size, xp, yp, lam, wp, phi))
+
+    def set_bias_harmonic(self, axis, k, s0):
+        self._ck(self.lib.pyves_set_bias_harmonic(self.h, axis, k, s0))
+
+    @property
+    def basis_size(self):
+        out = _i64(0)
+        self._ck(self.lib.pyves_basis_size(self.h, ctypes.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------------------------------------ state
+    def set_state(self, pos=None, vel=None):
+        """SoA arrays [dims, n]: CUDA tensors (device copy) or numpy arrays (host copy)."""
+        host = isinstance(pos if pos is not None else vel, np.ndarray)
+        keep = []
+        for t in (pos, vel):
+            if t is None:
+                keep.append(None)
+            elif host:
+                keep.append(np.ascontiguousarray(t, dtype=self.np_dtype).reshape(self.dims, self.n))
+            else:
+                keep.append(self._check(t, (self.dims, self.n)))
+        self._ck(self.lib.pyves_set_state(self.h, _ptr(keep[0]), _ptr(keep[1]), int(host), self.stream))
+
+    def get_state(self, host=False, out=None):
+        import torch
+        if out is not None:
+            pos, vel = out
+        elif host:
+            pos = np.empty((self.dims, self.n), dtype=self.np_dtype)
+            vel = np.empty((self.dims, self.n), dtype=self.np_dtype)
+        else:
+            pos = torch.empty((self.dims, self.n), dtype=self.torch_dtype, device="cuda:%d" % self.device)
+            vel = torch.empty_like(pos)
+        host = isinstance(pos, np.ndarray)
+        self._ck(self.lib.pyves_get_state(self.h, _ptr(pos), _ptr(vel), int(host), self.stream))
+        return pos, vel
+
+    def init_positions_mc(self, box, beta, ntrials=100):
+        b, bp = _darr(box)
+        nf = _i64(0)
+        self._ck(self.lib.pyves_init_positions_mc(self.h, bp, beta, ntrials, ctypes.byref(nf), self.stream))
+        return nf.value
+
+    def init_velocities(self):
+        self._ck(self.lib.pyves_init_velocities(self.h, self.stream))
+
+    # --------------------------------------------------------------------------------------- hot path
+    def step(self, nsteps, noise=None):
+        if noise is not None:
+            self._check(noise, (nsteps, self.dims, self.n))
+        self._ck(self.lib.pyves_step(self.h, nsteps, _ptr(noise), self.stream))
+
+    def step_record(self, nsteps, every=1, n_rec=1, noise=None):
+        import torch
+        if noise is not None:
+            self._check(noise, (nsteps, self.dims, self.n))
+        nframes = (nsteps + every - 1) // every
+        traj = torch.empty((nframes, self.dims, n_rec), dtype=self.torch_dtype, device="cuda:%d" % self.device)
+        self._ck(self.lib.pyves_step_record(self.h, nsteps, every, n_rec, _ptr(traj), _ptr(noise), self.stream))
+        return traj
+
+    def eval_bias(self, pos, want_energy=True, want_force=True):
+        """pos [n, ncols] -> (E [n], F [n, ncols]); torch CUDA tensors or numpy (host staging)."""
+        import torch
+        host = isinstance(pos, np.ndarray)
+        if host:
+            pos = np.ascontiguousarray(pos, dtype=self.np_dtype)
+            n, ncols = pos.shape
+            E = np.empty(n, dtype=self.np_dtype) if want_energy else None
+            F = np.empty((n, ncols), dtype=self.np_dtype) if want_force else None
+        else:
+            self._check(pos)
+            n, ncols = pos.shape
+            E = torch.empty(n, dtype=self.torch_dtype, device=pos.device) if want_energy else None
+            F = torch.empty((n, ncols), dtype=self.torch_dtype, device=pos.device) if want_force else None
+        self._ck(self.lib.pyves_eval_bias(self.h, _ptr(pos), n, ncols, _ptr(E), _ptr(F), int(host), self.stream))
+        return E, F
+
+    def energies(self, host=False):
+        import torch
+        if host:
+            PE = np.empty(self.n, dtype=self.np_dtype)
+            KE = np.empty(self.n, dtype=self.np_dtype)
+        else:
+            PE = torch.empty(self.n, dtype=self.torch_dtype, device="cuda:%d" % self.device)
+            KE = torch.empty_like(PE)
+        self._ck(self.lib.pyves_energies(self.h, _ptr(PE), _ptr(KE), int(host), self.stream))
+        return PE, KE
+
+    def moments(self, pos=None, row_weights=None, cov=False, host=False):
+        """(sum_w, sum_wf [K], sum_wff [K, K] or None) of the walkers (pos None) or of rows pos [n, ncols]."""
+        import torch
+        K = self.basis_size
+        n, ncols = (0, 0) if pos is None else pos.shape
+        if pos is not None and isinstance(pos, np.ndarray):
+            host = True
+            pos = np.ascontiguousarray(pos, dtype=self.np_dtype)
+        if row_weights is not None and isinstance(row_weights, np.ndarray):
+            host = True
+            row_weights = np.ascontiguousarray(row_weights, dtype=self.np_dtype)
+        if host:
+            sw = np.zeros(1)
+            sf = np.zeros(K)
+            sff = np.zeros((K, K)) if cov else None
+        else:
+            dev = "cuda:%d" % self.device
+            if pos is not None:
+                self._check(pos)
+            if row_weights is not None:
+                self._check(row_weights)
+            sw = torch.zeros(1, dtype=torch.float64, device=dev)
+            sf = torch.zeros(K, dtype=torch.float64, device=dev)
+            sff = torch.zeros((K, K), dtype=torch.float64, device=dev) if cov else None
+        self._ck(self.lib.pyves_moments(self.h, _ptr(pos), n, ncols, _ptr(row_weights), _ptr(sw), _ptr(sf), _ptr(sff),
+                                        int(host), self.stream))
+        return sw, sf, sff
+
+    def histogram(self, ranges, nbins, axis=0, pos=None, row_weights=None, counts=None, host=False):
+        """1D (nbins int) or 2D (nbins pair) histogram, accumulated into ``counts`` (float64)."""
+        import torch
+        ndim = 1 if np.isscalar(nbins) else 2
+        nb = np.ascontiguousarray(np.atleast_1d(nbins).astype(np.int32))
+        r, rp = _darr(np.ravel(ranges))
+        shape = (int(nb[0]),) if ndim == 1 else (int(nb[0]), int(nb[1]))
+        n, ncols = (0, 0) if pos is None else pos.shape
+        if (pos is not None and isinstance(pos, np.ndarray)) or isinstance(counts, np.ndarray):
+            host = True
+        if counts is None:
+            counts = np.zeros(shape) if host else torch.zeros(shape, dtype=torch.float64, device="cuda:%d" % self.device)
+        if host and pos is not None:
+            pos = np.ascontiguousarray(pos, dtype=self.np_dtype)
+        if host and row_weights is not None:
+            row_weights = np.ascontiguousarray(row_weights, dtype=self.np_dtype)
+        self._ck(self.lib.pyves_histogram(self.h, _ptr(pos), n, ncols, ndim, axis, rp, nb.ctypes.data_as(_ip),
+                                          _ptr(row_weights), _ptr(counts), int(host), self.stream))
+        return counts

@@ -1,0 +1,969 @@
+// C ABI of pyves_b200 (include/pyves_b200.h): handle, parameter upload, kernel dispatch.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "langevin.cuh"
+#include "misc_kernels.cuh"
+#include "moments.cuh"
+
+using namespace pv;
+
+static std::atomic<int64_t> g_launches{0};
+static thread_local std::string g_err;
+
+struct pyves_ctx {
+  int device = 0;
+  int64_t n = 0;
+  int dims = 2;
+  uint64_t seed = 0;
+  int prec = PYVES_F32;
+  size_t esz = 4;
+  void* pos = nullptr;
+  void* vel = nullptr;
+  bool have_int = false, have_pot = false;
+  double mass = 1, kT = 0, friction = 0, dt = 0;
+  int scheme = 0;
+  PotParams<double> pot{};
+  uint64_t gid0 = 0;
+  int64_t step = 0;
+  int bias_kind = PYVES_BIAS_NONE;
+  // Legendre 1D
+  int l1_axis = 0, l1_degree = 0;
+  double l1_lo = -1, l1_hi = 1;
+  double l1_w[kMaxK1] = {0};
+  // Legendre 2D
+  int l2_dx = 0, l2_dy = 0;
+  double l2_mm[4] = {-1, 1, -1, 1};
+  std::vector<double> l2_w;
+  void* l2_w_dev = nullptr;
+  // MLP
+  int mlp_axis = 0, mlp_act = 0;
+  double mlp_lo = 0, mlp_hi = 1;
+  std::vector<int> mlp_sizes;       // hidden widths
+  std::vector<double> mlp_theta;
+  void* mlp_theta_dev = nullptr;
+  void* mlp_packed_dev = nullptr;
+  int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
+  int mlp_width = 0, mlp_linear = 0;
+  double mlp_bout = 0, mlp_u0 = 0;
+  // path CV
+  int pc_degree = 0, pc_npath = 0;
+  double pc_lam = 0, pc_phi = 0;
+  double pc_w[kMaxK1] = {0};
+  void* pc_path_dev = nullptr;
+  // harmonic
+  int h_axis = 0;
+  double h_k = 0, h_s0 = 0;
+  // scratch
+  double* scratch = nullptr;
+  size_t scratch_doubles = 0;
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  unsigned long long* fail_dev = nullptr;
+  int variant = -1;
+  std::string err;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int fail(pyves_ctx* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(h, PYVES_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+  } while (0)
+
+int ensure_scratch(pyves_ctx* h, size_t doubles) {
+  if (doubles <= h->scratch_doubles) return PYVES_OK;
+  if (h->scratch) cudaFree(h->scratch);
+  h->scratch = nullptr;
+  h->scratch_doubles = 0;
+  CU(cudaMalloc(&h->scratch, doubles * sizeof(double)));
+  h->scratch_doubles = doubles;
+  return PYVES_OK;
+}
+
+int ensure_stage(pyves_ctx* h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return PYVES_OK;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  CU(cudaMalloc(&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return PYVES_OK;
+}
+
+// upload a double host array as the handle's element type
+int upload(pyves_ctx* h, void** dev, const double* src, size_t count) {
+  if (*dev) cudaFree(*dev);
+  *dev = nullptr;
+  if (count == 0) return PYVES_OK;
+  CU(cudaMalloc(dev, count * h->esz));
+  if (h->prec == PYVES_F64) {
+    CU(cudaMemcpy(*dev, src, count * sizeof(double), cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> tmp(count);
+    for (size_t i = 0; i < count; ++i) tmp[i] = (float)src[i];
+    CU(cudaMemcpy(*dev, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return PYVES_OK;
+}
+
+template <typename T> PotParams<T> pot_params(const pyves_ctx* h) {
+  PotParams<T> P;
+  P.kind = h->pot.kind;
+  for (int i = 0; i < 11; ++i) P.p[i] = (T)h->pot.p[i];
+  return P;
+}
+
+template <typename T> IntegratorParams<T> integrator_params(const pyves_ctx* h) {
+  const double a = std::exp(-h->friction * h->dt);
+  const double b = h->friction != 0.0 ? (1.0 - a) / h->friction : h->dt;
+  const double c = std::sqrt(h->kT * (1.0 - a * a));
+  IntegratorParams<T> I;
+  I.a = (T)a;
+  I.b_over_m = (T)(b / h->mass);
+  I.c_over_sqrtm = (T)(c / std::sqrt(h->mass));
+  I.dt = (T)h->dt;
+  I.dt_over_m = (T)(h->dt / h->mass);
+  I.scheme = h->scheme;
+  return I;
+}
+
+template <typename T> Legendre1DParams<T> l1_params(const pyves_ctx* h) {
+  Legendre1DParams<T> P;
+  P.axis = h->l1_axis;
+  P.degree = h->l1_degree;
+  P.centre = (T)((h->l1_lo + h->l1_hi) / 2);
+  P.inv_half = (T)(1.0 / ((h->l1_hi - h->l1_lo) / 2));
+  for (int i = 0; i < kMaxK1; ++i) P.w[i] = (T)h->l1_w[i];
+  return P;
+}
+
+template <typename T> Legendre2DSmemParams<T> l2_params(const pyves_ctx* h) {
+  Legendre2DSmemParams<T> P;
+  P.cx = (T)((h->l2_mm[0] + h->l2_mm[1]) / 2);
+  P.ihx = (T)(1.0 / ((h->l2_mm[1] - h->l2_mm[0]) / 2));
+  P.cy = (T)((h->l2_mm[2] + h->l2_mm[3]) / 2);
+  P.ihy = (T)(1.0 / ((h->l2_mm[3] - h->l2_mm[2]) / 2));
+  P.kx = h->l2_dx + 1;
+  P.ky = h->l2_dy + 1;
+  P.w = static_cast<const T*>(h->l2_w_dev);
+  return P;
+}
+
+template <typename T, int KX, int KY> Legendre2DStaticParams<T, KX, KY> l2_static_params(const pyves_ctx* h) {
+  const Legendre2DSmemParams<T> S = l2_params<T>(h);
+  Legendre2DStaticParams<T, KX, KY> P;
+  P.cx = S.cx;
+  P.ihx = S.ihx;
+  P.cy = S.cy;
+  P.ihy = S.ihy;
+  for (int i = 0; i < KX * KY; ++i) P.w[i] = (T)h->l2_w[i];
+  return P;
+}
+
+template <typename T> MlpParams<T> mlp_params(const pyves_ctx* h) {
+  MlpParams<T> P;
+  P.axis = h->mlp_axis;
+  P.linear = h->mlp_linear;
+  P.width = h->mlp_width;
+  P.lo = (T)h->mlp_lo;
+  P.inv_range = (T)(1.0 / (h->mlp_hi - h->mlp_lo));
+  P.bout = (T)h->mlp_bout;
+  P.u0 = (T)h->mlp_u0;
+  P.packed = static_cast<const T*>(h->mlp_packed_dev);
+  return P;
+}
+
+template <typename T> OtherParams<T> other_params(const pyves_ctx* h) {
+  OtherParams<T> P;
+  std::memset(&P, 0, sizeof(P));
+  P.kind = h->bias_kind;
+  if (h->bias_kind == PYVES_BIAS_PATHCV) {
+    P.degree = h->pc_degree;
+    P.npath = h->pc_npath;
+    P.lam = (T)h->pc_lam;
+    P.phi = (T)h->pc_phi;
+    for (int i = 0; i < kMaxK1; ++i) P.w[i] = (T)h->pc_w[i];
+    P.path = static_cast<const T*>(h->pc_path_dev);
+  } else if (h->bias_kind == PYVES_BIAS_HARMONIC) {
+    P.axis = h->h_axis;
+    P.k = (T)h->h_k;
+    P.s0 = (T)h->h_s0;
+  } else if (h->bias_kind == PYVES_BIAS_MLP_1D) {
+    P.axis = h->mlp_axis;
+    P.act = h->mlp_act;
+    P.s0 = (T)h->mlp_lo;
+    P.k = (T)(1.0 / (h->mlp_hi - h->mlp_lo));
+    P.n_layers = (int)h->mlp_sizes.size() + 1;
+    P.sizes[0] = 1;
+    for (size_t i = 0; i < h->mlp_sizes.size(); ++i) P.sizes[i + 1] = h->mlp_sizes[i];
+    P.sizes[h->mlp_sizes.size() + 1] = 1;
+    P.theta = static_cast<const T*>(h->mlp_theta_dev);
+  }
+  return P;
+}
+
+template <typename T> BiasAnyParams<T> any_params(const pyves_ctx* h) {
+  BiasAnyParams<T> P;
+  std::memset(&P, 0, sizeof(P));
+  P.kind = h->bias_kind;
+  if (h->bias_kind == PYVES_BIAS_LEGENDRE_1D) P.l1 = l1_params<T>(h);
+  else if (h->bias_kind == PYVES_BIAS_LEGENDRE_2D) P.l2 = l2_params<T>(h);
+  else if (h->bias_kind != PYVES_BIAS_NONE) P.other = other_params<T>(h);
+  return P;
+}
+
+int64_t basis_size(const pyves_ctx* h) {
+  switch (h->bias_kind) {
+    case PYVES_BIAS_LEGENDRE_1D: return h->l1_degree + 1;
+    case PYVES_BIAS_LEGENDRE_2D: return (int64_t)(h->l2_dx + 1) * (h->l2_dy + 1);
+    case PYVES_BIAS_PATHCV: return h->pc_degree + 1;
+    case PYVES_BIAS_MLP_1D: return (int64_t)h->mlp_theta.size();
+    default: return 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- stepping
+template <typename T, class Pot, class Bias, int WPT, int MINB>
+int run_fast(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP, cudaStream_t st) {
+  CU((launch_langevin2d<T, Pot, Bias, WPT, MINB>(A, integrator_params<T>(h), pot_params<T>(h), BP, make_keys(h->seed), st)));
+  g_launches++;
+  return PYVES_OK;
+}
+
+template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaStream_t st) {
+  if (h->bias_kind == PYVES_BIAS_MLP_1D) {
+    for (int w : h->mlp_sizes)
+      if (w > kGenH) return fail(h, PYVES_EUNSUPPORTED, "MLP hidden width > 128 is not supported");
+  }
+  if (h->dims == 2) {
+    CU((launch_langevin_general<T, 2>(A, integrator_params<T>(h), pot_params<T>(h), any_params<T>(h), make_keys(h->seed), st)));
+  } else {
+    CU((launch_langevin_general<T, 3>(A, integrator_params<T>(h), pot_params<T>(h), any_params<T>(h), make_keys(h->seed), st)));
+  }
+  g_launches++;
+  return PYVES_OK;
+}
+
+template <typename T>
+int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t every, int64_t n_rec, cudaStream_t st) {
+  StepArgs<T> A;
+  A.pos = static_cast<T*>(h->pos);
+  A.vel = static_cast<T*>(h->vel);
+  A.n = h->n;
+  A.gid0 = h->gid0;
+  A.step0 = h->step;
+  A.nsteps = nsteps;
+  A.noise = static_cast<const T*>(noise);
+  A.traj = static_cast<T*>(traj);
+  A.every = every > 0 ? every : 1;
+  A.n_rec = n_rec;
+  const bool fast = h->dims == 2 && h->scheme == PYVES_SCHEME_OPENMM_LANGEVIN && traj == nullptr && h->variant != 99;
+  if (!fast) return run_general<T>(h, A, st);
+  const int pk = h->pot.kind;
+  using DW = PotDoubleWell2D<T>;
+  using SL = PotSlipBond2D<T>;
+  using SB = PotSzaboBerezhkovskii<T>;
+  using GP = PotGeneric<T>;
+  switch (h->bias_kind) {
+    case PYVES_BIAS_NONE: {
+      typename BiasNone<T>::Params BP;
+      if (pk == PYVES_POT_DOUBLE_WELL_2D) return run_fast<T, DW, BiasNone<T>, 2, 1>(h, A, BP, st);
+      if (pk == PYVES_POT_SLIP_BOND_2D) return run_fast<T, SL, BiasNone<T>, 2, 1>(h, A, BP, st);
+      if (pk == PYVES_POT_SZABO_BEREZHKOVSKII) return run_fast<T, SB, BiasNone<T>, 2, 1>(h, A, BP, st);
+      return run_fast<T, GP, BiasNone<T>, 2, 1>(h, A, BP, st);
+    }
+    case PYVES_BIAS_LEGENDRE_1D: {
+      const Legendre1DParams<T> BP = l1_params<T>(h);
+      if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_fast<T, DW, BiasLegendre1D<T, 5>, 2, 1>(h, A, BP, st);
+      if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_fast<T, SL, BiasLegendre1D<T, 12>, 2, 1>(h, A, BP, st);
+      return run_fast<T, GP, BiasLegendre1D<T, 0>, 2, 1>(h, A, BP, st);
+    }
+    case PYVES_BIAS_LEGENDRE_2D: {
+      const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
+      const Legendre2DSmemParams<T> BP = l2_params<T>(h);
+      if (pk == PYVES_POT_DOUBLE_WELL_2D) {
+        if (kx == 8 && ky == 8)
+          return run_fast<T, DW, BiasLegendre2DStatic<T, 8, 8>, 2, 1>(h, A, l2_static_params<T, 8, 8>(h), st);
+        if (kx == 16 && ky == 16) {
+          switch (h->variant) {
+            case 1: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 3>(h, A, l2_static_params<T, 16, 16>(h), st);
+            case 2: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 2, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
+            case 3: return run_fast<T, DW, BiasLegendre2DSmem<T, 16>, 1, 1>(h, A, BP, st);
+            case 4: return run_fast<T, DW, BiasLegendre2DSmem<T, 16>, 2, 1>(h, A, BP, st);
+            default: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
+          }
+        }
+        if (ky > 16 && ky <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
+        if (ky > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);
+      }
+      if (ky <= 16) return run_fast<T, GP, BiasLegendre2DSmem<T, 16>, 1, 1>(h, A, BP, st);
+      if (ky <= 32) return run_fast<T, GP, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
+      return run_fast<T, GP, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);
+    }
+    case PYVES_BIAS_MLP_1D: {
+      const MlpParams<T> BP = mlp_params<T>(h);
+      const bool relu = h->mlp_act == PYVES_ACT_RELU;
+      const bool sb = pk == PYVES_POT_SZABO_BEREZHKOVSKII && relu;
+      switch (h->mlp_H) {
+        case 0:
+          if (sb) return run_fast<T, SB, BiasMlp<T, 0, PYVES_ACT_RELU>, 2, 1>(h, A, BP, st);
+          if (relu) return run_fast<T, GP, BiasMlp<T, 0, PYVES_ACT_RELU>, 2, 1>(h, A, BP, st);
+          return run_fast<T, GP, BiasMlp<T, 0, PYVES_ACT_TANH>, 2, 1>(h, A, BP, st);
+        case 32:
+          if (relu) return run_fast<T, GP, BiasMlp<T, 32, PYVES_ACT_RELU>, 1, 1>(h, A, BP, st);
+          return run_fast<T, GP, BiasMlp<T, 32, PYVES_ACT_TANH>, 1, 1>(h, A, BP, st);
+        case 48:
+          if (sb) return run_fast<T, SB, BiasMlp<T, 48, PYVES_ACT_RELU>, 1, 1>(h, A, BP, st);
+          if (relu) return run_fast<T, GP, BiasMlp<T, 48, PYVES_ACT_RELU>, 1, 1>(h, A, BP, st);
+          return run_fast<T, GP, BiasMlp<T, 48, PYVES_ACT_TANH>, 1, 1>(h, A, BP, st);
+        case 64:
+          if (relu) return run_fast<T, GP, BiasMlp<T, 64, PYVES_ACT_RELU>, 1, 1>(h, A, BP, st);
+          return run_fast<T, GP, BiasMlp<T, 64, PYVES_ACT_TANH>, 1, 1>(h, A, BP, st);
+        default: return run_general<T>(h, A, st);
+      }
+    }
+    default: return run_fast<T, GP, BiasOther<T>, 1, 1>(h, A, other_params<T>(h), st);
+  }
+}
+
+bool valid_axis(int axis) { return axis == 0 || axis == 1; }
+
+}  // namespace
+
+template <typename T>
+static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, const void* w, double* sum_w, double* sum_wf, double* sum_wff, cudaStream_t st) {
+  RowSource<T> S;
+  if (pos) {
+    S.pos = static_cast<const T*>(pos);
+    S.n = n;
+    S.stride_row = ncols;
+    S.stride_col = 1;
+    S.ncols = ncols;
+  } else {
+    S.pos = static_cast<const T*>(h->pos);
+    S.n = h->n;
+    S.stride_row = 1;
+    S.stride_col = h->n;
+    S.ncols = h->dims;
+  }
+  S.w = static_cast<const T*>(w);
+  const int64_t K = basis_size(h);
+  int rc = ensure_scratch(h, moments_scratch_doubles(K, sum_wff != nullptr));
+  if (rc) return rc;
+  int launches = 0;
+  if (h->bias_kind == PYVES_BIAS_MLP_1D) {
+    if (sum_wff) return fail(h, PYVES_EUNSUPPORTED, "second moments are not defined for the MLP bias");
+    MlpGradParams<T> M;
+    M.axis = h->mlp_axis;
+    M.act = h->mlp_act;
+    M.n_layers = (int)h->mlp_sizes.size() + 1;
+    M.sizes[0] = 1;
+    for (size_t i = 0; i < h->mlp_sizes.size(); ++i) M.sizes[i + 1] = h->mlp_sizes[i];
+    M.sizes[h->mlp_sizes.size() + 1] = 1;
+    M.lo = (T)h->mlp_lo;
+    M.inv_range = (T)(1.0 / (h->mlp_hi - h->mlp_lo));
+    M.theta = static_cast<const T*>(h->mlp_theta_dev);
+    M.n_params = (int)K;
+    CU(launch_moments_mlp<T>(S, M, sum_w, sum_wf, h->scratch, st, &launches));
+  } else {
+    BasisParams<T> B;
+    std::memset(&B, 0, sizeof(B));
+    B.kind = h->bias_kind;
+    B.kb = 1;
+    if (h->bias_kind == PYVES_BIAS_LEGENDRE_1D) {
+      const Legendre1DParams<T> P = l1_params<T>(h);
+      B.ka = h->l1_degree + 1;
+      B.axis = h->l1_axis;
+      B.ca = P.centre;
+      B.iha = P.inv_half;
+    } else if (h->bias_kind == PYVES_BIAS_LEGENDRE_2D) {
+      const Legendre2DSmemParams<T> P = l2_params<T>(h);
+      B.ka = P.kx;
+      B.kb = P.ky;
+      B.ca = P.cx;
+      B.iha = P.ihx;
+      B.cb = P.cy;
+      B.ihb = P.ihy;
+    } else {
+      B.ka = h->pc_degree + 1;
+      B.npath = h->pc_npath;
+      B.lam = (T)h->pc_lam;
+      B.path = static_cast<const T*>(h->pc_path_dev);
+    }
+    CU(launch_moments_basis<T>(S, B, sum_w, sum_wf, sum_wff, h->scratch, st, &launches));
+  }
+  g_launches += launches;
+  return PYVES_OK;
+}
+
+// =================================================================================================
+extern "C" {
+
+int pyves_abi_version(void) { return PYVES_ABI_VERSION; }
+int64_t pyves_launch_count(void) { return g_launches.load(); }
+
+const char* pyves_last_error(const pyves_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_t seed, int precision) {
+  pyves_ctx* h = nullptr;
+  if (!out) return fail(h, PYVES_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (n_walkers < 1) return fail(h, PYVES_EINVAL, "n_walkers must be >= 1");
+  if (dims != 2 && dims != 3) return fail(h, PYVES_EINVAL, "dims must be 2 or 3");
+  if (precision != PYVES_F32 && precision != PYVES_F64) return fail(h, PYVES_EINVAL, "precision must be PYVES_F32 or PYVES_F64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, PYVES_ECUDA, "no CUDA device available");
+  }
+  if (device < 0 || device >= ndev) return fail(h, PYVES_EINVAL, "invalid device ordinal");
+  h = new (std::nothrow) pyves_ctx();
+  if (!h) return fail(nullptr, PYVES_ENOMEM, "out of host memory");
+  h->device = device;
+  h->n = n_walkers;
+  h->dims = dims;
+  h->seed = seed;
+  h->prec = precision;
+  h->esz = precision == PYVES_F64 ? 8 : 4;
+  DeviceGuard g(device);
+  const size_t bytes = (size_t)n_walkers * dims * h->esz;
+  cudaError_t e = cudaMalloc(&h->pos, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->vel, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->fail_dev, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->pos, 0, bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->vel, 0, bytes);
+  if (e != cudaSuccess) {
+    const std::string msg = std::string("pyves_create: ") + cudaGetErrorString(e);
+    pyves_destroy(h);
+    return fail(nullptr, e == cudaErrorMemoryAllocation ? PYVES_ENOMEM : PYVES_ECUDA, msg);
+  }
+  *out = h;
+  return PYVES_OK;
+}
+
+int pyves_destroy(pyves_t* h) {
+  if (!h) return PYVES_OK;
+  DeviceGuard g(h->device);
+  void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
+                  h->scratch, h->stage, h->fail_dev};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete h;
+  return PYVES_OK;
+}
+
+int pyves_set_integrator(pyves_t* h, double mass, double kT, double friction, double dt, int scheme) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!(mass > 0) || !(kT >= 0) || !(friction >= 0) || !(dt > 0)) return fail(h, PYVES_EINVAL, "mass, dt must be > 0; kT, friction >= 0");
+  if (scheme != PYVES_SCHEME_OPENMM_LANGEVIN && scheme != PYVES_SCHEME_MIDDLE) return fail(h, PYVES_EINVAL, "unknown integration scheme");
+  h->mass = mass;
+  h->kT = kT;
+  h->friction = friction;
+  h->dt = dt;
+  h->scheme = scheme;
+  h->have_int = true;
+  return PYVES_OK;
+}
+
+int pyves_set_potential(pyves_t* h, int kind, const double* params, int nparams) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  PotParams<double> P;
+  std::memset(&P, 0, sizeof(P));
+  P.kind = kind;
+  auto need = [&](int k) { return params != nullptr && nparams == k; };
+  switch (kind) {
+    case PYVES_POT_SINGLE_WELL_1D:
+    case PYVES_POT_DOUBLE_WELL_1D:
+    case PYVES_POT_SINGLE_WELL_2D:
+    case PYVES_POT_DOUBLE_WELL_2D:
+    case PYVES_POT_MULLER_BROWN:
+      if (nparams != 0) return fail(h, PYVES_EINVAL, "this potential takes no parameters");
+      break;
+    case PYVES_POT_SLIP_BOND_2D:
+    case PYVES_POT_CATCH_BOND_2D: {
+      const int k = kind == PYVES_POT_SLIP_BOND_2D ? 7 : 11;
+      if (!need(k)) return fail(h, PYVES_EINVAL, "slip/catch bond potential needs 7/11 parameters");
+      for (int i = 0; i < k; ++i) P.p[i] = params[i];
+      if (params[3] == 0 || params[6] == 0) return fail(h, PYVES_EINVAL, "y_scale and xy_scale must be non-zero");
+      P.p[3] = 1.0 / params[3];   // kernels multiply by the reciprocal scales
+      P.p[6] = 1.0 / params[6];
+      if (k == 11) {
+        if (params[8] == 0 || params[10] == 0) return fail(h, PYVES_EINVAL, "gx_scale and gy_scale must be non-zero");
+        P.p[8] = 1.0 / params[8];
+        P.p[10] = 1.0 / params[10];
+      }
+    } break;
+    case PYVES_POT_SZABO_BEREZHKOVSKII:
+      if (!need(4)) return fail(h, PYVES_EINVAL, "Szabo-Berezhkovskii potential needs 4 parameters");
+      for (int i = 0; i < 4; ++i) P.p[i] = params[i];
+      break;
+    default: return fail(h, PYVES_EINVAL, "unknown potential kind");
+  }
+  h->pot = P;
+  h->have_pot = true;
+  return PYVES_OK;
+}
+
+int pyves_set_walker_offset(pyves_t* h, int64_t gid0) {
+  if (!h || gid0 < 0) return fail(h, PYVES_EINVAL, "bad walker offset");
+  h->gid0 = (uint64_t)gid0;
+  return PYVES_OK;
+}
+
+int pyves_set_step_counter(pyves_t* h, int64_t step) {
+  if (!h || step < 0) return fail(h, PYVES_EINVAL, "bad step counter");
+  h->step = step;
+  return PYVES_OK;
+}
+
+int pyves_get_step_counter(const pyves_t* h, int64_t* step) {
+  if (!h || !step) return PYVES_EINVAL;
+  *step = h->step;
+  return PYVES_OK;
+}
+
+int pyves_set_tuning(pyves_t* h, int variant) {
+  if (!h) return PYVES_EINVAL;
+  h->variant = variant;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_none(pyves_t* h) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  h->bias_kind = PYVES_BIAS_NONE;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_legendre1d(pyves_t* h, int axis, int degree, double lo, double hi, const double* w) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  if (degree < 0 || degree > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degree must be in [0, 63]");
+  if (!(hi > lo) || !w) return fail(h, PYVES_EINVAL, "need max > min and weights");
+  h->l1_axis = axis;
+  h->l1_degree = degree;
+  h->l1_lo = lo;
+  h->l1_hi = hi;
+  std::memset(h->l1_w, 0, sizeof(h->l1_w));
+  for (int i = 0; i <= degree; ++i) h->l1_w[i] = w[i];
+  h->bias_kind = PYVES_BIAS_LEGENDRE_1D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm, const double* w) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (deg_x < 0 || deg_x > PYVES_MAX_DEGREE || deg_y < 0 || deg_y > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degrees must be in [0, 63]");
+  if (!mm || !w || !(mm[1] > mm[0]) || !(mm[3] > mm[2])) return fail(h, PYVES_EINVAL, "need max > min per axis and weights");
+  DeviceGuard g(h->device);
+  const size_t K = (size_t)(deg_x + 1) * (deg_y + 1);
+  h->l2_dx = deg_x;
+  h->l2_dy = deg_y;
+  std::memcpy(h->l2_mm, mm, sizeof(h->l2_mm));
+  h->l2_w.assign(w, w + K);
+  const int rc = upload(h, &h->l2_w_dev, w, K);
+  if (rc) return rc;
+  h->bias_kind = PYVES_BIAS_LEGENDRE_2D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act, const double* theta) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  if (n_hidden < 1) return fail(h, PYVES_EINVAL, "NNBasis needs at least one hidden layer");
+  if (n_hidden > 8) return fail(h, PYVES_EUNSUPPORTED, "at most 8 hidden layers are supported");
+  if (act != PYVES_ACT_RELU && act != PYVES_ACT_TANH) return fail(h, PYVES_EUNSUPPORTED, "activation must be ReLU or Tanh");
+  if (!sizes || !theta || hi == lo) return fail(h, PYVES_EINVAL, "need sizes, parameters and max != min");
+  for (int i = 0; i < n_hidden; ++i)
+    if (sizes[i] < 1) return fail(h, PYVES_EINVAL, "hidden layer sizes must be >= 1");
+  DeviceGuard g(h->device);
+  std::vector<int> dims(1, 1);
+  dims.insert(dims.end(), sizes, sizes + n_hidden);
+  dims.push_back(1);
+  size_t np = 0;
+  std::vector<size_t> woff, boff;
+  for (size_t l = 0; l + 1 < dims.size(); ++l) {
+    woff.push_back(np);
+    np += (size_t)dims[l] * dims[l + 1];
+    boff.push_back(np);
+    np += dims[l + 1];
+  }
+  h->mlp_axis = axis;
+  h->mlp_act = act;
+  h->mlp_lo = lo;
+  h->mlp_hi = hi;
+  h->mlp_sizes.assign(sizes, sizes + n_hidden);
+  h->mlp_theta.assign(theta, theta + np);
+  int rc = upload(h, &h->mlp_theta_dev, theta, np);
+  if (rc) return rc;
+  // fold the activation-free pair Linear(1,h0) -> Linear(h0,h1)  (ves/basis.py:197-202)
+  const int L = n_hidden;
+  h->mlp_linear = 0;
+  h->mlp_H = -1;
+  h->mlp_width = 0;
+  const double* W0 = theta + woff[0];
+  const double* b0 = theta + boff[0];
+  std::vector<double> packed;
+  if (L == 1) {
+    const double* Wo = theta + woff[1];
+    double u0 = 0, bo = theta[boff[1]];
+    for (int j = 0; j < dims[1]; ++j) {
+      u0 += Wo[j] * W0[j];
+      bo += Wo[j] * b0[j];
+    }
+    h->mlp_linear = 1;
+    h->mlp_u0 = u0;
+    h->mlp_bout = bo;
+    h->mlp_H = 0;
+  } else if (L == 2 || L == 3) {
+    const int h0 = dims[1], h1 = dims[2];
+    const double* W1 = theta + woff[1];
+    const double* b1 = theta + boff[1];
+    std::vector<double> u(h1), c(h1);
+    for (int j = 0; j < h1; ++j) {
+      double su = 0, sc = b1[j];
+      for (int i = 0; i < h0; ++i) {
+        su += W1[j * h0 + i] * W0[i];
+        sc += W1[j * h0 + i] * b0[i];
+      }
+      u[j] = su;
+      c[j] = sc;
+    }
+    if (L == 2) {
+      const int Wp = (h1 + 3) / 4 * 4;
+      packed.assign((size_t)3 * Wp, 0.0);
+      const double* Wo = theta + woff[2];
+      for (int j = 0; j < h1; ++j) {
+        packed[j] = u[j];
+        packed[Wp + j] = c[j];
+        packed[2 * Wp + j] = Wo[j];
+      }
+      h->mlp_bout = theta[boff[2]];
+      h->mlp_width = Wp;
+      h->mlp_H = 0;
+    } else {
+      const int h2 = dims[3];
+      const int m = h1 > h2 ? h1 : h2;
+      const int H = m <= 32 ? 32 : (m <= 48 ? 48 : (m <= 64 ? 64 : -1));
+      if (H > 0) {
+        packed.assign((size_t)4 * H + (size_t)H * H, 0.0);
+        const double* W2 = theta + woff[2];
+        const double* b2 = theta + boff[2];
+        const double* Wo = theta + woff[3];
+        for (int j = 0; j < h1; ++j) {
+          packed[j] = u[j];
+          packed[H + j] = c[j];
+        }
+        for (int j = 0; j < h2; ++j) {
+          packed[2 * H + j] = Wo[j];
+          packed[3 * H + j] = b2[j];
+          for (int i = 0; i < h1; ++i) packed[4 * H + (size_t)j * H + i] = W2[j * h1 + i];
+        }
+        h->mlp_bout = theta[boff[3]];
+        h->mlp_H = H;
+      }
+    }
+  }
+  rc = upload(h, &h->mlp_packed_dev, packed.data(), packed.size());
+  if (rc) return rc;
+  h->bias_kind = PYVES_BIAS_MLP_1D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, const double* y_i, double lam, const double* w, double phi) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (degree < 0 || degree > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degree must be in [0, 63]");
+  if (npath < 1 || npath > PYVES_MAX_PATH) return fail(h, PYVES_EINVAL, "path needs 1..256 images");
+  if (!x_i || !y_i || !w || !(lam > 0)) return fail(h, PYVES_EINVAL, "need path images, weights and lam > 0");
+  DeviceGuard g(h->device);
+  std::vector<double> path(x_i, x_i + npath);
+  path.insert(path.end(), y_i, y_i + npath);
+  const int rc = upload(h, &h->pc_path_dev, path.data(), path.size());
+  if (rc) return rc;
+  h->pc_degree = degree;
+  h->pc_npath = npath;
+  h->pc_lam = lam;
+  h->pc_phi = phi;
+  std::memset(h->pc_w, 0, sizeof(h->pc_w));
+  for (int i = 0; i <= degree; ++i) h->pc_w[i] = w[i];
+  h->bias_kind = PYVES_BIAS_PATHCV;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_harmonic(pyves_t* h, int axis, double k, double s0) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  h->h_axis = axis;
+  h->h_k = k;
+  h->h_s0 = s0;
+  h->bias_kind = PYVES_BIAS_HARMONIC;
+  return PYVES_OK;
+}
+
+int pyves_basis_size(const pyves_t* h, int64_t* K) {
+  if (!h || !K) return PYVES_EINVAL;
+  *K = basis_size(h);
+  return PYVES_OK;
+}
+
+// ------------------------------------------------------------------------------------------ state
+int pyves_set_state(pyves_t* h, const void* pos, const void* vel, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = (size_t)h->n * h->dims * h->esz;
+  const cudaMemcpyKind kind = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (pos) CU(cudaMemcpyAsync(h->pos, pos, bytes, kind, st));
+  if (vel) CU(cudaMemcpyAsync(h->vel, vel, bytes, kind, st));
+  if (on_host) CU(cudaStreamSynchronize(st));
+  return PYVES_OK;
+}
+
+int pyves_get_state(pyves_t* h, void* pos, void* vel, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = (size_t)h->n * h->dims * h->esz;
+  const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (pos) CU(cudaMemcpyAsync(pos, h->pos, bytes, kind, st));
+  if (vel) CU(cudaMemcpyAsync(vel, h->vel, bytes, kind, st));
+  if (on_host) CU(cudaStreamSynchronize(st));
+  return PYVES_OK;
+}
+
+int pyves_init_positions_mc(pyves_t* h, const double* box, double beta, int ntrials, int64_t* n_failed, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!h->have_pot) return fail(h, PYVES_ESTATE, "set_potential must be called first");
+  if (!box || !(box[1] >= box[0]) || !(box[3] >= box[2]) || !(beta > 0) || ntrials < 1) return fail(h, PYVES_EINVAL, "bad placement box / beta / ntrials");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->prec == PYVES_F64) {
+    CU(launch_init_positions<double>(static_cast<double*>(h->pos), h->n, h->dims, h->gid0, box, beta, ntrials, h->pot, make_keys(h->seed), h->fail_dev, st));
+  } else {
+    CU(launch_init_positions<float>(static_cast<float*>(h->pos), h->n, h->dims, h->gid0, box, beta, ntrials, h->pot, make_keys(h->seed), h->fail_dev, st));
+  }
+  g_launches++;
+  unsigned long long nf = 0;
+  CU(cudaMemcpyAsync(&nf, h->fail_dev, sizeof(nf), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_failed) *n_failed = (int64_t)nf;
+  return PYVES_OK;
+}
+
+int pyves_init_velocities(pyves_t* h, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!h->have_int) return fail(h, PYVES_ESTATE, "set_integrator must be called first");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double sigma = std::sqrt(h->kT / h->mass);
+  if (h->prec == PYVES_F64) {
+    CU(launch_init_velocities<double>(static_cast<double*>(h->vel), h->n, h->dims, h->gid0, sigma, make_keys(h->seed), st));
+  } else {
+    CU(launch_init_velocities<float>(static_cast<float*>(h->vel), h->n, h->dims, h->gid0, (float)sigma, make_keys(h->seed), st));
+  }
+  g_launches++;
+  return PYVES_OK;
+}
+
+// --------------------------------------------------------------------------------------- hot path
+int pyves_step_record(pyves_t* h, int64_t nsteps, int64_t every, int64_t n_rec, void* traj_out, const void* injected_noise, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!h->have_int || !h->have_pot) return fail(h, PYVES_ESTATE, "set_integrator and set_potential must be called before stepping");
+  if (nsteps < 0) return fail(h, PYVES_EINVAL, "nsteps must be >= 0");
+  if (traj_out && (every < 1 || n_rec < 1 || n_rec > h->n)) return fail(h, PYVES_EINVAL, "recording needs every >= 1 and 1 <= n_rec <= n_walkers");
+  if (nsteps == 0) return PYVES_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rc = h->prec == PYVES_F64 ? do_step<double>(h, nsteps, injected_noise, traj_out, every, n_rec, st)
+                                      : do_step<float>(h, nsteps, injected_noise, traj_out, every, n_rec, st);
+  if (rc == PYVES_OK) h->step += nsteps;
+  return rc;
+}
+
+int pyves_step(pyves_t* h, int64_t nsteps, const void* injected_noise, void* stream) {
+  return pyves_step_record(h, nsteps, 1, 0, nullptr, injected_noise, stream);
+}
+
+int pyves_eval_bias(pyves_t* h, const void* pos, int64_t n, int ncols, void* E, void* F, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (n < 0 || ncols < 1 || ncols > 3 || (!pos && n > 0)) return fail(h, PYVES_EINVAL, "need positions [n][ncols], ncols in 1..3");
+  if (h->bias_kind == PYVES_BIAS_MLP_1D)
+    for (int w : h->mlp_sizes)
+      if (w > kGenH) return fail(h, PYVES_EUNSUPPORTED, "MLP hidden width > 128 is not supported");
+  if (n == 0) return PYVES_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t pb = (size_t)n * ncols * h->esz, eb = (size_t)n * h->esz;
+  const void* dpos = pos;
+  void *dE = E, *dF = F;
+  if (on_host) {
+    const int rc = ensure_stage(h, 2 * pb + eb);
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->stage);
+    CU(cudaMemcpyAsync(base, pos, pb, cudaMemcpyHostToDevice, st));
+    dpos = base;
+    dF = F ? base + pb : nullptr;
+    dE = E ? base + 2 * pb : nullptr;
+  }
+  if (h->prec == PYVES_F64) {
+    CU(launch_eval_bias<double>(static_cast<const double*>(dpos), n, ncols, static_cast<double*>(dE), static_cast<double*>(dF), any_params<double>(h), st));
+  } else {
+    CU(launch_eval_bias<float>(static_cast<const float*>(dpos), n, ncols, static_cast<float*>(dE), static_cast<float*>(dF), any_params<float>(h), st));
+  }
+  g_launches++;
+  if (on_host) {
+    if (E) CU(cudaMemcpyAsync(E, dE, eb, cudaMemcpyDeviceToHost, st));
+    if (F) CU(cudaMemcpyAsync(F, dF, pb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PYVES_OK;
+}
+
+int pyves_energies(pyves_t* h, void* PE, void* KE, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!h->have_int || !h->have_pot) return fail(h, PYVES_ESTATE, "set_integrator and set_potential must be called first");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t eb = (size_t)h->n * h->esz;
+  void *dPE = PE, *dKE = KE;
+  if (on_host) {
+    const int rc = ensure_stage(h, 2 * eb);
+    if (rc) return rc;
+    dPE = PE ? h->stage : nullptr;
+    dKE = KE ? static_cast<char*>(h->stage) + eb : nullptr;
+  }
+  if (h->prec == PYVES_F64) {
+    CU(launch_energies<double>(static_cast<const double*>(h->pos), static_cast<const double*>(h->vel), h->n, h->dims, static_cast<double*>(dPE), static_cast<double*>(dKE), h->mass, h->dt, pot_params<double>(h), any_params<double>(h), st));
+  } else {
+    CU(launch_energies<float>(static_cast<const float*>(h->pos), static_cast<const float*>(h->vel), h->n, h->dims, static_cast<float*>(dPE), static_cast<float*>(dKE), (float)h->mass, (float)h->dt, pot_params<float>(h), any_params<float>(h), st));
+  }
+  g_launches++;
+  if (on_host) {
+    if (PE) CU(cudaMemcpyAsync(PE, dPE, eb, cudaMemcpyDeviceToHost, st));
+    if (KE) CU(cudaMemcpyAsync(KE, dKE, eb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PYVES_OK;
+}
+
+int pyves_moments(pyves_t* h, const void* pos, int64_t n, int ncols, const void* row_weights, double* sum_w, double* sum_wf, double* sum_wff, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  const int64_t K = basis_size(h);
+  if (K == 0) return fail(h, PYVES_ESTATE, "the current bias has no basis functions / parameters");
+  if (!sum_w || !sum_wf) return fail(h, PYVES_EINVAL, "sum_w and sum_wf are required");
+  if (pos && (n < 0 || ncols < 1 || ncols > 3)) return fail(h, PYVES_EINVAL, "need positions [n][ncols], ncols in 1..3");
+  if (h->bias_kind == PYVES_BIAS_LEGENDRE_2D && pos && ncols < 2) return fail(h, PYVES_EINVAL, "the 2D basis needs at least 2 columns");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nrows = pos ? n : h->n;
+  const void *dpos = pos, *dw = row_weights;
+  double *dsw = sum_w, *dsf = sum_wf, *dsff = sum_wff;
+  if (on_host) {
+    const size_t pb = pos ? (size_t)n * ncols * h->esz : 0, wb = row_weights ? (size_t)nrows * h->esz : 0;
+    const size_t pbp = (pb + 15) / 16 * 16, wbp = (wb + 15) / 16 * 16;
+    const size_t ob = (size_t)(1 + K + (sum_wff ? K * K : 0)) * sizeof(double);
+    const int rc = ensure_stage(h, pbp + wbp + ob);
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->stage);
+    if (pos) {
+      CU(cudaMemcpyAsync(base, pos, pb, cudaMemcpyHostToDevice, st));
+      dpos = base;
+    }
+    if (row_weights) {
+      CU(cudaMemcpyAsync(base + pbp, row_weights, wb, cudaMemcpyHostToDevice, st));
+      dw = base + pbp;
+    }
+    dsw = reinterpret_cast<double*>(base + pbp + wbp);
+    dsf = dsw + 1;
+    dsff = sum_wff ? dsf + K : nullptr;
+  }
+  const int rc = h->prec == PYVES_F64 ? moments_impl<double>(h, dpos, n, ncols, dw, dsw, dsf, dsff, st)
+                                      : moments_impl<float>(h, dpos, n, ncols, dw, dsw, dsf, dsff, st);
+  if (rc) return rc;
+  if (on_host) {
+    CU(cudaMemcpyAsync(sum_w, dsw, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sum_wf, dsf, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+    if (sum_wff) CU(cudaMemcpyAsync(sum_wff, dsff, sizeof(double) * K * K, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PYVES_OK;
+}
+
+int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim, int axis, const double* range, const int* nbins, const void* row_weights, double* counts, int on_host, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if ((ndim != 1 && ndim != 2) || !range || !nbins || !counts) return fail(h, PYVES_EINVAL, "need ndim 1|2, range, nbins, counts");
+  if (ndim == 1 && !valid_axis(axis) && !(axis == 2)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  if (nbins[0] < 1 || (ndim == 2 && nbins[1] < 1) || !(range[1] > range[0]) || (ndim == 2 && !(range[3] > range[2]))) return fail(h, PYVES_EINVAL, "bad bins / range");
+  if (pos && (n < 0 || ncols < 1 || ncols > 3 || (ndim == 2 && ncols < 2) || (ndim == 1 && axis >= ncols))) return fail(h, PYVES_EINVAL, "positions do not have the requested columns");
+  if (!pos && ndim == 1 && axis >= h->dims) return fail(h, PYVES_EINVAL, "Invalid axis");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nrows = pos ? n : h->n;
+  const size_t nb = (size_t)nbins[0] * (ndim == 2 ? nbins[1] : 1);
+  const void *dpos = pos ? pos : h->pos, *dw = row_weights;
+  double* dcounts = counts;
+  if (on_host) {
+    const size_t pb = pos ? (size_t)n * ncols * h->esz : 0, wb = row_weights ? (size_t)nrows * h->esz : 0;
+    const size_t pbp = (pb + 15) / 16 * 16, wbp = (wb + 15) / 16 * 16;
+    const int rc = ensure_stage(h, pbp + wbp + nb * sizeof(double));
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->stage);
+    if (pos) {
+      CU(cudaMemcpyAsync(base, pos, pb, cudaMemcpyHostToDevice, st));
+      dpos = base;
+    }
+    if (row_weights) {
+      CU(cudaMemcpyAsync(base + pbp, row_weights, wb, cudaMemcpyHostToDevice, st));
+      dw = base + pbp;
+    }
+    dcounts = reinterpret_cast<double*>(base + pbp + wbp);
+    CU(cudaMemcpyAsync(dcounts, counts, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  const int64_t srow = pos ? ncols : 1, scol = pos ? 1 : h->n;
+  if (h->prec == PYVES_F64) {
+    CU(launch_histogram<double>(static_cast<const double*>(dpos), nrows, srow, scol, ndim, axis, range, nbins, static_cast<const double*>(dw), dcounts, st));
+  } else {
+    CU(launch_histogram<float>(static_cast<const float*>(dpos), nrows, srow, scol, ndim, axis, range, nbins, static_cast<const float*>(dw), dcounts, st));
+  }
+  g_launches++;
+  if (on_host) {
+    CU(cudaMemcpyAsync(counts, dcounts, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PYVES_OK;
+}
+
+int pyves_fp32_fma_peak(int device, double* tflops) {
+  pyves_ctx* h = nullptr;
+  if (!tflops) return fail(h, PYVES_EINVAL, "tflops is NULL");
+  DeviceGuard g(device);
+  CU(fp32_fma_peak(tflops));
+  g_launches += 5;
+  return PYVES_OK;
+}
+
+}  // extern "C"

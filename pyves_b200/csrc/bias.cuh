@@ -1,0 +1,440 @@
+// Bias energy functions evaluated per walker: energy and gradient w.r.t. (x, y).
+// Replaces the TorchScript module + autograd that openmmtorch.TorchForce runs every step
+// (ves/bias.py:52-58) for the modules of ves/basis.py.  CPU twins: oracle/legendre.py,
+// oracle/mlp.py, oracle/pathcv.py.
+//
+// Functor interface:
+//   Params                       POD passed BY VALUE as a kernel parameter (constant bank)
+//   smem_bytes(P)                dynamic shared memory the functor needs
+//   stage(P, smem)               cooperative fill of shared memory (all threads; caller syncs)
+//   grad<WANT_E>(P, smem, x, y, e, gx, gy)   ACCUMULATES dV/dx, dV/dy (and V when WANT_E)
+#pragma once
+#include "common.cuh"
+
+namespace pv {
+
+// s = (q - centre) * inv_half clamped to [-1, 1]; `inside` is where torch.clamp passes the
+// gradient (inclusive at both ends)  -- ves/basis.py:143,147.
+template <typename T> PV_DEV T scale_clamp(T q, T centre, T inv_half, bool& inside) {
+  const T s = (q - centre) * inv_half;
+  inside = (s >= T(-1)) && (s <= T(1));
+  return Math<T>::min(Math<T>::max(s, T(-1)), T(1));
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct BiasNone {
+  struct Params {};
+  static size_t smem_bytes(const Params&) { return 0; }
+  static PV_DEV void stage(const Params&, void*) {}
+  template <bool WANT_E> static PV_DEV void grad(const Params&, const void*, T, T, T&, T&, T&) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// LegendreBasis1D (ves/basis.py:86-156).  DEG > 0: compile-time degree, recursion fully
+// unrolled, weights are constant-bank operands.  DEG == 0: runtime degree.
+template <typename T> struct Legendre1DParams {
+  int axis;
+  int degree;
+  T centre;
+  T inv_half;
+  T w[kMaxK1];
+};
+
+template <typename T, int DEG> struct BiasLegendre1D {
+  using Params = Legendre1DParams<T>;
+  static size_t smem_bytes(const Params&) { return 0; }
+  static PV_DEV void stage(const Params&, void*) {}
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
+    bool inside;
+    const T s = scale_clamp(P.axis ? y : x, P.centre, P.inv_half, inside);
+    const int deg = DEG > 0 ? DEG : P.degree;
+    T pm = T(1), p = s, dpm = T(0), dp = T(1);
+    T E = P.w[0], g = T(0);
+    if (deg >= 1) {
+      E = Math<T>::fma(P.w[1], s, E);
+      g = P.w[1];
+    }
+    if (DEG > 0) {
+#pragma unroll
+      for (int n = 1; n < DEG; ++n) {
+        const T pn = leg_a<T>(n) * s * p - leg_b<T>(n) * pm;
+        const T dpn = Math<T>::fma(leg_c<T>(n), p, dpm);
+        g = Math<T>::fma(P.w[n + 1], dpn, g);
+        if (WANT_E) E = Math<T>::fma(P.w[n + 1], pn, E);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+      }
+    } else {
+      for (int n = 1; n < deg; ++n) {
+        const T fn = T(n), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
+        const T pn = (c * s * p - fn * pm) * inv;
+        const T dpn = Math<T>::fma(c, p, dpm);
+        g = Math<T>::fma(P.w[n + 1], dpn, g);
+        if (WANT_E) E = Math<T>::fma(P.w[n + 1], pn, E);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+      }
+    }
+    g = inside ? g * P.inv_half : T(0);
+    gx += P.axis ? T(0) : g;
+    gy += P.axis ? g : T(0);
+    if (WANT_E) e += E;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 2D tensor-product Legendre basis, V = sum_ij w_ij P_i(x') P_j(y')  (per-axis
+// conventions of ves/basis.py:143-147).  Fills Py[0..KY), dPy[0..KY) by recursion.
+template <typename T, int KY> PV_DEV void legendre_fill(T s, T (&P)[KY], T (&dP)[KY]) {
+  P[0] = T(1);
+  dP[0] = T(0);
+  if (KY > 1) {
+    P[1] = s;
+    dP[1] = T(1);
+  }
+#pragma unroll
+  for (int n = 1; n + 1 < KY; ++n) {
+    P[n + 1] = leg_a<T>(n) * s * P[n] - leg_b<T>(n) * P[n - 1];
+    dP[n + 1] = Math<T>::fma(leg_c<T>(n), P[n], dP[n - 1]);
+  }
+}
+
+// Static sizes, weights by value in the constant bank, everything unrolled: the 2 KX KY FMAs
+// of A_i = sum_j w_ij P_j(y'), B_i = sum_j w_ij P'_j(y') take their weight as a c[bank][imm]
+// operand, so no load instruction is issued for them.
+template <typename T, int KX, int KY> struct Legendre2DStaticParams {
+  T cx, ihx, cy, ihy;
+  T w[KX * KY];
+};
+
+template <typename T, int KX, int KY> struct BiasLegendre2DStatic {
+  using Params = Legendre2DStaticParams<T, KX, KY>;
+  static size_t smem_bytes(const Params&) { return 0; }
+  static PV_DEV void stage(const Params&, void*) {}
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    T Py[KY], dPy[KY];
+    legendre_fill<T, KY>(sy, Py, dPy);
+    T ax = T(0), ay = T(0), E = T(0);
+    T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
+#pragma unroll
+    for (int i = 0; i < KX; ++i) {
+      if (i == 1) {
+        px = sx;
+        dpx = T(1);
+      } else if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      T A = P.w[i * KY] * Py[0];
+      T B = T(0);
+#pragma unroll
+      for (int j = 1; j < KY; ++j) {
+        A = Math<T>::fma(P.w[i * KY + j], Py[j], A);
+        B = Math<T>::fma(P.w[i * KY + j], dPy[j], B);
+      }
+      ax = Math<T>::fma(dpx, A, ax);
+      ay = Math<T>::fma(px, B, ay);
+      if (WANT_E) E = Math<T>::fma(px, A, E);
+    }
+    gx += inx ? ax * P.ihx : T(0);
+    gy += iny ? ay * P.ihy : T(0);
+    if (WANT_E) e += E;
+  }
+};
+
+// Runtime sizes (kx, ky <= KYP): weights zero-padded to [kx][KYP] in shared memory, read with
+// 128-bit broadcast loads; the loop over i is a runtime loop with the x recursion on the fly.
+template <typename T> struct Legendre2DSmemParams {
+  T cx, ihx, cy, ihy;
+  int kx, ky;
+  const T* w;   // device, row-major [kx][ky]
+};
+
+template <typename T, int KYP> struct BiasLegendre2DSmem {
+  using Params = Legendre2DSmemParams<T>;
+  static size_t smem_bytes(const Params& P) { return (size_t)P.kx * KYP * sizeof(T); }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    T* w = reinterpret_cast<T*>(smem);
+    for (int idx = threadIdx.x; idx < P.kx * KYP; idx += blockDim.x) {
+      const int i = idx / KYP, j = idx % KYP;
+      w[idx] = j < P.ky ? P.w[i * P.ky + j] : T(0);
+    }
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    constexpr int V = 16 / sizeof(T);   // elements per 128-bit load
+    struct alignas(16) Vec { T v[V]; };
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    T Py[KYP], dPy[KYP];
+    legendre_fill<T, KYP>(sy, Py, dPy);
+    T ax = T(0), ay = T(0), E = T(0);
+    T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
+    const Vec* row = reinterpret_cast<const Vec*>(smem);
+    for (int i = 0; i < P.kx; ++i) {
+      if (i == 1) {
+        px = sx;
+        dpx = T(1);
+      } else if (i >= 2) {
+        const T fn = T(i - 1), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
+        const T pn = (c * sx * px - fn * pxm) * inv;
+        const T dpn = Math<T>::fma(c, px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      T A0 = T(0), A1 = T(0), B0 = T(0), B1 = T(0);
+#pragma unroll
+      for (int jv = 0; jv < KYP / V; ++jv) {
+        const Vec wv = row[jv];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          const int j = jv * V + q;
+          if (q & 1) {
+            A1 = Math<T>::fma(wv.v[q], Py[j], A1);
+            B1 = Math<T>::fma(wv.v[q], dPy[j], B1);
+          } else {
+            A0 = Math<T>::fma(wv.v[q], Py[j], A0);
+            B0 = Math<T>::fma(wv.v[q], dPy[j], B0);
+          }
+        }
+      }
+      row += KYP / V;
+      const T A = A0 + A1, B = B0 + B1;
+      ax = Math<T>::fma(dpx, A, ax);
+      ay = Math<T>::fma(px, B, ay);
+      if (WANT_E) E = Math<T>::fma(px, A, E);
+    }
+    gx += inx ? ax * P.ihx : T(0);
+    gy += iny ? ay * P.ihy : T(0);
+    if (WANT_E) e += E;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// NNBasis1D (ves/basis.py:184-232) in folded form.  The first two Linear layers have no
+// activation between them (:197-202), so the host folds them: z1 = u s + c.  The derivative
+// dV/ds is carried in forward mode next to the value, so each weight read from shared memory
+// feeds two FMAs.
+//   H == 0 : two hidden layers (no matmul left after folding), any width (padded to 4):
+//            streamed, no per-thread arrays.       shared (T): u[W] c[W] wout[W]
+//   H  > 0 : three hidden layers = one H x H matmul, widths padded to H.
+//                                                  shared (T): u[H] c[H] wout[H] b2[H] W2[H][H]
+// A single hidden layer is the reference's degenerate linear case V = u0 s + bout.
+template <typename T> struct MlpParams {
+  int axis;
+  int linear;      // 1: single hidden layer
+  int width;       // padded width of the streamed (H == 0) variant
+  T lo, inv_range;
+  T bout, u0;
+  const T* packed;  // device, layout above
+};
+
+template <typename T, int ACT> PV_DEV T act_fn(T z, T& d) {
+  if (ACT == PYVES_ACT_RELU) {
+    d = z > T(0) ? T(1) : T(0);
+    return Math<T>::max(z, T(0));
+  } else {
+    const T t = Math<T>::tanh(z);
+    d = T(1) - t * t;
+    return t;
+  }
+}
+
+template <typename T, int H, int ACT> struct BiasMlp {
+  using Params = MlpParams<T>;
+  static constexpr int V = 16 / sizeof(T);
+  struct alignas(16) Vec { T v[V]; };
+  static size_t smem_bytes(const Params& P) {
+    if (P.linear) return 0;
+    return (size_t)(H > 0 ? 4 * H + H * H : 3 * P.width) * sizeof(T);
+  }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    if (P.linear) return;
+    T* d = reinterpret_cast<T*>(smem);
+    const int n = H > 0 ? 4 * H + H * H : 3 * P.width;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = P.packed[i];
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    const T s = ((P.axis ? y : x) - P.lo) * P.inv_range;
+    T val = P.bout, dval = T(0);
+    const T* sm = reinterpret_cast<const T*>(smem);
+    if (P.linear) {
+      val = Math<T>::fma(P.u0, s, P.bout);
+      dval = P.u0;
+    } else if (H == 0) {
+      const int nv = P.width / V;
+      const Vec* uv = reinterpret_cast<const Vec*>(sm);
+      const Vec* cv = uv + nv;
+      const Vec* wv = cv + nv;
+      for (int iv = 0; iv < nv; ++iv) {
+        const Vec u = uv[iv], c = cv[iv], w = wv[iv];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          T d;
+          const T a = act_fn<T, ACT>(Math<T>::fma(u.v[q], s, c.v[q]), d);
+          val = Math<T>::fma(w.v[q], a, val);
+          dval = Math<T>::fma(w.v[q] * d, u.v[q], dval);
+        }
+      }
+    } else {
+      constexpr int HH = H > 0 ? H : 4;
+      const Vec* uv = reinterpret_cast<const Vec*>(sm);
+      const Vec* cv = reinterpret_cast<const Vec*>(sm + HH);
+      T h[HH], dh[HH];
+#pragma unroll
+      for (int iv = 0; iv < HH / V; ++iv) {
+        const Vec u = uv[iv], c = cv[iv];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          T d;
+          h[iv * V + q] = act_fn<T, ACT>(Math<T>::fma(u.v[q], s, c.v[q]), d);
+          dh[iv * V + q] = d * u.v[q];
+        }
+      }
+      const T* wout = sm + 2 * HH;
+      const T* b2 = sm + 3 * HH;
+      const Vec* W = reinterpret_cast<const Vec*>(sm + 4 * HH);
+#pragma unroll 2
+      for (int j = 0; j < HH; ++j) {
+        T z0 = b2[j], z1 = T(0), d0 = T(0), d1 = T(0);
+#pragma unroll
+        for (int iv = 0; iv < HH / V; ++iv) {
+          const Vec w = W[j * (HH / V) + iv];
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            if (q & 1) {
+              z1 = Math<T>::fma(w.v[q], h[iv * V + q], z1);
+              d1 = Math<T>::fma(w.v[q], dh[iv * V + q], d1);
+            } else {
+              z0 = Math<T>::fma(w.v[q], h[iv * V + q], z0);
+              d0 = Math<T>::fma(w.v[q], dh[iv * V + q], d0);
+            }
+          }
+        }
+        T d;
+        const T a = act_fn<T, ACT>(z0 + z1, d);
+        const T wo = wout[j];
+        val = Math<T>::fma(wo, a, val);
+        dval = Math<T>::fma(wo * d, d0 + d1, dval);
+      }
+    }
+    const T g = dval * P.inv_range;
+    gx += P.axis ? T(0) : g;
+    gy += P.axis ? g : T(0);
+    if (WANT_E) e += val;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Everything else behind one runtime switch: LegendreBasis2DPathCV (ves/basis.py:509-548),
+// HarmonicBias (ves/bias.py:133), and MLPs of any depth/width up to kGenH (unfolded, layer by
+// layer, activations in local memory).
+constexpr int kGenH = 128;
+
+template <typename T> struct OtherParams {
+  int kind;                  // PYVES_BIAS_PATHCV | PYVES_BIAS_HARMONIC | PYVES_BIAS_MLP_1D
+  // path CV
+  int degree, npath;
+  T lam, phi;
+  T w[kMaxK1];
+  const T* path;             // device: x_i[npath], y_i[npath]
+  // harmonic / mlp
+  int axis, act;
+  T k, s0;                   // harmonic; mlp: lo = s0, inv_range = k
+  int n_layers;              // mlp: number of Linear layers
+  int sizes[10];             // mlp: widths incl. input 1 and output 1
+  const T* theta;            // mlp: device, torch parameter order
+};
+
+template <typename T> struct BiasOther {
+  using Params = OtherParams<T>;
+  static size_t smem_bytes(const Params& P) { return P.kind == PYVES_BIAS_PATHCV ? 2 * (size_t)P.npath * sizeof(T) : 0; }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    if (P.kind == PYVES_BIAS_PATHCV) {
+      T* d = reinterpret_cast<T*>(smem);
+      for (int i = threadIdx.x; i < 2 * P.npath; i += blockDim.x) d[i] = P.path[i];
+    }
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    if (P.kind == PYVES_BIAS_HARMONIC) {
+      const T d = (P.axis ? y : x) - P.s0;
+      gx += P.axis ? T(0) : P.k * d;
+      gy += P.axis ? P.k * d : T(0);
+      if (WANT_E) e += T(0.5) * P.k * d * d;
+    } else if (P.kind == PYVES_BIAS_PATHCV) {
+      const T* xi = reinterpret_cast<const T*>(smem);
+      const T* yi = xi + P.npath;
+      T amax = T(-1e30);
+      for (int i = 0; i < P.npath; ++i) {
+        const T dx = x - xi[i], dy = y - yi[i];
+        amax = Math<T>::max(amax, -P.lam * (dx * dx + dy * dy));
+      }
+      T S0 = 0, S1 = 0, G0x = 0, G0y = 0, G1x = 0, G1y = 0;
+      for (int i = 0; i < P.npath; ++i) {
+        const T dx = x - xi[i], dy = y - yi[i];
+        const T ee = Math<T>::exp(-P.lam * (dx * dx + dy * dy) - amax);
+        const T ei = ee * T(i + 1);
+        S0 += ee; S1 += ei;
+        G0x += ee * dx; G0y += ee * dy;
+        G1x += ei * dx; G1y += ei * dy;
+      }
+      const T m2l = T(-2) * P.lam;
+      const T dL0x = m2l * G0x / S0, dL0y = m2l * G0y / S0;
+      const T dL1x = m2l * G1x / S1, dL1y = m2l * G1y / S1;
+      const T s = S1 / (S0 * T(P.npath));
+      bool inside;
+      const T sp = scale_clamp(s, T(0.5), T(2), inside);
+      T pm = T(1), p = sp, dpm = T(0), dp = T(1);
+      T E = P.w[0], g = T(0);
+      if (P.degree >= 1) { E += P.w[1] * sp; g = P.w[1]; }
+      for (int n = 1; n < P.degree; ++n) {
+        const T fn = T(n), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
+        const T pn = (c * sp * p - fn * pm) * inv;
+        const T dpn = Math<T>::fma(c, p, dpm);
+        g = Math<T>::fma(P.w[n + 1], dpn, g);
+        E = Math<T>::fma(P.w[n + 1], pn, E);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+      }
+      g = inside ? T(2) * g : T(0);
+      const T il = T(1) / P.lam;
+      gx += g * s * (dL1x - dL0x) - P.phi * dL0x * il;
+      gy += g * s * (dL1y - dL0y) - P.phi * dL0y * il;
+      if (WANT_E) e += E - P.phi * (amax + Math<T>::log(S0)) * il;
+    } else if (P.kind == PYVES_BIAS_MLP_1D) {
+      const T s = ((P.axis ? y : x) - P.s0) * P.k;
+      T h[kGenH], dh[kGenH], hn[kGenH], dhn[kGenH];
+      h[0] = s;
+      dh[0] = T(1);
+      const T* th = P.theta;
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int nin = P.sizes[l], nout = P.sizes[l + 1];
+        const T* W = th;
+        const T* b = th + nin * nout;
+        th = b + nout;
+        const bool activate = (l >= 1) && (l < P.n_layers - 1);   // ves/basis.py:197-205
+        for (int j = 0; j < nout; ++j) {
+          T z = b[j], dz = T(0);
+          for (int i = 0; i < nin; ++i) {
+            z = Math<T>::fma(W[j * nin + i], h[i], z);
+            dz = Math<T>::fma(W[j * nin + i], dh[i], dz);
+          }
+          if (activate) {
+            T d;
+            z = P.act == PYVES_ACT_RELU ? act_fn<T, PYVES_ACT_RELU>(z, d) : act_fn<T, PYVES_ACT_TANH>(z, d);
+            dz *= d;
+          }
+          hn[j] = z;
+          dhn[j] = dz;
+        }
+        for (int j = 0; j < nout; ++j) { h[j] = hn[j]; dh[j] = dhn[j]; }
+      }
+      const T g = dh[0] * P.k;
+      gx += P.axis ? T(0) : g;
+      gy += P.axis ? g : T(0);
+      if (WANT_E) e += h[0];
+    }
+  }
+};
+
+}  // namespace pv

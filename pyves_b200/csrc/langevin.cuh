@@ -1,0 +1,265 @@
+// Fused Langevin step kernels: potential force + bias force + Philox noise + integrator update
+// for `nsteps` consecutive steps per launch with the walker state held in registers.
+// Replaces the per-step round trip integrator.step(1) -> CustomExternalForce + TorchForce ->
+// LangevinIntegrator kernels of ves/langevin_dynamics.py:188 (OpenMM update restated in
+// SURVEY Appendix A.1; CPU twin oracle/langevin.py).
+#pragma once
+#include "bias.cuh"
+#include "philox.cuh"
+#include "potentials.cuh"
+
+namespace pv {
+
+constexpr int kStepThreads = 128;
+
+template <typename T> struct IntegratorParams {
+  T a;              // exp(-gamma dt)
+  T b_over_m;       // (1 - a) / gamma / m
+  T c_over_sqrtm;   // sqrt(kT (1 - a^2) / m)
+  T dt;
+  T dt_over_m;      // middle scheme
+  int scheme;
+};
+
+template <typename T> struct StepArgs {
+  T* pos;           // SoA [dims][n]
+  T* vel;
+  int64_t n;        // walkers on this GPU
+  uint64_t gid0;    // global id of local walker 0
+  int64_t step0;    // global index of the first step of this launch
+  int64_t nsteps;
+  const T* noise;   // NULL (Philox) or injected N(0,1) draws [nsteps][dims][n]
+  // general kernel only
+  T* traj;          // NULL or [n_frames][dims][n_rec]
+  int64_t every, n_rec;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: 2 simulated dimensions, OpenMM Langevin scheme, WPT walkers per thread, at least
+// MINB resident blocks per SM (register cap).  One
+// Philox4x32-10 call yields two Box-Muller pairs = the noise of two consecutive steps.
+template <typename T, class Pot, class Bias, int WPT, int MINB>
+__global__ void __launch_bounds__(kStepThreads, MINB)
+langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotParams<T> PP,
+                  const typename Bias::Params BP, const RngKeys K) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Bias::stage(BP, smem);
+  __syncthreads();
+
+  const int64_t base = (int64_t)blockIdx.x * (kStepThreads * WPT) + threadIdx.x;
+  int64_t w[WPT];
+  bool live[WPT];
+  T x[WPT], y[WPT], vx[WPT], vy[WPT];
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const int64_t idx = base + (int64_t)k * kStepThreads;
+    live[k] = idx < A.n;
+    w[k] = live[k] ? idx : A.n - 1;
+    x[k] = A.pos[w[k]];
+    y[k] = A.pos[A.n + w[k]];
+    vx[k] = A.vel[w[k]];
+    vy[k] = A.vel[A.n + w[k]];
+  }
+
+  auto advance = [&](int k, T zx, T zy) {
+    T gx = T(0), gy = T(0), e = T(0);
+    Pot::template grad<false>(PP, x[k], y[k], e, gx, gy);
+    Bias::template grad<false>(BP, smem, x[k], y[k], e, gx, gy);
+    vx[k] = Math<T>::fma(I.c_over_sqrtm, zx, Math<T>::fma(-I.b_over_m, gx, I.a * vx[k]));
+    vy[k] = Math<T>::fma(I.c_over_sqrtm, zy, Math<T>::fma(-I.b_over_m, gy, I.a * vy[k]));
+    x[k] = Math<T>::fma(I.dt, vx[k], x[k]);
+    y[k] = Math<T>::fma(I.dt, vy[k], y[k]);
+  };
+  // noise of steps 2c and 2c+1 for walker k
+  auto draw = [&](int k, int64_t t_even, T (&z)[4]) {
+    if (A.noise != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t ts = t_even + (q >> 1) - A.step0;
+        z[q] = (ts >= 0 && ts < A.nsteps) ? A.noise[(ts * 2 + (q & 1)) * A.n + w[k]] : T(0);
+      }
+    } else {
+      const uint4 r = philox_call(A.gid0 + (uint64_t)w[k], (uint64_t)(t_even >> 1), kStreamDyn2, K);
+      box_muller(r.x, r.y, z[0], z[1]);
+      box_muller(r.z, r.w, z[2], z[3]);
+    }
+  };
+
+  int64_t t = A.step0;
+  const int64_t end = A.step0 + A.nsteps;
+  if ((t & 1) && t < end) {   // odd head: second half of its Philox call
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      T z[4];
+      draw(k, t - 1, z);
+      advance(k, z[2], z[3]);
+    }
+    ++t;
+  }
+  for (; t + 1 < end; t += 2) {
+    T z[WPT][4];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) draw(k, t, z[k]);
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) advance(k, z[k][0], z[k][1]);
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) advance(k, z[k][2], z[k][3]);
+  }
+  if (t < end) {              // even tail: first half of its Philox call
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      T z[4];
+      draw(k, t, z);
+      advance(k, z[0], z[1]);
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    if (live[k]) {
+      A.pos[w[k]] = x[k];
+      A.pos[A.n + w[k]] = y[k];
+      A.vel[w[k]] = vx[k];
+      A.vel[A.n + w[k]] = vy[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// General path: 2 or 3 dimensions, both schemes, optional trajectory recording, one walker per
+// thread, any potential (PotGeneric) and any bias (BiasAny).  Used for reference-format runs
+// (n_walkers = 1, z simulated, traj.dat) and for the cases the fast table does not cover.
+template <typename T> struct BiasAnyParams {
+  int kind;
+  Legendre1DParams<T> l1;
+  Legendre2DSmemParams<T> l2;
+  OtherParams<T> other;
+};
+
+template <typename T> struct BiasAny {
+  using Params = BiasAnyParams<T>;
+  using L1 = BiasLegendre1D<T, 0>;
+  using L2 = BiasLegendre2DSmem<T, 64>;
+  using Ot = BiasOther<T>;
+  static size_t smem_bytes(const Params& P) {
+    if (P.kind == PYVES_BIAS_LEGENDRE_2D) return L2::smem_bytes(P.l2);
+    if (P.kind == PYVES_BIAS_NONE || P.kind == PYVES_BIAS_LEGENDRE_1D) return 0;
+    return Ot::smem_bytes(P.other);
+  }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    if (P.kind == PYVES_BIAS_LEGENDRE_2D) L2::stage(P.l2, smem);
+    else if (P.kind != PYVES_BIAS_NONE && P.kind != PYVES_BIAS_LEGENDRE_1D) Ot::stage(P.other, smem);
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    switch (P.kind) {
+      case PYVES_BIAS_NONE: break;
+      case PYVES_BIAS_LEGENDRE_1D: L1::template grad<WANT_E>(P.l1, smem, x, y, e, gx, gy); break;
+      case PYVES_BIAS_LEGENDRE_2D: L2::template grad<WANT_E>(P.l2, smem, x, y, e, gx, gy); break;
+      default: Ot::template grad<WANT_E>(P.other, smem, x, y, e, gx, gy); break;
+    }
+  }
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kStepThreads)
+langevin_general_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotParams<T> PP,
+                        const BiasAnyParams<T> BP, const RngKeys K) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BiasAny<T>::stage(BP, smem);
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+  const bool live = idx < A.n;
+  const int64_t w = live ? idx : A.n - 1;
+  T q[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    q[d] = A.pos[d * A.n + w];
+    v[d] = A.vel[d * A.n + w];
+  }
+  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+    const int64_t t = A.step0 + ts;
+    if (A.traj != nullptr && live && w < A.n_rec && ts % A.every == 0) {
+      const int64_t f = ts / A.every;
+#pragma unroll
+      for (int d = 0; d < D; ++d) A.traj[(f * D + d) * A.n_rec + w] = q[d];
+    }
+    T z[4] = {T(0), T(0), T(0), T(0)};
+    if (A.noise != nullptr) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) z[d] = A.noise[(ts * D + d) * A.n + w];
+    } else if (D == 2) {
+      const uint4 r = philox_call(A.gid0 + (uint64_t)w, (uint64_t)(t >> 1), kStreamDyn2, K);
+      if (t & 1) box_muller(r.z, r.w, z[0], z[1]);
+      else box_muller(r.x, r.y, z[0], z[1]);
+    } else {
+      const uint4 r = philox_call(A.gid0 + (uint64_t)w, (uint64_t)t, kStreamDyn3, K);
+      box_muller(r.x, r.y, z[0], z[1]);
+      box_muller(r.z, r.w, z[2], z[3]);
+    }
+    T g[3] = {T(0), T(0), T(0)}, e = T(0);
+    PotGeneric<T>::template grad<false>(PP, q[0], q[1], e, g[0], g[1]);
+    BiasAny<T>::template grad<false>(BP, smem, q[0], q[1], e, g[0], g[1]);
+    if (D == 3) g[2] = T(2000) * q[2];   // 1000 z^2, ves/potentials.py:105
+    if (I.scheme == PYVES_SCHEME_OPENMM_LANGEVIN) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        v[d] = Math<T>::fma(I.c_over_sqrtm, z[d], Math<T>::fma(-I.b_over_m, g[d], I.a * v[d]));
+        q[d] = Math<T>::fma(I.dt, v[d], q[d]);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        v[d] = Math<T>::fma(-I.dt_over_m, g[d], v[d]);
+        q[d] = Math<T>::fma(T(0.5) * I.dt, v[d], q[d]);
+        v[d] = Math<T>::fma(I.c_over_sqrtm, z[d], I.a * v[d]);
+        q[d] = Math<T>::fma(T(0.5) * I.dt, v[d], q[d]);
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      A.pos[d * A.n + w] = q[d];
+      A.vel[d * A.n + w] = v[d];
+    }
+  }
+}
+
+// launchers implemented in the langevin_*.cu translation units
+template <typename T, class Pot, class Bias, int WPT, int MINB>
+cudaError_t launch_langevin2d(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                              const typename Bias::Params& BP, const RngKeys& K, cudaStream_t st);
+template <typename T, int D>
+cudaError_t launch_langevin_general(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                    const BiasAnyParams<T>& BP, const RngKeys& K, cudaStream_t st);
+
+template <typename T, class Pot, class Bias, int WPT, int MINB>
+cudaError_t launch_langevin2d_impl(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                   const typename Bias::Params& BP, const RngKeys& K, cudaStream_t st) {
+  auto kern = langevin2d_kernel<T, Pot, Bias, WPT, MINB>;
+  const size_t sm = Bias::smem_bytes(BP);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  const int64_t per_block = (int64_t)kStepThreads * WPT;
+  const unsigned grid = (unsigned)((A.n + per_block - 1) / per_block);
+  kern<<<grid, kStepThreads, sm, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
+
+template <typename T, int D>
+cudaError_t launch_langevin_general_impl(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                         const BiasAnyParams<T>& BP, const RngKeys& K, cudaStream_t st) {
+  auto kern = langevin_general_kernel<T, D>;
+  const size_t sm = BiasAny<T>::smem_bytes(BP);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned grid = (unsigned)((A.n + kStepThreads - 1) / kStepThreads);
+  kern<<<grid, kStepThreads, sm, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
+
+}  // namespace pv

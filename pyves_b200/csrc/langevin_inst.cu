@@ -1,0 +1,69 @@
+// Explicit instantiations of the step kernels, split into groups so the translation units
+// compile in parallel:  nvcc -DPV_T=float|double -DPV_GROUP=0..3 langevin_inst.cu
+#include "langevin.cuh"
+
+#ifndef PV_T
+#define PV_T float
+#endif
+#ifndef PV_GROUP
+#define PV_GROUP 0
+#endif
+
+namespace pv {
+using T = PV_T;
+
+#define PV_FAST(POT, BIAS, WPT, MINB)                                                                     \
+  template <>                                                                                             \
+  cudaError_t launch_langevin2d<T, POT, BIAS, WPT, MINB>(                                                 \
+      const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,                         \
+      const typename BIAS::Params& BP, const RngKeys& K, cudaStream_t st) {                               \
+    return launch_langevin2d_impl<T, POT, BIAS, WPT, MINB>(A, I, PP, BP, K, st);                          \
+  }
+#define PV_COMMA ,
+
+#if PV_GROUP == 0   // double well: the BASELINE.json headline family
+PV_FAST(PotDoubleWell2D<T>, BiasNone<T>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 3)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 16>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 16>, 2, 1)
+#elif PV_GROUP == 1  // slip bond, Szabo-Berezhkovskii
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 64>, 1, 1)
+PV_FAST(PotSlipBond2D<T>, BiasNone<T>, 2, 1)
+PV_FAST(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12>, 2, 1)
+PV_FAST(PotSzaboBerezhkovskii<T>, BiasNone<T>, 2, 1)
+PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)
+PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_RELU>, 1, 1)
+#elif PV_GROUP == 2  // any potential x each bias family
+PV_FAST(PotGeneric<T>, BiasNone<T>, 2, 1)
+PV_FAST(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 2, 1)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 16>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 64>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasOther<T>, 1, 1)
+#elif PV_GROUP == 3  // any potential x MLP widths; the general kernel
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_TANH>, 2, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 32 PV_COMMA PYVES_ACT_RELU>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_RELU>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 64 PV_COMMA PYVES_ACT_RELU>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 32 PV_COMMA PYVES_ACT_TANH>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_TANH>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 64 PV_COMMA PYVES_ACT_TANH>, 1, 1)
+template <>
+cudaError_t launch_langevin_general<T, 2>(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                          const BiasAnyParams<T>& BP, const RngKeys& K, cudaStream_t st) {
+  return launch_langevin_general_impl<T, 2>(A, I, PP, BP, K, st);
+}
+template <>
+cudaError_t launch_langevin_general<T, 3>(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                          const BiasAnyParams<T>& BP, const RngKeys& K, cudaStream_t st) {
+  return launch_langevin_general_impl<T, 3>(A, I, PP, BP, K, st);
+}
+#endif
+
+}  // namespace pv

@@ -1,0 +1,266 @@
+#include "misc_kernels.cuh"
+
+namespace pv {
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) eval_bias_kernel(const T* __restrict__ pos, int64_t n, int ncols,
+                                                        T* __restrict__ E, T* __restrict__ F,
+                                                        const BiasAnyParams<T> BP) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BiasAny<T>::stage(BP, smem);
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const T x = pos[r * ncols];
+  const T y = ncols > 1 ? pos[r * ncols + 1] : T(0);
+  T e = T(0), gx = T(0), gy = T(0);
+  BiasAny<T>::template grad<true>(BP, smem, x, y, e, gx, gy);
+  if (E != nullptr) E[r] = e;
+  if (F != nullptr) {
+    F[r * ncols] = -gx;
+    if (ncols > 1) F[r * ncols + 1] = -gy;
+    if (ncols > 2) F[r * ncols + 2] = T(0);
+  }
+}
+
+template <typename T>
+cudaError_t launch_eval_bias(const T* pos, int64_t n, int ncols, T* E, T* F, const BiasAnyParams<T>& BP,
+                             cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  auto kern = eval_bias_kernel<T>;
+  const size_t sm = BiasAny<T>::smem_bytes(BP);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<(unsigned)((n + 127) / 128), 128, sm, st>>>(pos, n, ncols, E, F, BP);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) energies_kernel(const T* __restrict__ pos, const T* __restrict__ vel, int64_t n,
+                                                       int dims, T* __restrict__ PE, T* __restrict__ KE, T mass, T dt,
+                                                       const PotParams<T> PP, const BiasAnyParams<T> BP) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BiasAny<T>::stage(BP, smem);
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const T x = pos[r], y = pos[n + r];
+  const T z = dims > 2 ? pos[2 * n + r] : T(0);
+  T e = T(0), g[3] = {T(0), T(0), T(0)};
+  PotGeneric<T>::template grad<true>(PP, x, y, e, g[0], g[1]);
+  BiasAny<T>::template grad<true>(BP, smem, x, y, e, g[0], g[1]);
+  if (dims > 2) {
+    e += T(1000) * z * z;
+    g[2] = T(2000) * z;
+  }
+  T ke = T(0);
+  for (int d = 0; d < dims; ++d) {
+    const T vs = vel[d * n + r] - T(0.5) * dt * g[d] / mass;   // leap-frog half-step shift [UPSTREAM OpenMM]
+    ke += vs * vs;
+  }
+  if (PE != nullptr) PE[r] = e;
+  if (KE != nullptr) KE[r] = T(0.5) * mass * ke;
+}
+
+template <typename T>
+cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,
+                            const PotParams<T>& PP, const BiasAnyParams<T>& BP, cudaStream_t st) {
+  auto kern = energies_kernel<T>;
+  const size_t sm = BiasAny<T>::smem_bytes(BP);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<(unsigned)((n + 127) / 128), 128, sm, st>>>(pos, vel, n, dims, PE, KE, mass, dt, PP, BP);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) init_positions_kernel(T* __restrict__ pos, int64_t n, int dims, uint64_t gid0,
+                                                             double xmin, double xmax, double ymin, double ymax,
+                                                             double beta, int ntrials, const PotParams<double> PP,
+                                                             const RngKeys K, unsigned long long* fail_count) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  // Acceptance is decided in double so that every precision places walkers identically.
+  const double thresh = 0.6931471805599453 / beta;   // exp(-beta U) >= 0.5  <=>  U <= ln 2 / beta
+  double px = 0.0, py = 0.0;
+  bool ok = false;
+  for (int trial = 0; trial < ntrials && !ok; ++trial) {
+    const uint4 o = philox_call(gid0 + (uint64_t)r, (uint64_t)trial, kStreamPos, K);
+    const double tx = xmin + (xmax - xmin) * uniform01(o.x, 0.0);
+    const double ty = ymin + (ymax - ymin) * uniform01(o.y, 0.0);
+    double e = 0.0, gx = 0.0, gy = 0.0;
+    PotGeneric<double>::template grad<true>(PP, tx, ty, e, gx, gy);
+    if (e <= thresh) {
+      px = tx;
+      py = ty;
+      ok = true;
+    }
+  }
+  if (!ok) atomicAdd(fail_count, 1ull);
+  pos[r] = (T)px;
+  pos[n + r] = (T)py;
+  if (dims > 2) pos[2 * n + r] = T(0);
+}
+
+template <typename T>
+cudaError_t launch_init_positions(T* pos, int64_t n, int dims, uint64_t gid0, const double* box, double beta,
+                                  int ntrials, const PotParams<double>& PD, const RngKeys& K,
+                                  unsigned long long* fail_count, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(fail_count, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  init_positions_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pos, n, dims, gid0, box[0], box[1], box[2],
+                                                                        box[3], beta, ntrials, PD, K, fail_count);
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) init_velocities_kernel(T* __restrict__ vel, int64_t n, int dims, uint64_t gid0,
+                                                              T sigma_v, const RngKeys K) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint4 o = philox_call(gid0 + (uint64_t)r, 0ull, kStreamVel, K);
+  T z[4];
+  box_muller(o.x, o.y, z[0], z[1]);
+  box_muller(o.z, o.w, z[2], z[3]);
+  for (int d = 0; d < dims; ++d) vel[d * n + r] = sigma_v * z[d];
+}
+
+template <typename T>
+cudaError_t launch_init_velocities(T* vel, int64_t n, int dims, uint64_t gid0, T sigma_v, const RngKeys& K,
+                                   cudaStream_t st) {
+  init_velocities_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(vel, n, dims, gid0, sigma_v, K);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Histogram: per-block shared-memory bins (float counts) when they fit, flushed with one double
+// atomic per non-empty bin per block; global double atomics otherwise.
+constexpr int kHistSmemBins = 11 * 1024;
+
+__device__ __forceinline__ int hist_bin(double v, double lo, double hi, int nb) {
+  if (!(v >= lo && v <= hi)) return -1;
+  int b = (int)((v - lo) / (hi - lo) * nb);
+  return b >= nb ? nb - 1 : b;   // right edge belongs to the last bin (numpy)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ pos, int64_t n, int64_t stride_row,
+                                                        int64_t stride_col, int ndim, int axis, double lo0, double hi0,
+                                                        double lo1, double hi1, int nb0, int nb1,
+                                                        const T* __restrict__ w, double* __restrict__ counts,
+                                                        int use_smem) {
+  extern __shared__ float bins[];
+  const int nb = nb0 * nb1;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int b;
+    if (ndim == 1) {
+      b = hist_bin((double)pos[r * stride_row + axis * stride_col], lo0, hi0, nb0);
+    } else {
+      const int bx = hist_bin((double)pos[r * stride_row], lo0, hi0, nb0);
+      const int by = hist_bin((double)pos[r * stride_row + stride_col], lo1, hi1, nb1);
+      b = (bx < 0 || by < 0) ? -1 : bx * nb1 + by;
+    }
+    if (b < 0) continue;
+    const float wt = w != nullptr ? (float)w[r] : 1.f;
+    if (use_smem) atomicAdd(&bins[b], wt);
+    else atomicAdd(&counts[b], (double)wt);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+      if (bins[i] != 0.f) atomicAdd(&counts[i], (double)bins[i]);
+  }
+}
+
+template <typename T>
+cudaError_t launch_histogram(const T* pos, int64_t n, int64_t stride_row, int64_t stride_col, int ndim, int axis,
+                             const double* range, const int* nbins, const T* row_weights, double* counts,
+                             cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int nb0 = nbins[0], nb1 = ndim == 2 ? nbins[1] : 1;
+  const int nb = nb0 * nb1;
+  const int use_smem = nb <= kHistSmemBins;
+  int64_t blocks = (n + 255) / 256;
+  // few blocks per SM so that each flush amortises over many rows; float bins stay exact (< 2^24 per block)
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  histogram_kernel<T><<<(unsigned)blocks, 256, use_smem ? nb * sizeof(float) : 0, st>>>(
+      pos, n, stride_row, stride_col, ndim, axis, range[0], range[1], ndim == 2 ? range[2] : 0.0,
+      ndim == 2 ? range[3] : 1.0, nb0, nb1, row_weights, counts, use_smem);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 FMA peak: 16 independent FFMA chains per thread, register operands only.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, float b, float c, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
+}
+
+cudaError_t fp32_fma_peak(double* tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(float));
+  if (e != cudaSuccess) return e;
+  const int iters = 4096, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    fma_peak_kernel<<<blocks, threads>>>(out, 0.999f, 1e-3f, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16 * 8 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+#define PV_INST(T)                                                                                                 \
+  template cudaError_t launch_eval_bias<T>(const T*, int64_t, int, T*, T*, const BiasAnyParams<T>&, cudaStream_t); \
+  template cudaError_t launch_energies<T>(const T*, const T*, int64_t, int, T*, T*, T, T, const PotParams<T>&,     \
+                                          const BiasAnyParams<T>&, cudaStream_t);                                  \
+  template cudaError_t launch_init_positions<T>(T*, int64_t, int, uint64_t, const double*, double, int,            \
+                                                const PotParams<double>&, const RngKeys&, unsigned long long*,     \
+                                                cudaStream_t);                                                     \
+  template cudaError_t launch_init_velocities<T>(T*, int64_t, int, uint64_t, T, const RngKeys&, cudaStream_t);     \
+  template cudaError_t launch_histogram<T>(const T*, int64_t, int64_t, int64_t, int, int, const double*,           \
+                                           const int*, const T*, double*, cudaStream_t);
+PV_INST(float)
+PV_INST(double)
+
+}  // namespace pv

@@ -1,0 +1,37 @@
+// Batched bias evaluation, per-walker energies, ensemble initialisation, histograms and the
+// FP32-FMA peak probe.  Launchers are implemented in misc_kernels.cu for float and double.
+#pragma once
+#include "langevin.cuh"
+
+namespace pv {
+
+// TorchForce evaluation at caller positions pos[n][ncols] (ves/bias.py:58, ves/basis.py:123-156)
+template <typename T>
+cudaError_t launch_eval_bias(const T* pos, int64_t n, int ncols, T* E, T* F, const BiasAnyParams<T>& BP, cudaStream_t st);
+
+// PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
+template <typename T>
+cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,
+                            const PotParams<T>& PP, const BiasAnyParams<T>& BP, cudaStream_t st);
+
+// ves/config_creation.py:56-68 per walker; fail_count (device int64, zeroed by the launcher) counts
+// walkers that were never accepted.
+template <typename T>
+cudaError_t launch_init_positions(T* pos, int64_t n, int dims, uint64_t gid0, const double* box, double beta,
+                                  int ntrials, const PotParams<double>& PD, const RngKeys& K,
+                                  unsigned long long* fail_count, cudaStream_t st);
+
+// ves/langevin_dynamics.py:70-74 setVelocitiesToTemperature
+template <typename T>
+cudaError_t launch_init_velocities(T* vel, int64_t n, int dims, uint64_t gid0, T sigma_v, const RngKeys& K,
+                                   cudaStream_t st);
+
+// ves/visualization.py:475 (np.histogram2d semantics: last bin closed on the right)
+template <typename T>
+cudaError_t launch_histogram(const T* pos, int64_t n, int64_t stride_row, int64_t stride_col, int ndim, int axis,
+                             const double* range, const int* nbins, const T* row_weights, double* counts,
+                             cudaStream_t st);
+
+cudaError_t fp32_fma_peak(double* tflops);
+
+}  // namespace pv

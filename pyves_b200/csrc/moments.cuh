@@ -1,0 +1,49 @@
+// Ensemble moments of the basis functions: sum_w, sum_w f_k, sum_w f_k f_l.
+// Replaces the two Python loops of VESBias_SingleParticle_1D.update (ves/bias.py:219-233:
+// one module call per trajectory frame and per target node, then autograd) and provides the
+// ensemble averages <f_k>_V, <f_k f_l>_V of textbook VES.
+#pragma once
+#include "bias.cuh"
+
+namespace pv {
+
+// rows: element (r, c) at pos[r * stride_row + c * stride_col]
+template <typename T> struct RowSource {
+  const T* pos;
+  int64_t n;
+  int64_t stride_row, stride_col;
+  int ncols;
+  const T* w;   // NULL: all ones
+};
+
+// Product bases f_k = FA_a(sa) FB_b(sb), k = a * kb + b.  1D kinds have kb = 1.
+template <typename T> struct BasisParams {
+  int kind;            // PYVES_BIAS_LEGENDRE_1D | _2D | _PATHCV
+  int ka, kb;
+  int axis;            // 1D: which column feeds factor A
+  T ca, iha, cb, ihb;  // centre / inverse half width per factor
+  int npath;           // path CV
+  T lam;
+  const T* path;       // device x_i[npath], y_i[npath]
+};
+
+template <typename T> struct MlpGradParams {
+  int axis, act, n_layers;
+  int sizes[10];       // widths incl. input 1 and output 1
+  T lo, inv_range;
+  const T* theta;      // device, torch parameter order
+  int n_params;
+};
+
+// scratch must hold moments_scratch_doubles(K, cov) doubles
+size_t moments_scratch_doubles(int64_t K, bool cov);
+
+template <typename T>
+cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B, double* sum_w, double* sum_wf,
+                                 double* sum_wff, double* scratch, cudaStream_t st, int* launches);
+
+template <typename T>
+cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M, double* sum_w, double* sum_wf,
+                               double* scratch, cudaStream_t st, int* launches);
+
+}  // namespace pv

