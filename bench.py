@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- walker-steps/s of the biased-Langevin VES hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 2D double well, 16 x 16 tensor-product Legendre bias on
+[-2.5, 2.5] x [-2, 2], well-tempered target (bias factor 10, 100 x 100 grid, refreshed every 10
+updates), averaged-SGD coefficient update every 500 MD steps, 10^6 walkers per GPU (weak scaling;
+walkers shard by global id, one NCCL allreduce of the 257 basis moments per update).
+
+One bench "step" = one VES iteration = 500 fused Langevin steps of every walker + the moment
+reduction + the coefficient update + the bias re-upload.  ``value`` is measured with the walker state
+resident in HBM; ``e2e`` drives the same iteration through the C ABI with HOST buffers (state uploaded
+from pinned memory and read back every iteration).  ``--impl reference`` times the CPU
+implementation of the same path (the oracle's OpenMP C port: the reference itself is Python + OpenMM,
+and OpenMM is absent from this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KB = 8.31446261815324e-3
+KB_PY = 8.3145e-3
+TEMP = 300.0
+MINMAX = (-2.5, 2.5, -2.0, 2.0)
+FLOPS_PER_WALKER_STEP = {8: 4 * 64 + 4 * 8 + 6 * 14 + 32, 16: 1300, 32: 4628, 64: 17428}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers", type=int, default=1000000, help="walkers per GPU")
+    ap.add_argument("--stride", type=int, default=500, help="MD steps per VES iteration")
+    ap.add_argument("--basis", type=int, default=16, help="Legendre functions per axis")
+    ap.add_argument("--mu", type=float, default=1.0, help="averaged-SGD step size (kJ/mol)")
+    ap.add_argument("--seed", type=int, default=20221019)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockMonitor(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_bias(args, beta):
+    from pyves_b200.basis import LegendreBasis2D
+    from pyves_b200.bias import VESBias_Ensemble
+    from pyves_b200.target import Target_WellTempered_2D
+    d = args.basis - 1
+    basis = LegendreBasis2D(d, d, *MINMAX)                      # w = 0 at start
+    target = Target_WellTempered_2D(100, 100, bias_factor=10.0)
+    return VESBias_Ensemble(basis, target, beta, "averaged_sgd", {"mu": args.mu}, model_loc=None, target_update_every=10)
+
+
+def make_ensemble(args, rank, device):
+    from pyves_b200 import _lib
+    ens = _lib.Ensemble(args.walkers, dims=2, seed=args.seed, precision="fp32", device=device)
+    ens.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
+    ens.set_potential(_lib.POT_DOUBLE_WELL_2D)
+    ens.set_walker_offset(rank * args.walkers)
+    failed = ens.init_positions_mc(MINMAX, 1.0 / (KB_PY * TEMP))
+    assert failed == 0
+    ens.init_velocities()
+    return ens
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pyves_b200 import _lib
+    from pyves_b200.parallel import reduce_moments
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    beta = 1.0 / (KB_PY * TEMP)
+    from pyves_b200.potentials import _Potential
+    _Potential.quiet = True
+    bias = make_bias(args, beta)
+    ens = make_ensemble(args, rank, local)
+    bias.force.apply(ens)
+    K = args.basis * args.basis
+    n_total = args.walkers * world
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    step_events = []
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def iteration(timed):
+        flush.zero_()                                            # evict the 126 MB L2 between iterations
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        ens.step(args.stride)
+        if timed:
+            b.record()
+            step_events.append((a, b))
+        sw, sf, _ = reduce_moments(*ens.moments())               # one NCCL allreduce of 1 + K doubles
+        bias.update_from_moments(sw, sf)                         # host optimiser on K coefficients
+        bias.force.apply(ens)                                    # re-upload the coefficients
+
+    peak = _lib.fp32_fma_peak(local) if rank == 0 else None     # before the timed region
+    for _ in range(args.warmup):
+        iteration(False)
+    torch.cuda.synchronize()
+    barrier()
+    mon = ClockMonitor(local)
+    mon.start()
+    l0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        iteration(True)
+    t1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = mon.result()
+    launches = _lib.launch_count() - l0
+    elapsed = torch.tensor([t0.elapsed_time(t1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed)
+    value = n_total * args.stride * args.steps / elapsed
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hpos = torch.empty((2, args.walkers), dtype=torch.float32).pin_memory().numpy()
+        hvel = torch.empty((2, args.walkers), dtype=torch.float32).pin_memory().numpy()
+        ens.get_state(out=(hpos, hvel))
+
+        def e2e_iteration():
+            ens.set_state(hpos, hvel)                            # H2D of this iteration's inputs
+            ens.step(args.stride)
+            sw, sf, _ = ens.moments(host=True)                   # D2H of the result (moments)
+            ens.get_state(out=(hpos, hvel))                      # D2H of the walker state
+            if world > 1:
+                sw, sf, _ = reduce_moments(torch.from_numpy(sw).to(dev), torch.from_numpy(sf).to(dev))
+            bias.update_from_moments(sw, sf)
+            bias.force.apply(ens)
+
+        e2e_iteration()
+        torch.cuda.synchronize()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_iteration()
+        torch.cuda.synchronize()
+        barrier()
+        w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        state_bytes = 2 * 2 * args.walkers * 4
+        e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
+               "h2d_bytes_per_step": state_bytes + K * 8, "d2h_bytes_per_step": state_bytes + (K + 1) * 8}
+
+    if rank == 0:
+        flops = FLOPS_PER_WALKER_STEP.get(args.basis)
+        roof = None
+        if flops:
+            achieved = args.walkers * args.stride * flops / (kern_ms * 1e-3) * 1e-12
+            roof = {"bound": "fp32-fma (CUDA cores; neither HBM nor tensor bound)", "kernel": "langevin2d_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "FFMA micro-benchmark run in this process (pyves_fp32_fma_peak); nominal 74.4",
+                    "flops_per_walker_step": flops, "kernel_ms": kern_ms,
+                    "kernel_share_of_step": kern_ms * args.steps / (elapsed * 1e3), "traffic": None}
+        out = {"metric": "walker-steps/s (2D double well, Legendre bias)", "value": value, "unit": "walker-steps/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "configs[1]: 2D double well, %dx%d tensor Legendre bias, well-tempered target "
+                                      "(gamma 10, 100x100), averaged SGD update every %d steps, %d walkers per GPU"
+                                      % (args.basis, args.basis, args.stride, args.walkers),
+                          "walkers_total": n_total, "md_steps_per_bench_step": args.stride, "parallelism": "walkers sharded, dp%d" % world,
+                          "l2": "flushed between steps (256 MiB memset); state 16 MB/GPU is read once per 500 MD steps"},
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args, seconds=12.0)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_model(args, seed):
+    from oracle import cport, langevin
+    k = langevin.constants()
+    spec = dict(kind="leg2d", deg_x=args.basis - 1, deg_y=args.basis - 1, minmax=MINMAX,
+                weights=np.zeros((args.basis, args.basis)))
+    return cport, k, spec
+
+
+def cpu_state(n, k, seed):
+    from oracle import langevin, potentials
+    en = lambda x, y: potentials.energy_grad_xy(potentials.DOUBLE_WELL_2D, x, y)[0]
+    pos, ok = langevin.mc_placement(seed, 0, n, en, 1.0 / (KB_PY * TEMP), MINMAX)
+    vel = langevin.maxwell_boltzmann(seed, 0, n, k, 2)
+    return np.ascontiguousarray(pos.T), np.ascontiguousarray(vel.T)
+
+
+def cpu_iteration(cport, k, spec, opt, pos, vel, step0, stride, seed):
+    """One VES iteration of the CPU port: stride steps, first moments, averaged-SGD update."""
+    from oracle import potentials
+    m = cport.Model(potentials.DOUBLE_WELL_2D, (), spec, k, seed=seed, gid0=0)
+    m.run(pos, vel, step0, stride)
+    sf = m.moments(pos)
+    ft = np.zeros_like(sf)
+    ft[0] = 1.0                                                   # uniform target average of P_i P_j
+    spec["weights"] = opt.step(ft - sf / pos.shape[1]).reshape(spec["weights"].shape)
+
+
+def cpu_baseline(args, seconds=12.0):
+    from oracle import ves
+    cport, k, spec = cpu_model(args, args.seed)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu)
+    pos, vel = cpu_state(2048, k, args.seed)
+    t = time.perf_counter()
+    cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
+    rate = 2048 * 50 / (time.perf_counter() - t)
+    n = int(max(2048, min(args.walkers, rate * seconds / args.stride)))
+    pos, vel = cpu_state(n, k, args.seed)
+    t = time.perf_counter()
+    cpu_iteration(cport, k, spec, opt, pos, vel, 0, args.stride, args.seed)
+    dt = time.perf_counter() - t
+    return {"value": n * args.stride / dt, "unit": "walker-steps/s", "cores": cport.num_threads(), "kind": "port",
+            "sample": "%d walkers x %d steps + moments + update, FP64, gcc -O3 OpenMP C port of the same path "
+                      "(oracle/c/pyves_oracle.c); the reference itself (Python + OpenMM + TorchForce) cannot run here: "
+                      "OpenMM absent" % (n, args.stride)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import ves
+    cport, k, spec = cpu_model(args, args.seed)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu)
+    pos, vel = cpu_state(2048, k, args.seed)
+    t = time.perf_counter()
+    cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
+    rate = 2048 * 50 / (time.perf_counter() - t)
+    per_step_s = max(0.5, min(4.0, 90.0 / max(1, args.steps + args.warmup)))
+    n = int(max(2048, min(args.walkers, rate * per_step_s / args.stride)))
+    pos, vel = cpu_state(n, k, args.seed)
+    step0 = 0
+    for _ in range(args.warmup):
+        cpu_iteration(cport, k, spec, opt, pos, vel, step0, args.stride, args.seed)
+        step0 += args.stride
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_iteration(cport, k, spec, opt, pos, vel, step0, args.stride, args.seed)
+        step0 += args.stride
+    dt = time.perf_counter() - t
+    value = n * args.stride * args.steps / dt
+    sample = ("%d walkers x %d MD steps per bench step (bounded sample of the %d-walker workload), FP64, all host threads"
+              % (n, args.stride, args.walkers))
+    out = {"impl": "reference", "metric": "walker-steps/s (2D double well, Legendre bias)", "value": value,
+           "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "configs[1]: 2D double well, %dx%d tensor Legendre bias, averaged SGD update every %d steps"
+                                  % (args.basis, args.basis, args.stride), "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cport.num_threads(), "kind": "port",
+                            "sample": sample + "; OpenMP C port of the path (oracle/c/pyves_oracle.c) -- the reference's own "
+                                               "OpenMM + TorchForce stack is not installable here (no network)"},
+           "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

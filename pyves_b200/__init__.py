@@ -6,3 +6,15 @@ The compute path is the CUDA library ``csrc/libpyves_b200.so`` (C ABI in
 ``ves.*`` modules.  There is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+
+def install_as_ves():
+    """Register this package under the name ``ves`` so reference scripts (``from ves.basis import ...``)
+    import the B200 implementation unchanged."""
+    import importlib
+    import sys
+    me = sys.modules[__name__]
+    sys.modules["ves"] = me
+    for name in ("basis", "bias", "target", "potentials", "langevin_dynamics", "config_creation", "utils", "fes"):
+        sys.modules["ves." + name] = importlib.import_module(__name__ + "." + name)
+    return me

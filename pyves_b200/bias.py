@@ -1,0 +1,348 @@
+"""Bias potentials and their update rules -- mirror of ``ves/bias.py``.
+
+Reference classes kept with the same names and signatures: ``Bias`` (``ves/bias.py:16-30``),
+``NNBias`` (``:33-59``), ``HarmonicBias_SingleParticle_1D`` (+ ``_ForceModule``, ``:76-133``),
+``StaticBias_SingleParticle`` (``:136-152``), ``VESBias_SingleParticle_1D`` (``:160-253``).
+
+Differences in mechanism, not in behaviour:
+* ``.force`` returns a ``BiasDescriptor`` (bias kind + parameters) that the simulation uploads to its
+  CUDA handle, instead of an ``openmmtorch.TorchForce`` that re-reads ``model_loc`` from disk
+  (``ves/bias.py:56-59``).  ``model_loc`` still receives the TorchScript export (``:52-53,249-253``).
+* ``VESBias_SingleParticle_1D.update(traj)`` evaluates the reference's loss
+  ``(1/beta) log sum_t exp(beta V(x_t)) + sum_i p_i V(x_i)`` (``:216-236``) and its parameter gradient
+  with the CUDA kernels (``pyves_eval_bias`` + ``pyves_moments`` with soft-max row weights) instead of
+  <= 5200 Python-level module calls and autograd; the optimiser is the same ``torch.optim`` object.
+
+New: ``VESBias_Ensemble`` -- the textbook VES estimator (gradient ``-<f>_V + <f>_p``, Hessian
+``beta Cov_V f``) fed by ensemble moments, with averaged SGD (1st / 2nd order) or a ``torch.optim``
+optimiser, a refreshable (well-tempered) target and optional gradient running averages.
+"""
+import numpy as np
+import torch
+import torch.optim as optim
+
+from . import _lib
+from .basis import LegendreBasis1D, LegendreBasis2D, LegendreBasis2DPathCV, NNBasis1D, _KernelModule, _axis_id
+from .optim import AveragedSGD, RunningAverage, gradient_hessian
+
+
+class BiasDescriptor:
+    """What ``Bias.force`` hands to the simulation: a bias kind and its parameters."""
+
+    def __init__(self, kind, params):
+        self.kind = kind
+        self.params = params
+
+    def apply(self, ens):
+        p = self.params
+        if self.kind == "legendre1d":
+            ens.set_bias_legendre1d(p["axis"], p["degree"], p["lo"], p["hi"], p["w"])
+        elif self.kind == "legendre2d":
+            ens.set_bias_legendre2d(p["deg_x"], p["deg_y"], p["minmax"], p["w"])
+        elif self.kind == "mlp":
+            ens.set_bias_mlp(p["axis"], p["lo"], p["hi"], p["sizes"], p["act"], p["theta"])
+        elif self.kind == "pathcv":
+            ens.set_bias_pathcv(p["degree"], p["x_i"], p["y_i"], p["lam"], p["w"], p["phi"])
+        elif self.kind == "harmonic":
+            ens.set_bias_harmonic(p["axis"], p["k"], p["s0"])
+        elif self.kind == "none":
+            ens.set_bias_none()
+        else:
+            raise ValueError("unknown bias kind %r" % self.kind)
+
+
+################################################################################
+# Base classes
+################################################################################
+class Bias:
+    """Base class defining biases."""
+
+    def __init__(self):
+        pass
+
+    def update(self, traj):
+        # Biases are static by default.
+        raise NotImplementedError("This bias cannot be updated.")
+
+    @property
+    def force(self):
+        pass
+
+
+class NNBias(Bias):
+    """Base of the biases defined by a module ``self.model`` (set by the child class before
+    ``super().__init__()``); exports it as TorchScript to ``model_loc``."""
+
+    def __init__(self, model_loc="model.pt"):
+        self.model_loc = model_loc
+        self._export(self.model_loc)
+        super().__init__()
+
+    def _export(self, *paths):
+        if self.model_loc is None:
+            return
+        module = self.model.export_torchscript()
+        for path in paths:
+            module.save(path)
+
+    @property
+    def force(self):
+        return BiasDescriptor(*self.model.descriptor())
+
+
+################################################################################
+# Static biases
+################################################################################
+class HarmonicBias_SingleParticle_1D_ForceModule(_KernelModule):
+    """Harmonic potential $k/2 (s - s0)^2$ along x or y (``ves/bias.py:97-133``); like upstream, the
+    energies of all rows are summed into one scalar."""
+
+    def __init__(self, k, s0, axis='x'):
+        self.k = k
+        self.s0 = s0
+        self.axis = axis
+        super().__init__()
+
+    def _kernel_params(self):
+        return ()
+
+    def _upload(self, ens, params):
+        ens.set_bias_harmonic(_axis_id(self.axis), float(self.k), float(self.s0))
+
+    def forward(self, positions):
+        _axis_id(self.axis)
+        return torch.sum(self._run(positions))
+
+    def descriptor(self):
+        return ("harmonic", dict(axis=_axis_id(self.axis), k=float(self.k), s0=float(self.s0)))
+
+    def export_torchscript(self):
+        return torch.jit.script(_ExportHarmonic(float(self.k), float(self.s0), _axis_id(self.axis)))
+
+
+class _ExportHarmonic(torch.nn.Module):
+    def __init__(self, k: float, s0: float, axis: int):
+        super().__init__()
+        self.k, self.s0, self.axis = k, s0, axis
+
+    def forward(self, positions):
+        return 0.5 * self.k * torch.sum((positions[:, self.axis] - self.s0) ** 2)
+
+
+class HarmonicBias_SingleParticle_1D(NNBias):
+    """Harmonic bias $k/2 (s - s0)^2$ along the x- or y-coordinate (``ves/bias.py:76-94``)."""
+
+    def __init__(self, k, s0, axis='x', model_loc="model.pt"):
+        if axis not in ('x', 'y'):
+            raise ValueError("Invalid axis")
+        self.model = HarmonicBias_SingleParticle_1D_ForceModule(k, s0, axis=axis)
+        super().__init__(model_loc)
+
+
+class StaticBias_SingleParticle(NNBias):
+    """A static basis-set expanded potential: ``V_module`` is any module of ``pyves_b200.basis``
+    (``ves/bias.py:136-152``)."""
+
+    def __init__(self, V_module, model_loc):
+        self.model = V_module
+        super().__init__(model_loc)
+
+
+################################################################################
+# Dynamic biases
+################################################################################
+def _make_torch_optimizer(optimizer_type, params, optimizer_params):
+    if optimizer_type == 'SGD':
+        return optim.SGD(params, **optimizer_params)
+    if optimizer_type == 'RMSprop':
+        return optim.RMSprop(params, **optimizer_params)
+    if optimizer_type == 'Adam':
+        return optim.Adam(params, **optimizer_params)
+    raise ValueError("Requested optimizer not yet supported.")
+
+
+def _set_grads(model, flat):
+    flat = torch.as_tensor(flat, dtype=torch.float64)
+    o = 0
+    for p in model.parameters():
+        p.grad = flat[o:o + p.numel()].reshape(p.shape).to(device=p.device, dtype=p.dtype).clone()
+        o += p.numel()
+
+
+def _device_eval(model, pos_np):
+    """Energies of rows ``pos_np`` [N, C] (float64) through the module's CUDA evaluator, no autograd."""
+    t = torch.as_tensor(np.ascontiguousarray(pos_np, dtype=np.float64), device="cuda")
+    ens, _ = model._evaluator(t)
+    model._upload(ens, model._kernel_params())
+    return ens, t
+
+
+class VESBias_SingleParticle_1D(NNBias):
+    """Dynamic basis-set expanded potential along x or y of a single particle; ``update(traj)`` makes
+    one optimiser step on the reference's loss over the last ``update_steps`` frames
+    (``ves/bias.py:160-253``).
+
+    ``V_module`` is a ``LegendreBasis1D`` or ``NNBasis1D``; ``target`` a ``pyves_b200.target.Target_x``.
+    """
+
+    def __init__(self, V_module, target, beta, optimizer_type, optimizer_params, model_loc, update_steps=5000):
+        self.model = V_module
+        self.target = target
+        self.beta = beta
+        self.optimizer = _make_torch_optimizer(optimizer_type, self.model.parameters(), optimizer_params)
+        self.update_steps = update_steps
+        super().__init__(model_loc)
+
+    def loss_and_grad(self, traj):
+        """(loss, flat parameter gradient) of the reference's loss, computed on the GPU in FP64."""
+        traj = np.asarray(traj, dtype=np.float64)
+        T = traj.shape[0]
+        lo = max(T - self.update_steps, 0)
+        print(lo, T)                                                # ves/bias.py:218
+        ens, win = _device_eval(self.model, traj[lo:T].reshape(T - lo, -1))
+        E, _ = ens.eval_bias(win, want_force=False)
+        bE = self.beta * E
+        m = torch.max(bE)
+        ex = torch.exp(bE - m)
+        z = torch.sum(ex)
+        loss_V = (m + torch.log(z)) / self.beta
+        _, g_traj, _ = ens.moments(pos=win, row_weights=(ex / z).contiguous())
+        # target nodes are fed through the module as raw coordinates (ves/bias.py:229-233)
+        a = _axis_id(self.model.axis)
+        nodes = np.zeros((len(self.target.x), a + 1))
+        nodes[:, a] = self.target.x
+        tpos = torch.as_tensor(nodes, device="cuda")
+        p = torch.as_tensor(np.ascontiguousarray(self.target.p, dtype=np.float64), device="cuda")
+        Et, _ = ens.eval_bias(tpos, want_force=False)
+        _, g_tgt, _ = ens.moments(pos=tpos, row_weights=p)
+        loss = float(loss_V + torch.dot(p, Et))
+        return loss, (g_traj + g_tgt).cpu()
+
+    def update(self, traj):
+        self.optimizer.zero_grad()
+        loss, grad = self.loss_and_grad(traj)
+        print("Loss = {:.6f}".format(loss))
+        _set_grads(self.model, grad)
+        self.optimizer.step()
+        # overwrite the current model and archive it (ves/bias.py:249-253)
+        self._export(self.model_loc, self.model_loc + ".iter{}".format(np.asarray(traj).shape[0]))
+
+
+class VESBias_Ensemble(NNBias):
+    """Textbook VES update driven by ensemble moments (new; see module docstring).
+
+    Args:
+        V_module: ``LegendreBasis1D`` / ``LegendreBasis2D`` / ``LegendreBasis2DPathCV`` / ``NNBasis1D``.
+        target: a target of ``pyves_b200.target`` whose nodes live in the scaled coordinate [-1, 1]
+            of ``V_module`` (``Target_x`` family for 1D bases, ``Target_2D`` family for ``LegendreBasis2D``).
+        beta: 1 / kT.
+        optimizer_type: ``'averaged_sgd'`` (Bach-Moulines, ``optimizer_params`` = ``{'mu': .., 'second_order': bool}``)
+            or ``'SGD'`` / ``'RMSprop'`` / ``'Adam'`` (``torch.optim`` on the textbook gradient).
+        model_loc: TorchScript export path or None.
+        target_update_every: refresh a well-tempered target every this many updates.
+        gradient_average: None, ``'running'`` or a decay in (0, 1) for an exponentially weighted mean.
+    """
+
+    def __init__(self, V_module, target, beta, optimizer_type='averaged_sgd', optimizer_params=None, model_loc=None,
+                 target_update_every=10, gradient_average=None):
+        self.model = V_module
+        self.target = target
+        self.beta = beta
+        optimizer_params = dict(optimizer_params or {})
+        self.optimizer_type = optimizer_type
+        if optimizer_type == 'averaged_sgd':
+            if isinstance(V_module, NNBasis1D):
+                raise ValueError("averaged_sgd needs a linear basis expansion; use Adam / SGD / RMSprop for NNBasis1D")
+            w = np.concatenate([p.detach().cpu().numpy().ravel() for p in V_module.parameters()])
+            self.optimizer = AveragedSGD(w, mu=optimizer_params.get('mu', 1.0),
+                                         second_order=optimizer_params.get('second_order', False))
+        else:
+            self.optimizer = _make_torch_optimizer(optimizer_type, self.model.parameters(), optimizer_params)
+        self.target_update_every = int(target_update_every)
+        if gradient_average is None:
+            self.grad_avg = None
+        else:
+            self.grad_avg = RunningAverage(None if gradient_average == 'running' else float(gradient_average))
+        self.n_updates = 0
+        self._f_target = None
+        self.last_gradient = None
+        super().__init__(model_loc)
+
+    # -------------------------------------------------------------------------------------------
+    @property
+    def needs_covariance(self):
+        return self.optimizer_type == 'averaged_sgd' and self.optimizer.second_order
+
+    def _target_positions(self):
+        """Target nodes mapped from the scaled coordinate to real coordinates, [M, C]."""
+        m = self.model
+        s = np.asarray(self.target.x, dtype=np.float64)
+        if isinstance(m, LegendreBasis2D):
+            if getattr(self.target, "ndim", 1) != 2:
+                raise ValueError("LegendreBasis2D needs a 2D target")
+            cx, hx = (m.min_x + m.max_x) / 2, (m.max_x - m.min_x) / 2
+            cy, hy = (m.min_y + m.max_y) / 2, (m.max_y - m.min_y) / 2
+            return np.stack([cx + hx * s[:, 0], cy + hy * s[:, 1]], axis=1)
+        if isinstance(m, LegendreBasis2DPathCV):
+            raise NotImplementedError("ensemble VES along a path CV needs a target on the path; not provided yet")
+        a = _axis_id(m.axis)
+        pos = np.zeros((len(s), a + 1))
+        if isinstance(m, NNBasis1D):
+            pos[:, a] = m.min + (m.max - m.min) * (s + 1) / 2      # NN scaling maps [min, max] to [0, 1]
+        else:
+            pos[:, a] = (m.min + m.max) / 2 + (m.max - m.min) / 2 * s
+        return pos
+
+    def target_average(self, refresh=False):
+        """<dV/dparam>_p by quadrature over the target nodes (CUDA moments kernel with node weights)."""
+        if self._f_target is None or refresh or isinstance(self.model, NNBasis1D):
+            ens, tpos = _device_eval(self.model, self._target_positions())
+            q = torch.as_tensor(self.target.quadrature_weights(), device="cuda")
+            sw, sf, _ = ens.moments(pos=tpos, row_weights=q.contiguous())
+            self._f_target = (sf / sw).cpu().numpy()
+        return self._f_target
+
+    def refresh_target(self):
+        ens, tpos = _device_eval(self.model, self._target_positions())
+        V, _ = ens.eval_bias(tpos, want_force=False)
+        if self.target.update(V.cpu().numpy(), self.beta):
+            self._f_target = None
+
+    def update_from_moments(self, sum_w, sum_wf, sum_wff=None):
+        """One optimiser step from ensemble sums (already reduced over all GPUs)."""
+        tonp = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+        sum_w = float(tonp(sum_w).ravel()[0])
+        f_p = self.target_average()
+        grad, hess = gradient_hessian(sum_w, tonp(sum_wf), None if sum_wff is None else tonp(sum_wff), f_p, self.beta)
+        if self.grad_avg is not None:
+            grad = self.grad_avg.update(grad)
+        self.last_gradient = grad
+        if self.optimizer_type == 'averaged_sgd':
+            abar = self.optimizer.step(grad, hess)
+            with torch.no_grad():
+                o = 0
+                for p in self.model.parameters():
+                    p.copy_(torch.from_numpy(abar[o:o + p.numel()].reshape(tuple(p.shape))))
+                    o += p.numel()
+        else:
+            self.optimizer.zero_grad()
+            _set_grads(self.model, grad)
+            self.optimizer.step()
+        self.n_updates += 1
+        if self.target_update_every > 0 and self.n_updates % self.target_update_every == 0:
+            self.refresh_target()
+        if self.model_loc is not None:
+            self._export(self.model_loc, self.model_loc + ".iter{}".format(self.n_updates))
+
+    def update(self, traj):
+        """Reference-style entry point: the rows of ``traj`` [T, C] are the samples of <.>_V."""
+        ens, rows = _device_eval(self.model, np.asarray(traj, dtype=np.float64).reshape(len(traj), -1))
+        sw, sf, sff = ens.moments(pos=rows, cov=self.needs_covariance)
+        self.update_from_moments(sw, sf, sff)
+
+    def fes(self, nodes_scaled=None):
+        """F(s) = -V(s) - (1/beta) ln p(s) at the target nodes, shifted to min 0 (kJ/mol)."""
+        ens, tpos = _device_eval(self.model, self._target_positions())
+        V, _ = ens.eval_bias(tpos, want_force=False)
+        F = -V.cpu().numpy() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
+        return F - F.min()

@@ -1,0 +1,321 @@
+"""Biased Langevin dynamics driver -- mirror of ``ves/langevin_dynamics.py`` for 1..N walkers.
+
+``SingleParticleSimulation`` keeps the reference's constructor, ``init_ves`` and ``__call__``
+signatures, defaults, error messages, public attributes (``traj``, ``PE``, ``KE``) and output files
+(``traj.dat`` / ``energies.dat`` formats of ``ves/langevin_dynamics.py:206-235``, a pickled state at
+every checkpoint).  Instead of an OpenMM ``Context`` with one particle stepped one ``step(1)`` at a
+time from Python (``:123,188``), the state of ``n_walkers`` independent walkers lives on the GPU and
+the fused step kernel of the CUDA library advances whole stretches between two "events"
+(trajectory frame, energy sample, checkpoint, bias update) in one launch.
+
+New keywords: ``n_walkers`` (ensemble size; sharded over the ranks of an initialised
+``torch.distributed`` process group), ``device``, ``precision`` ('fp32' | 'fp64'), ``scheme``
+('openmm_langevin' | 'middle'), ``dims`` (2 drops the decoupled z coordinate, 3 keeps it),
+``traj_walkers`` (how many walkers are recorded), ``sample_every`` (moment sampling stride of the
+ensemble VES update).  With ``n_walkers=1`` the behaviour and file contents follow the reference:
+frame ``t`` is the position before step ``t`` (``:180-188``), ``bias.update(self.traj)`` runs at
+``i == startafter`` and then whenever ``i % learnevery == 0`` (``:134-159``).
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bias import Bias, VESBias_Ensemble
+from .parallel import dist_info, reduce_moments, shard
+
+KB = 8.31446261815324e-3      # kJ/mol/K as OpenMM defines it (the integrator's kT)
+
+
+class State:
+    """Picklable snapshot (replaces ``openmm.State``): positions / velocities [n_walkers, dims]."""
+
+    def __init__(self, positions, velocities, step, seed, walker_offset=0):
+        self.positions = np.asarray(positions)
+        self.velocities = np.asarray(velocities)
+        self.step = int(step)
+        self.seed = int(seed)
+        self.walker_offset = int(walker_offset)
+
+    def getPositions(self, asNumpy=True):
+        return self.positions
+
+    def getVelocities(self, asNumpy=True):
+        return self.velocities
+
+
+class SingleParticleSimulation:
+    """Langevin dynamics of independent particles on a 2D potential energy surface with an optional
+    VES bias (``ves/langevin_dynamics.py:15-235``)."""
+
+    def __init__(self,
+                 potential,
+                 mass: int = 1,
+                 temp: float = 300,
+                 friction: float = 20,
+                 timestep: float = 10,
+                 init_state=None,
+                 init_coord: np.ndarray = np.array([0, 0, 0]).reshape((1, 3)),
+                 gpu: bool = True,
+                 cpu_threads: int = None,
+                 seed: int = None,
+                 traj_in_mem: bool = True,
+                 n_walkers: int = 1,
+                 device: int = None,
+                 precision: str = None,
+                 scheme: str = "openmm_langevin",
+                 dims: int = None,
+                 traj_walkers: int = 1,
+                 sample_every: int = None,
+                 process_group=None):
+        # units as upstream: Da, K, 1/ps, fs
+        self.mass = float(mass)
+        self.temp = float(temp)
+        self.friction = float(friction)
+        self.timestep = float(timestep)
+        self.dt_ps = self.timestep * 1e-3
+        self.potential = potential
+        self.init_state = init_state
+        self.process_group = process_group
+        self.rank, self.world = dist_info(process_group)
+        self.n_walkers_total = int(n_walkers)
+        lo, hi = shard(self.n_walkers_total, self.rank, self.world)
+        if hi <= lo:
+            raise ValueError("n_walkers must be at least the number of ranks")
+        self.walker_offset, self.n_walkers = lo, hi - lo
+        self.dims = int(dims) if dims is not None else (3 if self.n_walkers_total == 1 else 2)
+        self.precision = precision or ("fp64" if self.n_walkers_total == 1 else "fp32")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", 0)) if self.world > 1 else torch.cuda.current_device()
+        self.device = device
+        self.seed = int.from_bytes(os.urandom(7), "little") if seed is None else int(seed)
+        if init_state is not None:
+            self.seed = getattr(init_state, "seed", self.seed) if seed is None else self.seed
+        print("Running simulation of {} walker(s) on GPU {} ({}, {} simulated dimensions).".format(
+            self.n_walkers, self.device, self.precision, self.dims))
+
+        self.ens = _lib.Ensemble(self.n_walkers, dims=self.dims, seed=self.seed, precision=self.precision, device=self.device)
+        self.ens.set_integrator(self.mass, KB * self.temp, self.friction, self.dt_ps, scheme)
+        self.ens.set_potential(potential.kind, potential.params)
+        self.ens.set_walker_offset(self.walker_offset)
+
+        if init_state is None:
+            pos = np.asarray(init_coord, dtype=np.float64)
+            if pos.ndim == 1:
+                pos = pos.reshape(1, -1)
+            if pos.shape[0] == 1:
+                pos = np.repeat(pos, self.n_walkers, axis=0)
+            elif pos.shape[0] == self.n_walkers_total and self.world > 1:
+                pos = pos[lo:hi]
+            if pos.shape[0] != self.n_walkers:
+                raise ValueError("init_coord must have 1 or n_walkers rows")
+            self._set_positions(pos)
+            self.ens.init_velocities()
+        else:
+            self._set_positions(np.asarray(init_state.getPositions()))
+            vel = np.asarray(init_state.getVelocities())
+            self.ens.set_state(None, np.ascontiguousarray(self._cols(vel).T))
+            self.ens.step_counter = getattr(init_state, "step", 0)
+
+        self.traj_in_mem = traj_in_mem
+        self.traj_walkers = max(1, min(int(traj_walkers), self.n_walkers))
+        self.sample_every = sample_every
+        self.biased = False
+
+    # ------------------------------------------------------------------------------------------------
+    def _cols(self, a):
+        """[n, C] -> [n, dims] (pad z with zeros / drop it)."""
+        a = np.asarray(a, dtype=np.float64).reshape(self.n_walkers, -1)
+        if a.shape[1] >= self.dims:
+            return a[:, :self.dims]
+        return np.concatenate([a, np.zeros((a.shape[0], self.dims - a.shape[1]))], axis=1)
+
+    def _set_positions(self, pos):
+        self.ens.set_state(np.ascontiguousarray(self._cols(pos).T), None)
+
+    def place_walkers(self, ntrials=100, xmin=0, xmax=1, ymin=0, ymax=1):
+        """Monte-Carlo placement of every walker (rule of ``ves/config_creation.py:56-68``) + fresh velocities."""
+        from .config_creation import ensemble_init_coord
+        ensemble_init_coord(self.ens, self.temp, ntrials, xmin, xmax, ymin, ymax)
+        self.ens.init_velocities()
+
+    def get_state(self):
+        pos, vel = self.ens.get_state(host=True)
+        return State(pos.T.copy(), vel.T.copy(), self.ens.step_counter, self.seed, self.walker_offset)
+
+    # ------------------------------------------------------------------------------------------------
+    def init_ves(self, bias: Bias, static: bool = False, startafter: int = 2, learnevery: int = 50):
+        """Initialize simulation with VES bias (``ves/langevin_dynamics.py:85-107``)."""
+        self.biased = True
+        if static:
+            self.static = True
+            self.startafter = None
+            self.learnevery = None
+        else:
+            self.static = False
+            if startafter < 2:
+                raise ValueError("Cannot start VES updates before timestep 2.")
+            self.startafter = startafter
+            self.learnevery = learnevery
+        self.bias = bias
+        self.update_on = False
+
+    # ------------------------------------------------------------------------------------------------
+    def _update_bias(self, i, ves_update_params):
+        if isinstance(self.bias, VESBias_Ensemble):
+            self._sample_moments()
+            sw, sf, sff = reduce_moments(*self._acc, group=self.process_group)   # one allreduce per update
+            self.bias.update_from_moments(sw, sf, sff)
+            self._acc = None
+        else:
+            self.bias.update(self.traj, **ves_update_params)
+        self.bias.force.apply(self.ens)
+
+    def _sample_moments(self):
+        """Accumulate sum_w, sum_w f, (sum_w f f) of the current walkers for the next ensemble update."""
+        if getattr(self, "_sampled_at", None) == self.ens.step_counter and self._acc is not None:
+            return
+        s = self.ens.moments(cov=self.bias.needs_covariance)
+        if self._acc is None:
+            self._acc = list(s)
+        else:
+            for k in range(3):
+                if s[k] is not None:
+                    self._acc[k] += s[k]
+        self._sampled_at = self.ens.step_counter
+
+    def _events(self, i, nsteps, chkevery, trajevery, energyevery):
+        """Smallest step index > i at which the host must do something."""
+        nxt = nsteps
+        for every in (chkevery, energyevery):
+            if every:
+                nxt = min(nxt, (i // every + 1) * every)
+        if self.biased and not self.static:
+            if i < self.startafter:
+                nxt = min(nxt, self.startafter)
+            nxt = min(nxt, max((i // self.learnevery + 1) * self.learnevery, self.startafter + 1))
+            if isinstance(self.bias, VESBias_Ensemble) and self.sample_every:
+                nxt = min(nxt, (i // self.sample_every + 1) * self.sample_every)
+        return nxt
+
+    def __call__(self,
+                 nsteps: int = 1000,
+                 chkevery: int = 500,
+                 trajevery: int = 1,
+                 energyevery: int = 1,
+                 chkfile="./chk_state.pkl",
+                 trajfile="./traj.dat",
+                 energyfile="./energies.dat",
+                 ves_update_params={}):
+        self.traj = None
+        self.PE = []
+        self.KE = []
+        self._acc = None
+        self._traj_written = 0
+        self.traj_ensemble = None
+        frames = []
+        i = 0
+        i_last = 0
+        ens = self.ens
+        write = self.rank == 0
+        ftraj = open(trajfile, "w") if (write and trajfile and trajevery) else None
+        fener = open(energyfile, "w") if (write and energyfile and energyevery) else None
+        self._ftraj, self._trajevery = ftraj, trajevery
+        if ftraj:
+            ftraj.write("# t[ps]    x [nm]    y [nm]    z[nm]\n")
+        if fener:
+            fener.write("# t[ps]    PE [kJ/mol]    KE [kJ/mol]\n")
+        try:
+            while i < nsteps:
+                # ---- VES bookkeeping at iteration i (ves/langevin_dynamics.py:134-169)
+                if self.biased:
+                    if not self.static:
+                        if i == self.startafter:
+                            print("[VES] {} bias: Initializing dynamic bias at timestep {}.".format(type(self.bias).__name__, i))
+                            self._sync_traj(frames)
+                            self._update_bias(i, ves_update_params)
+                        elif i > self.startafter and i % self.learnevery == 0:
+                            print("[VES] {} bias: Updating dynamic bias at timestep {}.".format(type(self.bias).__name__, i))
+                            self._sync_traj(frames)
+                            self._update_bias(i, ves_update_params)
+                        elif isinstance(self.bias, VESBias_Ensemble) and self.sample_every and i % self.sample_every == 0 and i > 0:
+                            self._sample_moments()
+                    elif i == 0:
+                        print("[VES] {} bias: Initializing static bias.".format(type(self.bias).__name__))
+                        self.bias.force.apply(ens)
+                if i > 0 and chkevery and i % chkevery == 0:
+                    self._dump_state(chkfile, i)
+                if energyevery and i % energyevery == 0:
+                    PE, KE = ens.energies(host=True)
+                    self.PE.append(float(PE[0]) if self.n_walkers_total == 1 else float(np.mean(PE)))
+                    self.KE.append(float(KE[0]) if self.n_walkers_total == 1 else float(np.mean(KE)))
+                    if fener:
+                        fener.write("{:10.5f}\t{:10.7f}\t{:10.7f}\n".format(i * self.dt_ps, self.PE[-1], self.KE[-1]))
+                # ---- advance to the next event, recording frames inside the kernel
+                nxt = self._events(i, nsteps, chkevery, trajevery, energyevery)
+                if trajevery:
+                    head = (-i) % trajevery                     # steps until the next frame index
+                    if head and head < nxt - i:
+                        ens.step(head)
+                        i += head
+                    if i % trajevery == 0 and i < nxt:
+                        t = ens.step_record(nxt - i, every=trajevery, n_rec=self.traj_walkers)
+                        frames.append((i, t))
+                        i = nxt
+                    elif i < nxt:
+                        ens.step(nxt - i)
+                        i = nxt
+                else:
+                    ens.step(nxt - i)
+                    i = nxt
+                i_last = i
+                if len(frames) >= 64:
+                    self._sync_traj(frames)
+            self._sync_traj(frames)
+        finally:
+            self._ftraj = None
+            if ftraj:
+                ftraj.close()
+            if fener:
+                fener.close()
+        # Finalize: checkpoint named after the last loop index, as upstream (:195)
+        self._dump_state(chkfile, max(i_last - 1, 0))
+
+    # ------------------------------------------------------------------------------------------------
+    def _sync_traj(self, frames):
+        """Move recorded frames to the host: ``self.traj`` ([T, 3] of walker 0, plus
+        ``self.traj_ensemble`` [T, traj_walkers, dims]) and the trajectory file."""
+        if not frames:
+            return
+        ftraj, trajevery = self._ftraj, self._trajevery
+        chunks = []
+        for i0, t in frames:
+            chunks.append(t.permute(0, 2, 1).cpu().numpy().astype(np.float64))      # [frames, rec, dims]
+        frames.clear()
+        new = np.concatenate(chunks, axis=0)
+        if self.traj_in_mem:
+            first = new[:, 0, :]
+            if first.shape[1] < 3:
+                first = np.concatenate([first, np.zeros((first.shape[0], 3 - first.shape[1]))], axis=1)
+            self.traj = first if self.traj is None else np.vstack((self.traj, first))
+            if self.traj_walkers > 1:
+                prev = self.traj_ensemble
+                self.traj_ensemble = new if prev is None else np.concatenate([prev, new], axis=0)
+        if ftraj is not None:
+            k0 = self._traj_written
+            for k in range(new.shape[0]):
+                p = new[k, 0]
+                z = p[2] if p.shape[0] > 2 else 0.0
+                ftraj.write("{:10.5f}\t{:10.7f}\t{:10.7f}\t{:10.7f}\n".format((k0 + k) * trajevery * self.dt_ps, p[0], p[1], z))
+        self._traj_written += new.shape[0]
+
+    def _dump_state(self, ofilename, i):
+        t = i * self.dt_ps
+        print("Checkpoint at {:10.7f} ps".format(t))
+        if not ofilename:
+            return
+        name = ofilename if self.world == 1 else "{}.rank{}".format(ofilename, self.rank)
+        with open(name, "wb") as fh:
+            pickle.dump(self.get_state(), fh)
