@@ -73,6 +73,7 @@ def test_potentials_match_reference_golden(golden):
         P.Potential2D.potential(objs["SlipBondPotential2D"].__class__.__mro__[1], 0, 0)
     # the expression is printed at construction, as upstream
     buf = io.StringIO()
+    P._Potential.quiet = False
     with contextlib.redirect_stdout(buf):
         P.DoubleWellPotential2D()
     assert "[Potential] Initializing potential with expression:" in buf.getvalue()
