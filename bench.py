@@ -38,7 +38,7 @@ FLOPS_PER_WALKER_STEP = {8: 4 * 64 + 4 * 8 + 6 * 14 + 32, 16: 1300, 32: 4628, 64
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=1000000, help="walkers per GPU")
@@ -57,7 +57,7 @@ class ClockMonitor(threading.Thread):
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.power = [], set(), []
@@ -107,7 +107,8 @@ def make_bias(args, beta):
     d = args.basis - 1
     basis = LegendreBasis2D(d, d, *MINMAX)                      # w = 0 at start
     target = Target_WellTempered_2D(100, 100, bias_factor=10.0)
-    return VESBias_Ensemble(basis, target, beta, "averaged_sgd", {"mu": args.mu}, model_loc=None, target_update_every=10)
+    return VESBias_Ensemble(basis, target, beta, "averaged_sgd", {"mu": args.mu, "averaging": "ewma", "decay": 0.9},
+                            model_loc=None, target_update_every=10)
 
 
 def make_ensemble(args, rank, device):
@@ -278,7 +279,7 @@ def cpu_iteration(cport, k, spec, opt, pos, vel, step0, stride, seed):
 def cpu_baseline(args, seconds=12.0):
     from oracle import ves
     cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.9)
     pos, vel = cpu_state(2048, k, args.seed)
     t = time.perf_counter()
     cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
@@ -300,7 +301,7 @@ def run_reference(args):
         return
     from oracle import ves
     cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.9)
     pos, vel = cpu_state(2048, k, args.seed)
     t = time.perf_counter()
     cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)

@@ -159,6 +159,8 @@ int pyves_set_tuning(pyves_t* h, int variant);
 
 /* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */
 int pyves_fp32_fma_peak(int device, double* tflops);
+/* the same probe issued as packed FP32x2 FMAs (FFMA2, sm_100) */
+int pyves_fp32_fma2_peak(int device, double* tflops);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence) */
 int64_t pyves_launch_count(void);
 

@@ -76,13 +76,15 @@ def gradient_hessian(sum_w, sum_f, sum_ff, f_target, beta):
 
 class AveragedSGD:
     """alpha^{n+1} = alpha^n - mu [grad(abar^n) + H(abar^n)(alpha^n - abar^n)];
-    abar^n = mean of alpha^0..alpha^n; the applied bias uses abar."""
+    abar^n = mean of alpha^0..alpha^n (``decay=None``) or the exponentially weighted mean
+    abar <- decay abar + (1 - decay) alpha; the applied bias uses abar."""
 
-    def __init__(self, alpha0, mu):
+    def __init__(self, alpha0, mu, decay=None):
         self.alpha = np.array(alpha0, dtype=np.float64)
         self.abar = self.alpha.copy()
         self.n = 0
         self.mu = mu
+        self.decay = decay
 
     def step(self, grad, hess=None):
         d = grad.copy()
@@ -90,7 +92,10 @@ class AveragedSGD:
             d = d + hess @ (self.alpha - self.abar)
         self.alpha = self.alpha - self.mu * d
         self.n += 1
-        self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
+        if self.decay is None:
+            self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
+        else:
+            self.abar = self.decay * self.abar + (1 - self.decay) * self.alpha
         return self.abar
 
 

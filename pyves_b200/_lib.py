@@ -57,6 +57,7 @@ SIGNATURES = {
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
+    "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
 }
 
@@ -101,9 +102,10 @@ def launch_count():
     return int(load().pyves_launch_count())
 
 
-def fp32_fma_peak(device=0):
+def fp32_fma_peak(device=0, packed=False):
     out = _d(0.0)
-    rc = load().pyves_fp32_fma_peak(device, ctypes.byref(out))
+    fn = load().pyves_fp32_fma2_peak if packed else load().pyves_fp32_fma_peak
+    rc = fn(device, ctypes.byref(out))
     if rc:
         _raise(rc, None)
     return out.value

@@ -236,7 +236,8 @@ class VESBias_Ensemble(NNBias):
         target: a target of ``pyves_b200.target`` whose nodes live in the scaled coordinate [-1, 1]
             of ``V_module`` (``Target_x`` family for 1D bases, ``Target_2D`` family for ``LegendreBasis2D``).
         beta: 1 / kT.
-        optimizer_type: ``'averaged_sgd'`` (Bach-Moulines, ``optimizer_params`` = ``{'mu': .., 'second_order': bool}``)
+        optimizer_type: ``'averaged_sgd'`` (Bach-Moulines, ``optimizer_params`` = ``{'mu': .., 'second_order': bool,
+            'averaging': 'ewma' | 'running', 'decay': 0.9}``)
             or ``'SGD'`` / ``'RMSprop'`` / ``'Adam'`` (``torch.optim`` on the textbook gradient).
         model_loc: TorchScript export path or None.
         target_update_every: refresh a well-tempered target every this many updates.
@@ -255,7 +256,9 @@ class VESBias_Ensemble(NNBias):
                 raise ValueError("averaged_sgd needs a linear basis expansion; use Adam / SGD / RMSprop for NNBasis1D")
             w = np.concatenate([p.detach().cpu().numpy().ravel() for p in V_module.parameters()])
             self.optimizer = AveragedSGD(w, mu=optimizer_params.get('mu', 1.0),
-                                         second_order=optimizer_params.get('second_order', False))
+                                         second_order=optimizer_params.get('second_order', False),
+                                         averaging=optimizer_params.get('averaging', 'ewma'),
+                                         decay=optimizer_params.get('decay', 0.9))
         else:
             self.optimizer = _make_torch_optimizer(optimizer_type, self.model.parameters(), optimizer_params)
         self.target_update_every = int(target_update_every)

@@ -961,7 +961,16 @@ int pyves_fp32_fma_peak(int device, double* tflops) {
   pyves_ctx* h = nullptr;
   if (!tflops) return fail(h, PYVES_EINVAL, "tflops is NULL");
   DeviceGuard g(device);
-  CU(fp32_fma_peak(tflops));
+  CU(fp32_fma_peak(tflops, 0));
+  g_launches += 5;
+  return PYVES_OK;
+}
+
+int pyves_fp32_fma2_peak(int device, double* tflops) {
+  pyves_ctx* h = nullptr;
+  if (!tflops) return fail(h, PYVES_EINVAL, "tflops is NULL");
+  DeviceGuard g(device);
+  CU(fp32_fma_peak(tflops, 1));
   g_launches += 5;
   return PYVES_OK;
 }

@@ -113,9 +113,14 @@ template <typename T, int KX, int KY> struct BiasLegendre2DStatic {
     bool inx, iny;
     const T sx = scale_clamp(x, P.cx, P.ihx, inx);
     const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    // Q[j] = (P_j(y'), P'_j(y')): one packed FMA per weight updates (A_i, B_i) together
     T Py[KY], dPy[KY];
     legendre_fill<T, KY>(sy, Py, dPy);
-    T ax = T(0), ay = T(0), E = T(0);
+    Pair<T> Q[KY];
+#pragma unroll
+    for (int j = 0; j < KY; ++j) Q[j] = Pair<T>::make(Py[j], dPy[j]);
+    Pair<T> G = Pair<T>::make(T(0), T(0));   // (dV/dsx, dV/dsy)
+    T E = T(0);
     T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
 #pragma unroll
     for (int i = 0; i < KX; ++i) {
@@ -127,19 +132,19 @@ template <typename T, int KX, int KY> struct BiasLegendre2DStatic {
         const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
         pxm = px; px = pn; dpxm = dpx; dpx = dpn;
       }
-      T A = P.w[i * KY] * Py[0];
-      T B = T(0);
+      Pair<T> AB0 = Pair<T>::make(T(0), T(0)), AB1 = AB0;   // two chains per row for ILP
 #pragma unroll
-      for (int j = 1; j < KY; ++j) {
-        A = Math<T>::fma(P.w[i * KY + j], Py[j], A);
-        B = Math<T>::fma(P.w[i * KY + j], dPy[j], B);
+      for (int j = 0; j < KY; j += 2) {
+        AB0 = Pair<T>::fma_bcast(Q[j], P.w[i * KY + j], AB0);
+        if (j + 1 < KY) AB1 = Pair<T>::fma_bcast(Q[j + 1], P.w[i * KY + j + 1], AB1);
       }
-      ax = Math<T>::fma(dpx, A, ax);
-      ay = Math<T>::fma(px, B, ay);
-      if (WANT_E) E = Math<T>::fma(px, A, E);
+      const Pair<T> one = Pair<T>::make(T(1), T(1));
+      const Pair<T> AB = Pair<T>::fma(AB0, one, AB1);
+      G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
+      if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
     }
-    gx += inx ? ax * P.ihx : T(0);
-    gy += iny ? ay * P.ihy : T(0);
+    gx += inx ? G.lo() * P.ihx : T(0);
+    gy += iny ? G.hi() * P.ihy : T(0);
     if (WANT_E) e += E;
   }
 };

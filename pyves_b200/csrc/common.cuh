@@ -32,6 +32,51 @@ template <> struct Math<double> {
   static PV_DEV double max(double a, double b) { return ::fmax(a, b); }
 };
 
+// Two values updated by one instruction.  For float this is Blackwell's packed FP32x2 datapath
+// (PTX fma.rn.f32x2 -> SASS FFMA2, new on sm_100): one issue slot performs two FMAs, and a scalar
+// operand is broadcast to both halves, so (A, B) += w * (P, P') costs a single instruction.
+// For double it is simply two DFMAs.
+template <typename T> struct Pair;
+
+template <> struct Pair<float> {
+  unsigned long long v;
+  static PV_DEV Pair make(float lo, float hi) {
+    Pair p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p.v) : "f"(lo), "f"(hi));
+    return p;
+  }
+  PV_DEV float lo() const {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+  }
+  PV_DEV float hi() const {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+  }
+  // a * w + c with the scalar w broadcast to both halves
+  static PV_DEV Pair fma_bcast(Pair a, float w, Pair c) {
+    Pair d, ww = make(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(ww.v), "l"(c.v));
+    return d;
+  }
+  static PV_DEV Pair fma(Pair a, Pair b, Pair c) {
+    Pair d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return d;
+  }
+};
+
+template <> struct Pair<double> {
+  double x, y;
+  static PV_DEV Pair make(double lo, double hi) { return Pair{lo, hi}; }
+  PV_DEV double lo() const { return x; }
+  PV_DEV double hi() const { return y; }
+  static PV_DEV Pair fma_bcast(Pair a, double w, Pair c) { return Pair{::fma(a.x, w, c.x), ::fma(a.y, w, c.y)}; }
+  static PV_DEV Pair fma(Pair a, Pair b, Pair c) { return Pair{::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)}; }
+};
+
 // Legendre recursion coefficients: P_{n+1} = A_n s P_n - B_n P_{n-1}, A_n = (2n+1)/(n+1),
 // B_n = n/(n+1); derivative P'_{n+1} = P'_{n-1} + C_n P_n, C_n = 2n+1  (ves/basis.py:111-112).
 template <typename T> PV_DEV constexpr T leg_a(int n) { return T(2 * n + 1) / T(n + 1); }

@@ -219,7 +219,26 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, float b, floa
   if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
 }
 
-cudaError_t fp32_fma_peak(double* tflops) {
+// Same probe with the packed FP32x2 instruction (FFMA2): 8 chains of pairs per thread.
+__global__ void __launch_bounds__(256) fma2_peak_kernel(float* out, float b, float c, int iters) {
+  Pair<float> a[8];
+  const Pair<float> cc = Pair<float>::make(c, c);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = Pair<float>::make((float)(threadIdx.x + i) * 1e-3f, (float)i * 2e-3f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = Pair<float>::fma_bcast(a[i], b, cc);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i].lo() + a[i].hi();
+  if (s == 123.456f) out[0] = s;
+}
+
+cudaError_t fp32_fma_peak(double* tflops, int packed) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -233,7 +252,8 @@ cudaError_t fp32_fma_peak(double* tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0);
-    fma_peak_kernel<<<blocks, threads>>>(out, 0.999f, 1e-3f, iters);
+    if (packed) fma2_peak_kernel<<<blocks, threads>>>(out, 0.999f, 1e-3f, iters);
+    else fma_peak_kernel<<<blocks, threads>>>(out, 0.999f, 1e-3f, iters);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0.f;

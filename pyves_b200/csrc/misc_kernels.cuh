@@ -32,6 +32,6 @@ cudaError_t launch_histogram(const T* pos, int64_t n, int64_t stride_row, int64_
                              const double* range, const int* nbins, const T* row_weights, double* counts,
                              cudaStream_t st);
 
-cudaError_t fp32_fma_peak(double* tflops);
+cudaError_t fp32_fma_peak(double* tflops, int packed);
 
 }  // namespace pv

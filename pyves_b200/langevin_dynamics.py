@@ -165,6 +165,8 @@ class SingleParticleSimulation:
     # ------------------------------------------------------------------------------------------------
     def _update_bias(self, i, ves_update_params):
         if isinstance(self.bias, VESBias_Ensemble):
+            if i == self.startafter:
+                self.bias.force.apply(self.ens)      # defines the basis for the moment kernels; forces start now
             self._sample_moments()
             sw, sf, sff = reduce_moments(*self._acc, group=self.process_group)   # one allreduce per update
             self.bias.update_from_moments(sw, sf, sff)
@@ -240,7 +242,8 @@ class SingleParticleSimulation:
                             print("[VES] {} bias: Updating dynamic bias at timestep {}.".format(type(self.bias).__name__, i))
                             self._sync_traj(frames)
                             self._update_bias(i, ves_update_params)
-                        elif isinstance(self.bias, VESBias_Ensemble) and self.sample_every and i % self.sample_every == 0 and i > 0:
+                        elif (isinstance(self.bias, VESBias_Ensemble) and self.sample_every and i > self.startafter
+                              and i % self.sample_every == 0):
                             self._sample_moments()
                     elif i == 0:
                         print("[VES] {} bias: Initializing static bias.".format(type(self.bias).__name__))

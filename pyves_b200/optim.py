@@ -22,13 +22,26 @@ def gradient_hessian(sum_w, sum_wf, sum_wff, f_target, beta):
 
 
 class AveragedSGD:
-    """Bach-Moulines averaged SGD; ``second_order`` adds the Hessian correction term."""
+    """Bach-Moulines averaged SGD.
 
-    def __init__(self, alpha0, mu=1.0, second_order=False):
+    ``second_order`` adds the Hessian correction ``H (alpha - abar)``, i.e. the gradient is Taylor
+    expanded from the averaged coefficients (where the ensemble is sampled) to the instantaneous
+    ones; without it the iterates overshoot by the lag of the average and the scheme oscillates.
+    ``averaging='running'`` is the plain mean of all iterates (the textbook choice, converging like
+    1/n); ``averaging='ewma'`` is the exponentially weighted mean with factor ``decay`` (the
+    "weighted average" option named in the reference's README, ``README.md:16-20``), which forgets
+    the transient and is what the ensemble runs use.
+    """
+
+    def __init__(self, alpha0, mu=1.0, second_order=False, averaging='running', decay=0.9):
+        if averaging not in ('running', 'ewma'):
+            raise ValueError("averaging must be 'running' or 'ewma'")
         self.alpha = np.array(alpha0, dtype=np.float64).ravel()
         self.abar = self.alpha.copy()
         self.mu = float(mu)
         self.second_order = bool(second_order)
+        self.averaging = averaging
+        self.decay = float(decay)
         self.n = 0
 
     def step(self, grad, hess=None):
@@ -37,16 +50,21 @@ class AveragedSGD:
             d = d + hess @ (self.alpha - self.abar)
         self.alpha = self.alpha - self.mu * d
         self.n += 1
-        self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
+        if self.averaging == 'ewma':
+            self.abar = self.decay * self.abar + (1.0 - self.decay) * self.alpha
+        else:
+            self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
         return self.abar
 
     def state_dict(self):
-        return dict(alpha=self.alpha.copy(), abar=self.abar.copy(), mu=self.mu, second_order=self.second_order, n=self.n)
+        return dict(alpha=self.alpha.copy(), abar=self.abar.copy(), mu=self.mu, second_order=self.second_order,
+                    averaging=self.averaging, decay=self.decay, n=self.n)
 
     def load_state_dict(self, d):
         self.alpha = np.array(d["alpha"], dtype=np.float64)
         self.abar = np.array(d["abar"], dtype=np.float64)
         self.mu, self.second_order, self.n = float(d["mu"]), bool(d["second_order"]), int(d["n"])
+        self.averaging, self.decay = d.get("averaging", "running"), float(d.get("decay", 0.9))
 
 
 class RunningAverage:

@@ -244,7 +244,8 @@ def test_ensemble_ves_converges_to_analytic_fes():
     pot = potentials.DoubleWellPotential2D()
     kT = 8.3145e-3 * 300
     model = basis.LegendreBasis1D(6, -2.5, 2.5, weights=np.zeros(7))
-    b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(401), 1 / kT, "averaged_sgd", {"mu": 3.0})
+    b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(401), 1 / kT, "averaged_sgd",
+                              {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
     sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=65536, seed=7, temp=300)
     sim.place_walkers(xmin=-2.5, xmax=2.5, ymin=-2, ymax=2)
     sim.init_ves(b, startafter=100, learnevery=100)
@@ -268,7 +269,7 @@ def test_ensemble_second_order_slip_bond():
     kT = 8.3145e-3 * 300
     model = basis.LegendreBasis1D(12, -3.0, 6.0, weights=np.zeros(13))
     b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(401), 1 / kT, "averaged_sgd",
-                              {"mu": 2.0, "second_order": True})
+                              {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
     assert b.needs_covariance
     sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=32768, seed=3)
     sim.place_walkers(xmin=-8, xmax=10, ymin=-6, ymax=8)

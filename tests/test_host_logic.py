@@ -129,9 +129,12 @@ def test_optimisers_match_oracle():
     g1, h1 = ves.gradient_hessian(sw, sf, sff, ft, 0.4)
     g2, h2 = optim.gradient_hessian(sw, sf, sff, ft, 0.4)
     assert np.array_equal(g1, g2) and np.array_equal(h1, h2)
-    a, b = ves.AveragedSGD(np.ones(7), 0.3), optim.AveragedSGD(np.ones(7), 0.3, second_order=True)
+    a, b = ves.AveragedSGD(np.ones(7), 0.3), optim.AveragedSGD(np.ones(7), 0.3, second_order=True, averaging='running')
     for _ in range(5):
         assert np.allclose(a.step(g1, h1), b.step(g2, h2), rtol=0, atol=1e-15)
+    a, b = ves.AveragedSGD(np.ones(7), 0.3, decay=0.8), optim.AveragedSGD(np.ones(7), 0.3, averaging='ewma', decay=0.8)
+    for _ in range(5):
+        assert np.allclose(a.step(g1), b.step(g2), rtol=0, atol=1e-15)
     st = b.state_dict()
     c = optim.AveragedSGD(np.zeros(7))
     c.load_state_dict(st)
@@ -241,7 +244,7 @@ sw, sf, sff = ves.moments(f)
 out = reduce_moments(torch.tensor([sw]), torch.tensor(sf), torch.tensor(sff))
 ft = np.zeros(16); ft[0] = 1
 g, h = optim.gradient_hessian(float(out[0]), out[1].numpy(), out[2].numpy(), ft, 0.4)
-opt = optim.AveragedSGD(np.zeros(16), 0.5, second_order=True)
+opt = optim.AveragedSGD(np.zeros(16), 0.5, second_order=True, averaging='running')
 np.save(sys.argv[3] + "/rank%%d.npy" %% rank, opt.step(g, h))
 dist.destroy_process_group()
 """
@@ -266,6 +269,6 @@ def test_two_rank_moment_reduction_gloo(tmp_path):
     ft = np.zeros(16)
     ft[0] = 1
     g, h = optim.gradient_hessian(sw, sf, sff, ft, 0.4)
-    ref = optim.AveragedSGD(np.zeros(16), 0.5, second_order=True).step(g, h)
+    ref = optim.AveragedSGD(np.zeros(16), 0.5, second_order=True, averaging='running').step(g, h)
     r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(r0, r1) and np.allclose(r0, ref, rtol=1e-12, atol=1e-14)

@@ -29,22 +29,24 @@ def main():
     pot = potentials.DoubleWellPotential2D()
     model = basis.LegendreBasis2D(15, 15, -2.5, 2.5, -2.0, 2.0)
     tgt = target.Target_WellTempered_2D(100, 100, gamma)
-    b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd", {"mu": mu}, target_update_every=10)
+    decay = float(sys.argv[5]) if len(sys.argv) > 5 else 0.8
+    second = len(sys.argv) > 6 and sys.argv[6] == "second"
+    b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd", {"mu": mu, "averaging": "ewma", "decay": decay, "second_order": second},
+                              target_update_every=10)
     sim = SingleParticleSimulation(pot, n_walkers=n, seed=20221019)
     sim.place_walkers(xmin=-2.5, xmax=2.5, ymin=-2, ymax=2)
-    sim.init_ves(b, startafter=stride, learnevery=stride)
+    ens = sim.ens
+    b.force.apply(ens)
     xs, F_ref = fes.projection_x(pot, 300, [-2.25, 2.25], [-2, 2])
     hist = []
     t0 = time.time()
     done = 0
     for chunk in range(nup // 50):
-        sim(nsteps=50 * stride + 1 if chunk == 0 else 50 * stride, chkevery=0, trajevery=0, energyevery=0, chkfile=None, trajfile=None, energyfile=None) if chunk == 0 else None
-        if chunk > 0:
-            # continue: re-enter the loop with the cadence shifted (startafter already passed)
-            for _ in range(50):
-                sim.ens.step(stride)
-                sim._acc = None
-                sim._update_bias(0, {})
+        for _ in range(50):
+            ens.step(stride)
+            sw, sf, sff = ens.moments(cov=second)
+            b.update_from_moments(sw, sf, sff)
+            b.force.apply(ens)
         done += 50
         # F(x, y) = -V - kT ln p on the target grid, then project on x
         F2 = b.fes().reshape(100, 100) / kT

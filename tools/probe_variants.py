@@ -42,7 +42,8 @@ def main():
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 500
     rng = np.random.default_rng(0)
     out = {"n": n, "steps_per_launch": S, "fp32_fma_peak_tflops": _lib.fp32_fma_peak(0)}
-    print("FP32 FMA peak: %.1f TFLOP/s" % out["fp32_fma_peak_tflops"], flush=True)
+    out["fp32_fma2_peak_tflops"] = _lib.fp32_fma_peak(0, packed=True)
+    print("FP32 FMA peak: %.1f TFLOP/s (FFMA), %.1f TFLOP/s (FFMA2)" % (out["fp32_fma_peak_tflops"], out["fp32_fma2_peak_tflops"]), flush=True)
     rows = []
 
     def run(tag, prec, pot, params, setup, variants=(-1,), flops=None, box=(-2.5, 2.5, -2, 2)):
@@ -65,7 +66,14 @@ def main():
     DW, SLIP, SB = _lib.POT_DOUBLE_WELL_2D, _lib.POT_SLIP_BOND_2D, _lib.POT_SZABO_BEREZHKOVSKII
     slip = (0, 0, 1, 5, 4, 0, 2)
     sb = (2.2, 4.0, 4.04, 4.84)
-    for prec in ("fp32", "fp64"):
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
+    _run = run
+
+    def run(tag, *a, **k):
+        if only is None or any(o in tag for o in only):
+            _run(tag, *a, **k)
+
+    for prec in ("fp32", "fp64") if (len(sys.argv) <= 4) else (sys.argv[4],):
         run("dw_none", prec, DW, (), lambda e: e.set_bias_none(), flops=32)
         run("cfg1_dw_leg1d5", prec, DW, (), lambda e: e.set_bias_legendre1d(0, 5, -2.5, 2.5, rng.standard_normal(6)), flops=70)
         run("cfg3_slip_leg1d12", prec, SLIP, slip, lambda e: e.set_bias_legendre1d(0, 12, -3, 6, rng.standard_normal(13) * 0.1), flops=133, box=(-8, 10, -6, 8))
