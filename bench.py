@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument("--walkers", type=int, default=1000000, help="walkers per GPU")
     ap.add_argument("--stride", type=int, default=500, help="MD steps per VES iteration")
     ap.add_argument("--basis", type=int, default=16, help="Legendre functions per axis")
-    ap.add_argument("--mu", type=float, default=1.0, help="averaged-SGD step size (kJ/mol)")
+    ap.add_argument("--mu", type=float, default=0.5, help="averaged-SGD step size (kJ/mol)")
+    ap.add_argument("--fes-updates", type=int, default=600,
+                    help="untimed VES updates (100 MD steps each) run after the timed region before the FES RMSE is taken; 0 = skip")
     ap.add_argument("--seed", type=int, default=20221019)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -107,7 +109,8 @@ def make_bias(args, beta):
     d = args.basis - 1
     basis = LegendreBasis2D(d, d, *MINMAX)                      # w = 0 at start
     target = Target_WellTempered_2D(100, 100, bias_factor=10.0)
-    return VESBias_Ensemble(basis, target, beta, "averaged_sgd", {"mu": args.mu, "averaging": "ewma", "decay": 0.9},
+    return VESBias_Ensemble(basis, target, beta, "averaged_sgd",
+                            {"mu": args.mu, "averaging": "ewma", "decay": 0.8, "precondition": 1.0},
                             model_loc=None, target_update_every=10)
 
 
@@ -220,6 +223,18 @@ def run_ours(args):
         e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
                "h2d_bytes_per_step": state_bytes + K * 8, "d2h_bytes_per_step": state_bytes + (K + 1) * 8}
 
+    # ---- accuracy: continue the optimisation (untimed) and compare the FES with the analytic surface
+    fes_out = None
+    if args.fes_updates > 0:
+        for _ in range(args.fes_updates):
+            ens.step(100)
+            sw, sf, _ = reduce_moments(*ens.moments())
+            bias.update_from_moments(sw, sf)
+            bias.force.apply(ens)
+        if rank == 0:
+            fes_out = fes_rmse(bias, args)
+            fes_out["md_steps_total"] = (args.warmup + args.steps * (2 if not args.no_e2e else 1) + 1) * args.stride + 100 * args.fes_updates
+
     if rank == 0:
         flops = FLOPS_PER_WALKER_STEP.get(args.basis)
         roof = None
@@ -241,11 +256,36 @@ def run_ours(args):
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
         if e2e:
             out["e2e"] = e2e
+        if fes_out:
+            out["fes"] = fes_out
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args, seconds=12.0)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fes_rmse(bias, args):
+    """FES read-out F = -V - kT ln p on the target grid against the analytic surface
+    (x projection: ves/visualization.py:185-201; 2D: F = U), both restricted to F_ref <= 20 kT."""
+    from pyves_b200 import fes
+    from pyves_b200.potentials import DoubleWellPotential2D
+    kT = KB_PY * TEMP
+    pot = DoubleWellPotential2D()
+    m = bias.target.mesh[0]
+    F2 = bias.fes().reshape(bias.target.mesh) / kT
+    cx = MINMAX[0] + (MINMAX[1] - MINMAX[0]) * (np.arange(m) + 0.5) / m
+    cy = MINMAX[2] + (MINMAX[3] - MINMAX[2]) * (np.arange(bias.target.mesh[1]) + 0.5) / bias.target.mesh[1]
+    Fx = -np.log(np.exp(-(F2 - F2.min())).sum(1))
+    xs, F_ref = fes.projection_x(pot, TEMP, [-2.25, 2.25], [-2, 2])
+    rm_x = fes.rmse_kt(np.interp(xs, cx, Fx - Fx.min()), F_ref, clip=20.0)
+    gx, gy = np.meshgrid(cx, cy, indexing="ij")
+    U = pot.potential(gx, gy) / kT
+    U -= U.min()
+    sel = U <= 20
+    d = (F2 - F2[sel].min()) - U
+    return {"rmse_x_kt": rm_x, "rmse_2d_kt": float(np.sqrt(np.mean(d[sel] ** 2))), "unit": "kT",
+            "reference": "analytic F of DoubleWellPotential2D (x projection on a 200-point mesh; 2D surface), F_ref <= 20 kT"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -279,7 +319,7 @@ def cpu_iteration(cport, k, spec, opt, pos, vel, step0, stride, seed):
 def cpu_baseline(args, seconds=12.0):
     from oracle import ves
     cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.9)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.8)
     pos, vel = cpu_state(2048, k, args.seed)
     t = time.perf_counter()
     cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
@@ -301,7 +341,7 @@ def run_reference(args):
         return
     from oracle import ves
     cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.9)
+    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.8)
     pos, vel = cpu_state(2048, k, args.seed)
     t = time.perf_counter()
     cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)

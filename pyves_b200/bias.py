@@ -237,7 +237,8 @@ class VESBias_Ensemble(NNBias):
             of ``V_module`` (``Target_x`` family for 1D bases, ``Target_2D`` family for ``LegendreBasis2D``).
         beta: 1 / kT.
         optimizer_type: ``'averaged_sgd'`` (Bach-Moulines, ``optimizer_params`` = ``{'mu': .., 'second_order': bool,
-            'averaging': 'ewma' | 'running', 'decay': 0.9}``)
+            'averaging': 'ewma' | 'running', 'decay': 0.9, 'precondition': p}``; p > 0 scales the step of Legendre
+            coefficient k by (2k+1)^p, the inverse variance of P_k under the flat target)
             or ``'SGD'`` / ``'RMSprop'`` / ``'Adam'`` (``torch.optim`` on the textbook gradient).
         model_loc: TorchScript export path or None.
         target_update_every: refresh a well-tempered target every this many updates.
@@ -255,10 +256,18 @@ class VESBias_Ensemble(NNBias):
             if isinstance(V_module, NNBasis1D):
                 raise ValueError("averaged_sgd needs a linear basis expansion; use Adam / SGD / RMSprop for NNBasis1D")
             w = np.concatenate([p.detach().cpu().numpy().ravel() for p in V_module.parameters()])
+            scale = None
+            pw = float(optimizer_params.get('precondition', 0.0))      # exponent of the diagonal preconditioner
+            if pw:
+                if isinstance(V_module, LegendreBasis2D):
+                    scale = np.outer(2 * np.arange(V_module.degree_x + 1) + 1, 2 * np.arange(V_module.degree_y + 1) + 1).ravel()
+                else:
+                    scale = 2 * np.arange(V_module.degree + 1) + 1
+                scale = scale.astype(np.float64) ** pw
             self.optimizer = AveragedSGD(w, mu=optimizer_params.get('mu', 1.0),
                                          second_order=optimizer_params.get('second_order', False),
                                          averaging=optimizer_params.get('averaging', 'ewma'),
-                                         decay=optimizer_params.get('decay', 0.9))
+                                         decay=optimizer_params.get('decay', 0.9), scale=scale)
         else:
             self.optimizer = _make_torch_optimizer(optimizer_type, self.model.parameters(), optimizer_params)
         self.target_update_every = int(target_update_every)

@@ -311,13 +311,9 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
         if (kx == 8 && ky == 8)
           return run_fast<T, DW, BiasLegendre2DStatic<T, 8, 8>, 2, 1>(h, A, l2_static_params<T, 8, 8>(h), st);
         if (kx == 16 && ky == 16) {
-          switch (h->variant) {
-            case 1: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 3>(h, A, l2_static_params<T, 16, 16>(h), st);
-            case 2: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 2, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
-            case 3: return run_fast<T, DW, BiasLegendre2DSmem<T, 16>, 1, 1>(h, A, BP, st);
-            case 4: return run_fast<T, DW, BiasLegendre2DSmem<T, 16>, 2, 1>(h, A, BP, st);
-            default: return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
-          }
+          if (h->variant == 1)   // two rows interleaved (same speed on B200; kept for tuning runs)
+            return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16, 2>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
         }
         if (ky > 16 && ky <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
         if (ky > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);

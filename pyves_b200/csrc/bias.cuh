@@ -105,43 +105,55 @@ template <typename T, int KX, int KY> struct Legendre2DStaticParams {
   T w[KX * KY];
 };
 
-template <typename T, int KX, int KY> struct BiasLegendre2DStatic {
+// Packed evaluation: Q[j] = (P_j(y'), P'_j(y')) pairs, so that one packed FP32x2 FMA (FFMA2, with
+// the weight broadcast to both halves) updates (A_i, B_i) together.  ROWS rows are accumulated at a
+// time (2 * ROWS independent chains sharing the Q[j] operand).  Measured on B200 (profiles/): the
+// 16 x 16 kernel issues 533 instructions per walker-step instead of 748 with scalar FFMAs.
+template <typename T, int KX, int KY, int ROWS = 1> struct BiasLegendre2DStatic {
   using Params = Legendre2DStaticParams<T, KX, KY>;
+  static_assert(KX % ROWS == 0, "ROWS must divide KX");
   static size_t smem_bytes(const Params&) { return 0; }
   static PV_DEV void stage(const Params&, void*) {}
   template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
     bool inx, iny;
     const T sx = scale_clamp(x, P.cx, P.ihx, inx);
     const T sy = scale_clamp(y, P.cy, P.ihy, iny);
-    // Q[j] = (P_j(y'), P'_j(y')): one packed FMA per weight updates (A_i, B_i) together
     T Py[KY], dPy[KY];
     legendre_fill<T, KY>(sy, Py, dPy);
     Pair<T> Q[KY];
 #pragma unroll
     for (int j = 0; j < KY; ++j) Q[j] = Pair<T>::make(Py[j], dPy[j]);
-    Pair<T> G = Pair<T>::make(T(0), T(0));   // (dV/dsx, dV/dsy)
+    const Pair<T> zero = Pair<T>::make(T(0), T(0)), one = Pair<T>::make(T(1), T(1));
+    Pair<T> G = zero;   // (dV/dsx, dV/dsy)
     T E = T(0);
     T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
 #pragma unroll
-    for (int i = 0; i < KX; ++i) {
-      if (i == 1) {
-        px = sx;
-        dpx = T(1);
-      } else if (i >= 2) {
-        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
-        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
-        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
-      }
-      Pair<T> AB0 = Pair<T>::make(T(0), T(0)), AB1 = AB0;   // two chains per row for ILP
+    for (int i0 = 0; i0 < KX; i0 += ROWS) {
+      Pair<T> AB0[ROWS], AB1[ROWS];
 #pragma unroll
-      for (int j = 0; j < KY; j += 2) {
-        AB0 = Pair<T>::fma_bcast(Q[j], P.w[i * KY + j], AB0);
-        if (j + 1 < KY) AB1 = Pair<T>::fma_bcast(Q[j + 1], P.w[i * KY + j + 1], AB1);
+      for (int r = 0; r < ROWS; ++r) AB0[r] = AB1[r] = zero;
+#pragma unroll
+      for (int j = 0; j < KY; ++j)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          if (j & 1) AB1[r] = Pair<T>::fma_bcast(Q[j], P.w[(i0 + r) * KY + j], AB1[r]);
+          else AB0[r] = Pair<T>::fma_bcast(Q[j], P.w[(i0 + r) * KY + j], AB0[r]);
+        }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int i = i0 + r;
+        if (i == 1) {
+          px = sx;
+          dpx = T(1);
+        } else if (i >= 2) {
+          const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+          const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+          pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+        }
+        const Pair<T> AB = Pair<T>::fma(AB0[r], one, AB1[r]);
+        G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
+        if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
       }
-      const Pair<T> one = Pair<T>::make(T(1), T(1));
-      const Pair<T> AB = Pair<T>::fma(AB0, one, AB1);
-      G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
-      if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
     }
     gx += inx ? G.lo() * P.ihx : T(0);
     gy += iny ? G.hi() * P.ihy : T(0);

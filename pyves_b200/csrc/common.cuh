@@ -77,6 +77,18 @@ template <> struct Pair<double> {
   static PV_DEV Pair fma(Pair a, Pair b, Pair c) { return Pair{::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)}; }
 };
 
+// 128-bit broadcast load of loop-invariant coefficients from shared memory.  It is `asm volatile` on
+// purpose: the coefficients do not change during a launch, so the compiler would otherwise hoist all
+// of them out of the time loop and keep (then spill) hundreds of registers.
+PV_DEV void lds_vec(const float* p, float (&v)[4]) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+PV_DEV void lds_vec(const double* p, double (&v)[2]) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+}
+
 // Legendre recursion coefficients: P_{n+1} = A_n s P_n - B_n P_{n-1}, A_n = (2n+1)/(n+1),
 // B_n = n/(n+1); derivative P'_{n+1} = P'_{n-1} + C_n P_n, C_n = 2n+1  (ves/basis.py:111-112).
 template <typename T> PV_DEV constexpr T leg_a(int n) { return T(2 * n + 1) / T(n + 1); }

@@ -33,7 +33,7 @@ class AveragedSGD:
     the transient and is what the ensemble runs use.
     """
 
-    def __init__(self, alpha0, mu=1.0, second_order=False, averaging='running', decay=0.9):
+    def __init__(self, alpha0, mu=1.0, second_order=False, averaging='running', decay=0.9, scale=None):
         if averaging not in ('running', 'ewma'):
             raise ValueError("averaging must be 'running' or 'ewma'")
         self.alpha = np.array(alpha0, dtype=np.float64).ravel()
@@ -42,12 +42,18 @@ class AveragedSGD:
         self.second_order = bool(second_order)
         self.averaging = averaging
         self.decay = float(decay)
+        # optional diagonal preconditioner: per-coefficient step sizes mu * scale_k.  For Legendre bases
+        # scale_k = (2i+1)(2j+1) = 1 / Var_uniform(f_k) makes every mode relax at the same rate once the
+        # biased ensemble is close to the (flat) target.
+        self.scale = None if scale is None else np.array(scale, dtype=np.float64).ravel()
         self.n = 0
 
     def step(self, grad, hess=None):
         d = np.array(grad, dtype=np.float64)
         if self.second_order and hess is not None:
             d = d + hess @ (self.alpha - self.abar)
+        if self.scale is not None:
+            d = d * self.scale
         self.alpha = self.alpha - self.mu * d
         self.n += 1
         if self.averaging == 'ewma':

@@ -2,7 +2,7 @@
 """GPU run of BASELINE.json configs[1] to convergence: 2D double well, 16x16 Legendre bias, well-tempered
 target (gamma 10), averaged SGD; reports the FES RMSE (kT) of the x projection and of the 2D surface.
 
-usage: python tools/converge_cfg2.py [n_walkers] [n_updates] [stride] [mu]
+usage: python tools/converge_cfg2.py [n_walkers] [n_updates] [stride] [mu] [decay] [first|second] [mesh] [timestep_fs] [tag]
 """
 import json
 import os
@@ -28,12 +28,16 @@ def main():
     kT = 8.3145e-3 * 300
     pot = potentials.DoubleWellPotential2D()
     model = basis.LegendreBasis2D(15, 15, -2.5, 2.5, -2.0, 2.0)
-    tgt = target.Target_WellTempered_2D(100, 100, gamma)
+    mesh = int(sys.argv[7]) if len(sys.argv) > 7 else 100
+    tstep = float(sys.argv[8]) if len(sys.argv) > 8 else 10.0
+    tag = sys.argv[9] if len(sys.argv) > 9 else "run"
+    pre = float(sys.argv[10]) if len(sys.argv) > 10 else 1.0
+    tgt = target.Target_WellTempered_2D(mesh, mesh, gamma)
     decay = float(sys.argv[5]) if len(sys.argv) > 5 else 0.8
     second = len(sys.argv) > 6 and sys.argv[6] == "second"
-    b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd", {"mu": mu, "averaging": "ewma", "decay": decay, "second_order": second},
+    b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd", {"mu": mu, "averaging": "ewma", "decay": decay, "second_order": second, "precondition": pre},
                               target_update_every=10)
-    sim = SingleParticleSimulation(pot, n_walkers=n, seed=20221019)
+    sim = SingleParticleSimulation(pot, n_walkers=n, seed=20221019, timestep=tstep)
     sim.place_walkers(xmin=-2.5, xmax=2.5, ymin=-2, ymax=2)
     ens = sim.ens
     b.force.apply(ens)
@@ -41,20 +45,21 @@ def main():
     hist = []
     t0 = time.time()
     done = 0
-    for chunk in range(nup // 50):
-        for _ in range(50):
+    rep = max(50, nup // 10)
+    for chunk in range(nup // rep):
+        for _ in range(rep):
             ens.step(stride)
             sw, sf, sff = ens.moments(cov=second)
             b.update_from_moments(sw, sf, sff)
             b.force.apply(ens)
-        done += 50
+        done += rep
         # F(x, y) = -V - kT ln p on the target grid, then project on x
-        F2 = b.fes().reshape(100, 100) / kT
+        F2 = b.fes().reshape(mesh, mesh) / kT
         Fx = -np.log(np.exp(-(F2 - F2.min())).sum(1))
-        cx = -2.5 + 5.0 * (np.arange(100) + 0.5) / 100
+        cx = -2.5 + 5.0 * (np.arange(mesh) + 0.5) / mesh
         Fx_i = np.interp(xs, cx, Fx - Fx.min())
         rm = fes.rmse_kt(Fx_i, F_ref, clip=20.0)
-        gx, gy = np.meshgrid(cx, -2.0 + 4.0 * (np.arange(100) + 0.5) / 100, indexing="ij")
+        gx, gy = np.meshgrid(cx, -2.0 + 4.0 * (np.arange(mesh) + 0.5) / mesh, indexing="ij")
         U = pot.potential(gx, gy) / kT
         U -= U.min()
         m = U <= 20
@@ -63,7 +68,9 @@ def main():
         hist.append(dict(updates=done, md_steps=done * stride, rmse_x_kt=rm, rmse_2d_kt=rm2, wall_s=time.time() - t0))
         print(json.dumps(hist[-1]), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(dict(n_walkers=n, stride=stride, mu=mu, gamma=gamma, history=hist), open("gpurun_out/converge_cfg2.json", "w"), indent=1)
+    prof = dict(x=xs[::4].tolist(), F_est=(Fx_i - Fx_i.min())[::4].tolist(), F_ref=F_ref[::4].tolist())
+    json.dump(dict(n_walkers=n, stride=stride, mu=mu, gamma=gamma, decay=decay, second_order=second, mesh=mesh, timestep_fs=tstep,
+                   history=hist, profile_x=prof), open("gpurun_out/converge_cfg2_%s.json" % tag, "w"), indent=1)
 
 
 if __name__ == "__main__":
