@@ -272,7 +272,7 @@ def test_ensemble_second_order_slip_bond():
                               {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
     assert b.needs_covariance
     sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=32768, seed=3)
-    sim.place_walkers(xmin=-8, xmax=10, ymin=-6, ymax=8)
+    sim.place_walkers(ntrials=2000, xmin=-8, xmax=10, ymin=-6, ymax=8)   # acceptance ~3 % per draw
     sim.init_ves(b, startafter=200, learnevery=200)
     quiet(sim, nsteps=80001, chkevery=0, trajevery=0, energyevery=0, chkfile=None, trajfile=None, energyfile=None)
     x, Fx = fes.projection_x(pot, 300, [-3.0, 6.0], [-6, 8])
