@@ -291,6 +291,7 @@ def fes_rmse(bias, args):
 # ---------------------------------------------------------------------------------------------------
 def cpu_model(args, seed):
     from oracle import cport, langevin
+    cport.use_all_threads()
     k = langevin.constants()
     spec = dict(kind="leg2d", deg_x=args.basis - 1, deg_y=args.basis - 1, minmax=MINMAX,
                 weights=np.zeros((args.basis, args.basis)))

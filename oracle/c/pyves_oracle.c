@@ -226,6 +226,15 @@ int oracle_moments(const oracle_cfg* C, const double* pos, int64_t n, double* su
   return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use all host threads */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

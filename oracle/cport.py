@@ -99,3 +99,13 @@ class Model:
 
 def num_threads():
     return int(load().oracle_num_threads())
+
+
+def use_all_threads():
+    """Use every hardware thread this process may run on (launchers such as torchrun set OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().oracle_set_num_threads(n)
+    return num_threads()
