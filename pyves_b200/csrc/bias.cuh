@@ -187,7 +187,12 @@ template <typename T, int KYP> struct BiasLegendre2DSmem {
     const T sy = scale_clamp(y, P.cy, P.ihy, iny);
     T Py[KYP], dPy[KYP];
     legendre_fill<T, KYP>(sy, Py, dPy);
-    T ax = T(0), ay = T(0), E = T(0);
+    Pair<T> Q[KYP];                      // (P_j, P'_j): one packed FMA per weight, see BiasLegendre2DStatic
+#pragma unroll
+    for (int j = 0; j < KYP; ++j) Q[j] = Pair<T>::make(Py[j], dPy[j]);
+    const Pair<T> zero = Pair<T>::make(T(0), T(0)), one = Pair<T>::make(T(1), T(1));
+    Pair<T> G = zero;
+    T E = T(0);
     T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
     const Vec* row = reinterpret_cast<const Vec*>(smem);
     for (int i = 0; i < P.kx; ++i) {
@@ -200,30 +205,23 @@ template <typename T, int KYP> struct BiasLegendre2DSmem {
         const T dpn = Math<T>::fma(c, px, dpxm);
         pxm = px; px = pn; dpxm = dpx; dpx = dpn;
       }
-      T A0 = T(0), A1 = T(0), B0 = T(0), B1 = T(0);
+      Pair<T> AB0 = zero, AB1 = zero;
 #pragma unroll
       for (int jv = 0; jv < KYP / V; ++jv) {
         const Vec wv = row[jv];
 #pragma unroll
         for (int q = 0; q < V; ++q) {
-          const int j = jv * V + q;
-          if (q & 1) {
-            A1 = Math<T>::fma(wv.v[q], Py[j], A1);
-            B1 = Math<T>::fma(wv.v[q], dPy[j], B1);
-          } else {
-            A0 = Math<T>::fma(wv.v[q], Py[j], A0);
-            B0 = Math<T>::fma(wv.v[q], dPy[j], B0);
-          }
+          if (q & 1) AB1 = Pair<T>::fma_bcast(Q[jv * V + q], wv.v[q], AB1);
+          else AB0 = Pair<T>::fma_bcast(Q[jv * V + q], wv.v[q], AB0);
         }
       }
       row += KYP / V;
-      const T A = A0 + A1, B = B0 + B1;
-      ax = Math<T>::fma(dpx, A, ax);
-      ay = Math<T>::fma(px, B, ay);
-      if (WANT_E) E = Math<T>::fma(px, A, E);
+      const Pair<T> AB = Pair<T>::fma(AB0, one, AB1);
+      G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
+      if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
     }
-    gx += inx ? ax * P.ihx : T(0);
-    gy += iny ? ay * P.ihy : T(0);
+    gx += inx ? G.lo() * P.ihx : T(0);
+    gy += iny ? G.hi() * P.ihy : T(0);
     if (WANT_E) e += E;
   }
 };
@@ -298,42 +296,39 @@ template <typename T, int H, int ACT> struct BiasMlp {
       constexpr int HH = H > 0 ? H : 4;
       const Vec* uv = reinterpret_cast<const Vec*>(sm);
       const Vec* cv = reinterpret_cast<const Vec*>(sm + HH);
-      T h[HH], dh[HH];
+      Pair<T> HD[HH];                    // (h_i, dh_i/ds): one packed FMA per weight updates (z_j, dz_j/ds)
 #pragma unroll
       for (int iv = 0; iv < HH / V; ++iv) {
         const Vec u = uv[iv], c = cv[iv];
 #pragma unroll
         for (int q = 0; q < V; ++q) {
           T d;
-          h[iv * V + q] = act_fn<T, ACT>(Math<T>::fma(u.v[q], s, c.v[q]), d);
-          dh[iv * V + q] = d * u.v[q];
+          const T a = act_fn<T, ACT>(Math<T>::fma(u.v[q], s, c.v[q]), d);
+          HD[iv * V + q] = Pair<T>::make(a, d * u.v[q]);
         }
       }
       const T* wout = sm + 2 * HH;
       const T* b2 = sm + 3 * HH;
       const Vec* W = reinterpret_cast<const Vec*>(sm + 4 * HH);
+      const Pair<T> one = Pair<T>::make(T(1), T(1));
 #pragma unroll 2
       for (int j = 0; j < HH; ++j) {
-        T z0 = b2[j], z1 = T(0), d0 = T(0), d1 = T(0);
+        Pair<T> Z0 = Pair<T>::make(b2[j], T(0)), Z1 = Pair<T>::make(T(0), T(0));
 #pragma unroll
         for (int iv = 0; iv < HH / V; ++iv) {
           const Vec w = W[j * (HH / V) + iv];
 #pragma unroll
           for (int q = 0; q < V; ++q) {
-            if (q & 1) {
-              z1 = Math<T>::fma(w.v[q], h[iv * V + q], z1);
-              d1 = Math<T>::fma(w.v[q], dh[iv * V + q], d1);
-            } else {
-              z0 = Math<T>::fma(w.v[q], h[iv * V + q], z0);
-              d0 = Math<T>::fma(w.v[q], dh[iv * V + q], d0);
-            }
+            if (q & 1) Z1 = Pair<T>::fma_bcast(HD[iv * V + q], w.v[q], Z1);
+            else Z0 = Pair<T>::fma_bcast(HD[iv * V + q], w.v[q], Z0);
           }
         }
+        const Pair<T> Z = Pair<T>::fma(Z0, one, Z1);
         T d;
-        const T a = act_fn<T, ACT>(z0 + z1, d);
+        const T a = act_fn<T, ACT>(Z.lo(), d);
         const T wo = wout[j];
         val = Math<T>::fma(wo, a, val);
-        dval = Math<T>::fma(wo * d, d0 + d1, dval);
+        dval = Math<T>::fma(wo * d, Z.hi(), dval);
       }
     }
     const T g = dval * P.inv_range;
