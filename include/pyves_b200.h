@@ -154,7 +154,8 @@ int pyves_moments(pyves_t* h, const void* pos, int64_t n, int ncols, const void*
 int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim, int axis, const double* range,
                     const int* nbins, const void* row_weights, double* counts, int on_host, void* stream);
 
-/* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general kernel) */
+/* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel;
+ * 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed again) */
 int pyves_set_tuning(pyves_t* h, int variant);
 
 /* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */

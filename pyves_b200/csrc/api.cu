@@ -546,6 +546,10 @@ int pyves_get_step_counter(const pyves_t* h, int64_t* step) {
 
 int pyves_set_tuning(pyves_t* h, int variant) {
   if (!h) return PYVES_EINVAL;
+  if (variant == 98 || variant == 97) {   // 98: covariance on CUDA cores only; 97: tensor cores allowed again
+    set_no_tensor_cores(variant == 98);
+    return PYVES_OK;
+  }
   h->variant = variant;
   return PYVES_OK;
 }

@@ -309,8 +309,31 @@ size_t moments_scratch_doubles(int64_t K, bool cov) {
   const int npt = K64 * (K64 + 1) / 2;
   int g = kMaxBlocks / npt;
   if (g < 1) g = 1;
-  return first + (size_t)g * npt * kPairTile * kPairTile;
+  size_t total = first + (size_t)g * npt * kPairTile * kPairTile;
+  if (K > 128 && K <= 256) {   // room for the tensor-core path's per-CTA FP32 partials
+    const size_t tc = first + (cov_tc_scratch_floats(kMaxSmForScratch) + 1) / 2;
+    if (tc > total) total = tc;
+  }
+  return total;
 }
+
+template <typename T> struct TcDispatch {
+  static bool use(const RowSource<T>&, const BasisParams<T>&, int) { return false; }
+  static cudaError_t run(const RowSource<T>&, const BasisParams<T>&, double*, double*, int, cudaStream_t, int*) { return cudaErrorNotSupported; }
+};
+template <> struct TcDispatch<float> {
+  static bool use(const RowSource<float>& S, const BasisParams<float>& B, int n_sm) {
+    return n_sm <= kMaxSmForScratch && cov_tc_supported(S, B);
+  }
+  static cudaError_t run(const RowSource<float>& S, const BasisParams<float>& B, double* sum_wff, double* scratch, int n_sm,
+                         cudaStream_t st, int* launches) {
+    return launch_cov_tc(S, B, sum_wff, reinterpret_cast<float*>(scratch), n_sm, st, launches);
+  }
+};
+
+static bool g_no_tc = false;
+bool no_tensor_cores() { return g_no_tc; }
+void set_no_tensor_cores(bool v) { g_no_tc = v; }
 
 template <typename T>
 cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B, double* sum_w, double* sum_wf,
@@ -342,7 +365,13 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  if (sum_wff != nullptr) {
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (sum_wff != nullptr && !no_tensor_cores() && TcDispatch<T>::use(S, B, n_sm)) {
+    e = TcDispatch<T>::run(S, B, sum_wff, scratch + (size_t)kMaxBlocks * (K + 1), n_sm, st, launches);
+    if (e != cudaSuccess) return e;
+  } else if (sum_wff != nullptr) {
     constexpr int R = Tile<T>::kRows2;
     const int K64 = (K + kPairTile - 1) / kPairTile;
     const int npt = K64 * (K64 + 1) / 2;

@@ -42,6 +42,16 @@ template <typename T>
 cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B, double* sum_w, double* sum_wf,
                                  double* sum_wff, double* scratch, cudaStream_t st, int* launches);
 
+// tcgen05 / TF32 covariance (cov_tc.cu): used for FP32 handles, unit row weights, 2D Legendre bases with
+// 128 < K <= 256; everything else runs moments2_kernel on the CUDA cores.
+bool cov_tc_supported(const RowSource<float>& S, const BasisParams<float>& B);
+size_t cov_tc_scratch_floats(int n_sm);
+cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B, double* sum_wff, float* scratch, int n_sm,
+                          cudaStream_t st, int* launches);
+constexpr int kMaxSmForScratch = 160;
+bool no_tensor_cores();
+void set_no_tensor_cores(bool v);   // tuning / test switch: force the CUDA-core covariance
+
 template <typename T>
 cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M, double* sum_w, double* sum_wf,
                                double* scratch, cudaStream_t st, int* launches);

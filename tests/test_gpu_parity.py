@@ -411,3 +411,29 @@ def test_equilibrium_sampling_double_well_fes():
     assert abs(np.mean(x.astype(np.float64) ** 2) / (k["kT"] / 2) - 1) < 0.02
     assert abs(np.mean(v.astype(np.float64) ** 2) / k["kT"] - 1) < 0.02
     e.close()
+
+
+def test_covariance_tensor_core_path():
+    """K = 256 (16 x 16) covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM):
+    agrees with the FP64 oracle to TF32 rounding (2^-11 per factor, averaging out over rows) and with the
+    CUDA-core kernel; symmetric exactly; row 0 reproduces the first moments (f_0 = 1)."""
+    from oracle import ves
+    rng = np.random.default_rng(12)
+    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    for n in (31, 10007, 300000):
+        pos = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2.5, 2.5, n)], 1)
+        fr = biasspec.oracle_basis(spec, pos)
+        sw_r, sf_r, sff_r = ves.moments(fr)
+        e = biasspec.make_ensemble(n, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+        e.set_state(torch.tensor(pos.T.copy(), dtype=torch.float32, device=DEV), None)
+        sw, sf, sff = e.moments(cov=True)
+        sff = sff.cpu().numpy()
+        assert np.array_equal(sff, sff.T)
+        scale = np.sqrt(np.outer(np.diag(sff_r), np.diag(sff_r)))          # |C_kl| <= sqrt(C_kk C_ll)
+        assert np.max(np.abs(sff - sff_r) / scale) < 1e-3, n
+        assert np.max(np.abs(sff[0] - sf_r) / np.maximum(np.abs(fr).sum(0), 1.0)) < 1e-3
+        e.set_tuning(98)                                                    # same call on the CUDA cores
+        _, _, sff_cc = e.moments(cov=True)
+        e.set_tuning(97)
+        assert np.max(np.abs(sff_cc.cpu().numpy() - sff_r) / scale) < 1e-5
+        e.close()
