@@ -186,6 +186,18 @@ template <typename T, int KX, int KY> Legendre2DStaticParams<T, KX, KY> l2_stati
   return P;
 }
 
+template <typename T, int KX, int KY> Legendre2DStaticTParams<T, KX, KY> l2_static_t_params(const pyves_ctx* h) {
+  const Legendre2DSmemParams<T> S = l2_params<T>(h);
+  Legendre2DStaticTParams<T, KX, KY> P;
+  P.cx = S.cx;
+  P.ihx = S.ihx;
+  P.cy = S.cy;
+  P.ihy = S.ihy;
+  for (int i = 0; i < KX; ++i)
+    for (int j = 0; j < KY; ++j) P.wt[j * KX + i] = (T)h->l2_w[i * KY + j];
+  return P;
+}
+
 template <typename T> MlpParams<T> mlp_params(const pyves_ctx* h) {
   MlpParams<T> P;
   P.axis = h->mlp_axis;
@@ -308,12 +320,14 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
       const Legendre2DSmemParams<T> BP = l2_params<T>(h);
       if (pk == PYVES_POT_DOUBLE_WELL_2D) {
-        if (kx == 8 && ky == 8)
-          return run_fast<T, DW, BiasLegendre2DStatic<T, 8, 8>, 2, 1>(h, A, l2_static_params<T, 8, 8>(h), st);
+        // variant 1 selects the row-major functor (kept for tuning runs); default = column sweep
+        if (kx == 8 && ky == 8) {
+          if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 8, 8>, 2, 1>(h, A, l2_static_params<T, 8, 8>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8>, 2, 1>(h, A, l2_static_t_params<T, 8, 8>(h), st);
+        }
         if (kx == 16 && ky == 16) {
-          if (h->variant == 1)   // two rows interleaved (same speed on B200; kept for tuning runs)
-            return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16, 2>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
-          return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
+          if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
         }
         if (ky > 16 && ky <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
         if (ky > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);

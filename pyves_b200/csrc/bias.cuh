@@ -109,7 +109,7 @@ template <typename T, int KX, int KY> struct Legendre2DStaticParams {
 // the weight broadcast to both halves) updates (A_i, B_i) together.  ROWS rows are accumulated at a
 // time (2 * ROWS independent chains sharing the Q[j] operand).  Measured on B200 (profiles/): the
 // 16 x 16 kernel issues 533 instructions per walker-step instead of 748 with scalar FFMAs.
-template <typename T, int KX, int KY, int ROWS = 1> struct BiasLegendre2DStatic {
+template <typename T, int KX, int KY, int ROWS = 1, bool SPLIT = true> struct BiasLegendre2DStatic {
   using Params = Legendre2DStaticParams<T, KX, KY>;
   static_assert(KX % ROWS == 0, "ROWS must divide KX");
   static size_t smem_bytes(const Params&) { return 0; }
@@ -136,7 +136,7 @@ template <typename T, int KX, int KY, int ROWS = 1> struct BiasLegendre2DStatic 
       for (int j = 0; j < KY; ++j)
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-          if (j & 1) AB1[r] = Pair<T>::fma_bcast(Q[j], P.w[(i0 + r) * KY + j], AB1[r]);
+          if (SPLIT && (j & 1)) AB1[r] = Pair<T>::fma_bcast(Q[j], P.w[(i0 + r) * KY + j], AB1[r]);
           else AB0[r] = Pair<T>::fma_bcast(Q[j], P.w[(i0 + r) * KY + j], AB0[r]);
         }
 #pragma unroll
@@ -150,13 +150,73 @@ template <typename T, int KX, int KY, int ROWS = 1> struct BiasLegendre2DStatic 
           const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
           pxm = px; px = pn; dpxm = dpx; dpx = dpn;
         }
-        const Pair<T> AB = Pair<T>::fma(AB0[r], one, AB1[r]);
+        const Pair<T> AB = SPLIT ? Pair<T>::fma(AB0[r], one, AB1[r]) : AB0[r];
         G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
         if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
       }
     }
     gx += inx ? G.lo() * P.ihx : T(0);
     gy += iny ? G.hi() * P.ihy : T(0);
+    if (WANT_E) e += E;
+  }
+};
+
+// Column sweep ("j-outer") evaluation of the same sum, the default for the static sizes: the y
+// recursion yields Q_j = (P_j(y'), P'_j(y')) and every Q_j updates all KX row accumulators
+// (A_i, B_i) += w_ij Q_j with one packed FP32x2 FMA each (FFMA2, weight broadcast to both halves).
+//  * KX independent accumulation chains: no dependent-issue waits inside the contraction;
+//  * the weights of one column are contiguous (wt[j][i]) in the constant bank;
+//  * no FADD2 to merge split chains, no spills at 255 registers.
+// Measured on B200, 16 x 16, 10^6 walkers x 500 steps: 11.77 ms against 12.6-13.0 ms for the
+// row-major functor above (profiles/r01_variants.md).
+template <typename T, int KX, int KY> struct Legendre2DStaticTParams {
+  T cx, ihx, cy, ihy;
+  T wt[KY * KX];   // wt[j * KX + i] = w_ij
+};
+
+template <typename T, int KX, int KY> struct BiasLegendre2DStaticT {
+  using Params = Legendre2DStaticTParams<T, KX, KY>;
+  static_assert(KX >= 2 && KY >= 2, "static sizes start at 2 x 2");
+  static size_t smem_bytes(const Params&) { return 0; }
+  static PV_DEV void stage(const Params&, void*) {}
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    Pair<T> AB[KX];
+    // columns 0 and 1: Q_0 = (1, 0), Q_1 = (sy, 1)
+    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+    {
+      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
+#pragma unroll
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
+    }
+#pragma unroll
+    for (int j = 2; j < KY; ++j) {
+      const T pn = leg_a<T>(j - 1) * sy * p - leg_b<T>(j - 1) * pm;
+      const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
+      pm = p; p = pn; dpm = dp; dp = dpn;
+      const Pair<T> Q = Pair<T>::make(p, dp);
+#pragma unroll
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
+    }
+    // row sweep: (dV/dsx, dV/dsy) = sum_i (P'_i(x'), P_i(x')) * (A_i, B_i), two chains
+    Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));
+    T E = WANT_E ? AB[0].lo() : T(0);
+    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
+#pragma unroll
+    for (int i = 1; i < KX; ++i) {
+      if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G1);
+      else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G0);
+      if (WANT_E) E = Math<T>::fma(px, AB[i].lo(), E);
+    }
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
     if (WANT_E) e += E;
   }
 };

@@ -66,6 +66,11 @@ template <> struct Pair<float> {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
     return d;
   }
+  // acc += a * w in place (the accumulator is tied to one register pair)
+  static PV_DEV void acc_bcast(Pair& acc, Pair a, float w) {
+    const Pair ww = make(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(ww.v));
+  }
 };
 
 template <> struct Pair<double> {
@@ -75,6 +80,7 @@ template <> struct Pair<double> {
   PV_DEV double hi() const { return y; }
   static PV_DEV Pair fma_bcast(Pair a, double w, Pair c) { return Pair{::fma(a.x, w, c.x), ::fma(a.y, w, c.y)}; }
   static PV_DEV Pair fma(Pair a, Pair b, Pair c) { return Pair{::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)}; }
+  static PV_DEV void acc_bcast(Pair& acc, Pair a, double w) { acc.x = ::fma(a.x, w, acc.x); acc.y = ::fma(a.y, w, acc.y); }
 };
 
 // 128-bit broadcast load of loop-invariant coefficients from shared memory.  It is `asm volatile` on

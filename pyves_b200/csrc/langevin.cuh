@@ -38,7 +38,11 @@ template <typename T> struct StepArgs {
 // Fast path: 2 simulated dimensions, OpenMM Langevin scheme, WPT walkers per thread, at least
 // MINB resident blocks per SM (register cap).  One
 // Philox4x32-10 call yields two Box-Muller pairs = the noise of two consecutive steps.
-template <typename T, class Pot, class Bias, int WPT, int MINB>
+// INJECT selects the noise source at compile time (injected draws for the parity tests, Philox
+// otherwise): with no branch inside the time loop the whole two-step body is one basic block, so
+// ptxas interleaves the integer Philox rounds and the MUFU chain of Box-Muller with the FMA stream
+// of the bias instead of running them back to back.
+template <typename T, class Pot, class Bias, int WPT, int MINB, bool INJECT>
 __global__ void __launch_bounds__(kStepThreads, MINB)
 langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotParams<T> PP,
                   const typename Bias::Params BP, const RngKeys K) {
@@ -72,7 +76,7 @@ langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotPar
   };
   // noise of steps 2c and 2c+1 for walker k
   auto draw = [&](int k, int64_t t_even, T (&z)[4]) {
-    if (A.noise != nullptr) {
+    if (INJECT) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int64_t ts = t_even + (q >> 1) - A.step0;
@@ -236,7 +240,8 @@ cudaError_t launch_langevin_general(const StepArgs<T>& A, const IntegratorParams
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 cudaError_t launch_langevin2d_impl(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
                                    const typename Bias::Params& BP, const RngKeys& K, cudaStream_t st) {
-  auto kern = langevin2d_kernel<T, Pot, Bias, WPT, MINB>;
+  auto kern = A.noise != nullptr ? langevin2d_kernel<T, Pot, Bias, WPT, MINB, true>
+                                 : langevin2d_kernel<T, Pot, Bias, WPT, MINB, false>;
   const size_t sm = Bias::smem_bytes(BP);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -26,7 +26,8 @@ PV_FAST(PotDoubleWell2D<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
-PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16 PV_COMMA 2>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 #elif PV_GROUP == 1  // slip bond, Szabo-Berezhkovskii
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 64>, 1, 1)

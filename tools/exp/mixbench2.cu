@@ -1,0 +1,68 @@
+// Micro-benchmark 2: the 16-accumulator column sweep  AB[i] += w[j][i] * Q[j]  with the weights coming
+// from (0) kernel params = constant bank (compiler picks UR / LDC), (1) shared memory LDS.128.
+#include <cstdio>
+#include <cuda_runtime.h>
+struct W { float w[256]; };
+__device__ __forceinline__ void f2b(unsigned long long& acc, unsigned long long q, float w) {
+  unsigned long long ww;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(q), "l"(ww));
+}
+template <int SRC, int NQ> __global__ void __launch_bounds__(128) k(float* out, const W P, float a, int iters) {
+  __shared__ __align__(16) float sw[256];
+  for (int i = threadIdx.x; i < 256; i += 128) sw[i] = P.w[i];
+  __syncthreads();
+  unsigned long long AB[16], Q[NQ];
+  for (int i = 0; i < 16; ++i) AB[i] = i;
+  for (int j = 0; j < NQ; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(Q[j]) : "f"(a + j), "f"(a * j));
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (SRC == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f2b(AB[i], Q[j % NQ], P.w[j * 16 + i]);
+      } else {
+#pragma unroll
+        for (int iv = 0; iv < 4; ++iv) {
+          float4 w;
+          const unsigned ad = (unsigned)__cvta_generic_to_shared(&sw[j * 16 + iv * 4]);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(ad));
+          f2b(AB[iv * 4 + 0], Q[j % NQ], w.x); f2b(AB[iv * 4 + 1], Q[j % NQ], w.y);
+          f2b(AB[iv * 4 + 2], Q[j % NQ], w.z); f2b(AB[iv * 4 + 3], Q[j % NQ], w.w);
+        }
+      }
+    }
+  }
+  unsigned long long s = 0;
+  for (int i = 0; i < 16; ++i) s += AB[i];
+  if (s == 12345) out[0] = 1.f;
+}
+template <int SRC, int NQ> void run(const char* name, int bps) {
+  float* out; cudaMalloc(&out, 4);
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  W P; for (int i = 0; i < 256; ++i) P.w[i] = 1e-3f * i;
+  const int iters = 2000, blocks = sms * bps, threads = 128;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    k<SRC, NQ><<<blocks, threads>>>(out, P, 0.5f, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best) best = ms;
+  }
+  const double warps_per_sched = (double)bps;   // 128 threads = 4 warps = 1 per scheduler per block
+  const double cyc = best * 1e-3 * 1.965e9 / (iters * warps_per_sched);
+  printf("%-24s blocks/SM %d: %7.3f ms  cycles per 256-FFMA2 sweep per warp %.1f (ideal 512) -> %.3f\n", name, bps, best, cyc, 512 / cyc);
+  cudaFree(out);
+}
+int main() {
+  run<0, 16>("const-bank, 16 Q", 2);
+  run<0, 16>("const-bank, 16 Q", 4);
+  run<0, 1>("const-bank, 1 Q", 2);
+  run<0, 1>("const-bank, 1 Q", 4);
+  run<1, 16>("LDS.128, 16 Q", 2);
+  run<1, 16>("LDS.128, 16 Q", 4);
+  run<1, 1>("LDS.128, 1 Q", 4);
+  return 0;
+}
