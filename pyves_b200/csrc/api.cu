@@ -329,12 +329,12 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
           if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
           return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
         }
-        if (ky > 16 && ky <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
-        if (ky > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);
+        if (kx > 16 && kx <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 1, 5>, 1, 2>(h, A, BP, st);
+        if (kx > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 2, 5>, 1, 2>(h, A, BP, st);
       }
-      if (ky <= 16) return run_fast<T, GP, BiasLegendre2DSmem<T, 16>, 1, 1>(h, A, BP, st);
-      if (ky <= 32) return run_fast<T, GP, BiasLegendre2DSmem<T, 32>, 1, 1>(h, A, BP, st);
-      return run_fast<T, GP, BiasLegendre2DSmem<T, 64>, 1, 1>(h, A, BP, st);
+      if (kx <= 16) return run_fast<T, GP, BiasLegendre2DSmem<T, 16, 1, 7>, 1, 3>(h, A, BP, st);
+      if (kx <= 32) return run_fast<T, GP, BiasLegendre2DSmem<T, 32, 1, 5>, 1, 2>(h, A, BP, st);
+      return run_fast<T, GP, BiasLegendre2DSmem<T, 32, 2, 5>, 1, 2>(h, A, BP, st);
     }
     case PYVES_BIAS_MLP_1D: {
       const MlpParams<T> BP = mlp_params<T>(h);

@@ -221,67 +221,109 @@ template <typename T, int KX, int KY> struct BiasLegendre2DStaticT {
   }
 };
 
-// Runtime sizes (kx, ky <= KYP): weights zero-padded to [kx][KYP] in shared memory, read with
-// 128-bit broadcast loads; the loop over i is a runtime loop with the x recursion on the fly.
+// Runtime sizes: column sweep with the weights in shared memory.  Rows are handled in NRB blocks of RB
+// (kx <= RB * NRB); per row block the weights are transposed and zero-padded to wt[rb][kyp][RB]
+// (kyp = 2 + roundup(ky - 2, UNR)) and read with 128-bit broadcast loads.  A rolled loop over the
+// columns, UNR per trip, keeps RB accumulator pairs and one column of weights live (no spills, two to
+// three blocks per SM); each row block repeats the cheap y recursion.  Measured on B200 (FP32, 10^6
+// walkers): 32 x 32 1.25e10 walker-steps/s (0.80 of the FMA peak; the row-major version reached
+// 0.53), 64 x 64 0.75 (0.57), runtime 16 x 16 0.73 (0.48).
 template <typename T> struct Legendre2DSmemParams {
   T cx, ihx, cy, ihy;
   int kx, ky;
   const T* w;   // device, row-major [kx][ky]
 };
 
-template <typename T, int KYP> struct BiasLegendre2DSmem {
+template <typename T, int RB, int NRB, int UNR> struct BiasLegendre2DSmem {
   using Params = Legendre2DSmemParams<T>;
-  static size_t smem_bytes(const Params& P) { return (size_t)P.kx * KYP * sizeof(T); }
+  static constexpr int V = 16 / sizeof(T);   // elements per 128-bit load
+  static __host__ __device__ int kyp(int ky) { return 2 + (ky > 2 ? (ky - 2 + UNR - 1) / UNR * UNR : 0); }
+  static __host__ __device__ int nrb(int kx) { return (kx + RB - 1) / RB; }
+  static size_t smem_bytes(const Params& P) { return (size_t)kyp(P.ky) * (nrb(P.kx) * RB + 4) * sizeof(T); }
   static PV_DEV void stage(const Params& P, void* smem) {
-    T* w = reinterpret_cast<T*>(smem);
-    for (int idx = threadIdx.x; idx < P.kx * KYP; idx += blockDim.x) {
-      const int i = idx / KYP, j = idx % KYP;
-      w[idx] = j < P.ky ? P.w[i * P.ky + j] : T(0);
+    T* wt = reinterpret_cast<T*>(smem);
+    const int n = kyp(P.ky), nb = nrb(P.kx);
+    for (int idx = threadIdx.x; idx < nb * n * RB; idx += blockDim.x) {
+      const int r = idx % RB, j = (idx / RB) % n, i = (idx / (RB * n)) * RB + r;
+      wt[idx] = (i < P.kx && j < P.ky) ? P.w[i * P.ky + j] : T(0);
+    }
+    T* co = wt + nb * n * RB;   // co[4 j + {0, 1, 2}] = A_{j-1}, B_{j-1}, C_{j-1}: P_j from P_{j-1}, P_{j-2}
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const T fn = T(j > 0 ? j - 1 : 0);
+      co[4 * j + 0] = (T(2) * fn + T(1)) / (fn + T(1));
+      co[4 * j + 1] = fn / (fn + T(1));
+      co[4 * j + 2] = T(2) * fn + T(1);
+      co[4 * j + 3] = T(0);
     }
   }
   template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
-    constexpr int V = 16 / sizeof(T);   // elements per 128-bit load
-    struct alignas(16) Vec { T v[V]; };
     bool inx, iny;
     const T sx = scale_clamp(x, P.cx, P.ihx, inx);
     const T sy = scale_clamp(y, P.cy, P.ihy, iny);
-    T Py[KYP], dPy[KYP];
-    legendre_fill<T, KYP>(sy, Py, dPy);
-    Pair<T> Q[KYP];                      // (P_j, P'_j): one packed FMA per weight, see BiasLegendre2DStatic
-#pragma unroll
-    for (int j = 0; j < KYP; ++j) Q[j] = Pair<T>::make(Py[j], dPy[j]);
-    const Pair<T> zero = Pair<T>::make(T(0), T(0)), one = Pair<T>::make(T(1), T(1));
-    Pair<T> G = zero;
+    const int n = kyp(P.ky), nb = nrb(P.kx);
+    const T* co = reinterpret_cast<const T*>(smem) + nb * n * RB;
+    Pair<T> G0 = Pair<T>::make(T(0), T(0)), G1 = G0;   // (dV/dsx, dV/dsy), two chains
     T E = T(0);
     T pxm = T(1), px = T(1), dpxm = T(0), dpx = T(0);
-    const Vec* row = reinterpret_cast<const Vec*>(smem);
-    for (int i = 0; i < P.kx; ++i) {
-      if (i == 1) {
-        px = sx;
-        dpx = T(1);
-      } else if (i >= 2) {
-        const T fn = T(i - 1), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
-        const T pn = (c * sx * px - fn * pxm) * inv;
-        const T dpn = Math<T>::fma(c, px, dpxm);
-        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
-      }
-      Pair<T> AB0 = zero, AB1 = zero;
 #pragma unroll
-      for (int jv = 0; jv < KYP / V; ++jv) {
-        const Vec wv = row[jv];
+    for (int rb = 0; rb < NRB; ++rb) {
+      if (rb < nb) {
+        const T* wt = reinterpret_cast<const T*>(smem) + rb * n * RB;
+        Pair<T> AB[RB];
+        // columns 0 and 1: Q_0 = (1, 0), Q_1 = (sy, 1)
+        T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+        {
+          const Pair<T> Q1 = Pair<T>::make(sy, T(1));
 #pragma unroll
-        for (int q = 0; q < V; ++q) {
-          if (q & 1) AB1 = Pair<T>::fma_bcast(Q[jv * V + q], wv.v[q], AB1);
-          else AB0 = Pair<T>::fma_bcast(Q[jv * V + q], wv.v[q], AB0);
+          for (int iv = 0; iv < RB / V; ++iv) {
+            T w0[V], w1[V];
+            lds_vec(wt + iv * V, w0);
+            lds_vec(wt + RB + iv * V, w1);
+#pragma unroll
+            for (int q = 0; q < V; ++q) AB[iv * V + q] = Pair<T>::fma_bcast(Q1, w1[q], Pair<T>::make(w0[q], T(0)));
+          }
+        }
+#pragma unroll 1
+        for (int j0 = 2; j0 < n; j0 += UNR) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u;
+            T c[V];
+            lds_vec(co + 4 * j, c);
+            const T cc = sizeof(T) == 4 ? c[2] : T(2 * j - 1);   // FP64: the 128-bit load holds A, B only
+            const T pn = c[0] * sy * p - c[1] * pm;
+            const T dpn = Math<T>::fma(cc, p, dpm);
+            pm = p; p = pn; dpm = dp; dp = dpn;
+            const Pair<T> Q = Pair<T>::make(p, dp);
+#pragma unroll
+            for (int iv = 0; iv < RB / V; ++iv) {
+              T w[V];
+              lds_vec(wt + j * RB + iv * V, w);
+#pragma unroll
+              for (int q = 0; q < V; ++q) Pair<T>::acc_bcast(AB[iv * V + q], Q, w[q]);
+            }
+          }
+        }
+        // row sweep over this block, continuing the x recursion
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int i = rb * RB + r;
+          if (i == 1) {
+            px = sx;
+            dpx = T(1);
+          } else if (i >= 2) {
+            const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+            const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+            pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+          }
+          if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[r], G1);
+          else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[r], G0);
+          if (WANT_E) E = Math<T>::fma(px, AB[r].lo(), E);
         }
       }
-      row += KYP / V;
-      const Pair<T> AB = Pair<T>::fma(AB0, one, AB1);
-      G = Pair<T>::fma(Pair<T>::make(dpx, px), AB, G);
-      if (WANT_E) E = Math<T>::fma(px, AB.lo(), E);
     }
-    gx += inx ? G.lo() * P.ihx : T(0);
-    gy += iny ? G.hi() * P.ihy : T(0);
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
     if (WANT_E) e += E;
   }
 };

@@ -143,7 +143,7 @@ template <typename T> struct BiasAnyParams {
 template <typename T> struct BiasAny {
   using Params = BiasAnyParams<T>;
   using L1 = BiasLegendre1D<T, 0>;
-  using L2 = BiasLegendre2DSmem<T, 64>;
+  using L2 = BiasLegendre2DSmem<T, 32, 2, 5>;
   using Ot = BiasOther<T>;
   static size_t smem_bytes(const Params& P) {
     if (P.kind == PYVES_BIAS_LEGENDRE_2D) return L2::smem_bytes(P.l2);

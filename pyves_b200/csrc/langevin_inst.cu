@@ -29,8 +29,8 @@ PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 #elif PV_GROUP == 1  // slip bond, Szabo-Berezhkovskii
-PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32>, 1, 1)
-PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 64>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)
 PV_FAST(PotSlipBond2D<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12>, 2, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasNone<T>, 2, 1)
@@ -39,9 +39,9 @@ PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_RELU>
 #elif PV_GROUP == 2  // any potential x each bias family
 PV_FAST(PotGeneric<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 2, 1)
-PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 16>, 1, 1)
-PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32>, 1, 1)
-PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 64>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 16 PV_COMMA 1 PV_COMMA 7>, 1, 3)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
+PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasOther<T>, 1, 1)
 #elif PV_GROUP == 3  // any potential x MLP widths; the general kernel
 PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)

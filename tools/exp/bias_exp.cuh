@@ -4,69 +4,6 @@
 
 namespace pv {
 
-// j-outer ("column sweep") evaluation: the y recursion produces Q_j = (P_j(y'), P'_j(y')) one at
-// a time and every Q_j immediately updates all KX row accumulators (A_i, B_i) += w_ij Q_j, so
-//  * there are KX independent FFMA2 chains (no dependent-issue waits),
-//  * the Q_j never have to be live together (KX pairs of accumulators instead of KY pairs of Q),
-//  * the weights of one column are contiguous (wt[j][i]): four 128-bit uniform loads per column.
-// Row i = 0 (P_0(x) = 1, P'_0(x) = 0) only needs B_0 and column j = 0 (Q_0 = (1, 0)) only feeds
-// the A_i: both are done with scalar FMAs.
-template <typename T, int KX, int KY> struct Legendre2DStaticTParams {
-  T cx, ihx, cy, ihy;
-  T wt[KY * KX];   // wt[j * KX + i] = w_ij
-};
-
-template <typename T, int KX, int KY, int GCH = 2> struct BiasLegendre2DStaticT {
-  using Params = Legendre2DStaticTParams<T, KX, KY>;
-  static size_t smem_bytes(const Params&) { return 0; }
-  static PV_DEV void stage(const Params&, void*) {}
-  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
-    bool inx, iny;
-    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
-    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
-    Pair<T> AB[KX];
-    // column 1: Q_1 = (sy, 1);  column 0 contributes (w_i0, 0)
-    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
-    {
-      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
-#pragma unroll
-      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
-    }
-#pragma unroll
-    for (int j = 2; j < KY; ++j) {
-      const T pn = leg_a<T>(j - 1) * sy * p - leg_b<T>(j - 1) * pm;
-      const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
-      pm = p; p = pn; dpm = dp; dp = dpn;
-      const Pair<T> Q = Pair<T>::make(p, dp);
-#pragma unroll
-      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
-    }
-    // x sweep: G = sum_i (P'_i(x), P_i(x)) * (A_i, B_i)
-    Pair<T> G[GCH];
-    G[0] = Pair<T>::make(T(0), AB[0].hi());          // i = 0: (0, 1) * (A_0, B_0)
-#pragma unroll
-    for (int c = 1; c < GCH; ++c) G[c] = Pair<T>::make(T(0), T(0));
-    T E = WANT_E ? AB[0].lo() : T(0);
-    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
-#pragma unroll
-    for (int i = 1; i < KX; ++i) {
-      if (i >= 2) {
-        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
-        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
-        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
-      }
-      G[i % GCH] = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G[i % GCH]);
-      if (WANT_E) E = Math<T>::fma(px, AB[i].lo(), E);
-    }
-    T glo = G[0].lo(), ghi = G[0].hi();
-#pragma unroll
-    for (int c = 1; c < GCH; ++c) { glo += G[c].lo(); ghi += G[c].hi(); }
-    gx += inx ? glo * P.ihx : T(0);
-    gy += iny ? ghi * P.ihy : T(0);
-    if (WANT_E) e += E;
-  }
-};
-
 // Rolled column sweep: a runtime loop over the columns j (UNR columns per trip) keeps the register
 // footprint small (KX accumulator pairs + one column of weights), so 3-4 blocks of 128 threads fit
 // per SM.  SRC = 0: weights read from the constant bank with a register index (LDC.128);
@@ -139,6 +76,96 @@ template <typename T, int KX, int KY, int UNR, int SRC> struct BiasLegendre2DRol
     }
     gx += inx ? (G[0].lo() + G[1].lo()) * P.ihx : T(0);
     gy += iny ? (G[0].hi() + G[1].hi()) * P.ihy : T(0);
+    if (WANT_E) e += E;
+  }
+};
+
+// Column sweep for runtime sizes: weights transposed and zero-padded to wt[kyp][KXP] in shared memory
+// (kyp = 2 + roundup(ky - 2, UNR)), recursion coefficients in shared memory as well.  A rolled loop
+// over the columns (UNR per trip) keeps KXP accumulator pairs + UNR * 4 weights live.
+template <typename T> struct Legendre2DSmemTParams {
+  T cx, ihx, cy, ihy;
+  int kx, ky;
+  const T* w;   // device, row-major [kx][ky]
+};
+
+template <typename T, int KXP, int UNR> struct BiasLegendre2DSmemT {
+  using Params = Legendre2DSmemTParams<T>;
+  static constexpr int V = 16 / sizeof(T);
+  static __host__ __device__ int kyp(int ky) { return 2 + (ky > 2 ? (ky - 2 + UNR - 1) / UNR * UNR : 0); }
+  static size_t smem_bytes(const Params& P) { return (size_t)kyp(P.ky) * (KXP + 4) * sizeof(T); }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    T* wt = reinterpret_cast<T*>(smem);
+    const int n = kyp(P.ky);
+    for (int idx = threadIdx.x; idx < n * KXP; idx += blockDim.x) {
+      const int j = idx / KXP, i = idx % KXP;
+      wt[idx] = (i < P.kx && j < P.ky) ? P.w[i * P.ky + j] : T(0);
+    }
+    T* co = wt + n * KXP;   // co[4 j + {0,1,2}] = a_{j-1}, b_{j-1}, c_{j-1}: P_j from P_{j-1}, P_{j-2}
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const T fn = T(j > 0 ? j - 1 : 0);
+      co[4 * j + 0] = (T(2) * fn + T(1)) / (fn + T(1));
+      co[4 * j + 1] = fn / (fn + T(1));
+      co[4 * j + 2] = T(2) * fn + T(1);
+      co[4 * j + 3] = T(0);
+    }
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    const T* wt = reinterpret_cast<const T*>(smem);
+    const int n = kyp(P.ky);
+    const T* co = wt + n * KXP;
+    Pair<T> AB[KXP];
+    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+    {
+      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
+#pragma unroll
+      for (int iv = 0; iv < KXP / V; ++iv) {
+        T w0[V], w1[V];
+        lds_vec(wt + iv * V, w0);
+        lds_vec(wt + KXP + iv * V, w1);
+#pragma unroll
+        for (int q = 0; q < V; ++q) AB[iv * V + q] = Pair<T>::fma_bcast(Q1, w1[q], Pair<T>::make(w0[q], T(0)));
+      }
+    }
+#pragma unroll 1
+    for (int j0 = 2; j0 < n; j0 += UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u;
+        T c[V];
+        lds_vec(co + 4 * j, c);
+        const T pn = c[0] * sy * p - c[1] * pm;
+        const T dpn = Math<T>::fma(sizeof(T) == 4 ? c[2] : T(2 * j - 1), p, dpm);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+        const Pair<T> Q = Pair<T>::make(p, dp);
+#pragma unroll
+        for (int iv = 0; iv < KXP / V; ++iv) {
+          T w[V];
+          lds_vec(wt + j * KXP + iv * V, w);
+#pragma unroll
+          for (int q = 0; q < V; ++q) Pair<T>::acc_bcast(AB[iv * V + q], Q, w[q]);
+        }
+      }
+    }
+    Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));
+    T E = WANT_E ? AB[0].lo() : T(0);
+    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
+#pragma unroll
+    for (int i = 1; i < KXP; ++i) {
+      if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G1);
+      else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G0);
+      if (WANT_E) E = Math<T>::fma(px, AB[i].lo(), E);
+    }
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
     if (WANT_E) e += E;
   }
 };
