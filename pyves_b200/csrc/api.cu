@@ -695,7 +695,7 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
         for (int j = 0; j < h2; ++j) {
           packed[2 * H + j] = Wo[j];
           packed[3 * H + j] = b2[j];
-          for (int i = 0; i < h1; ++i) packed[4 * H + (size_t)j * H + i] = W2[j * h1 + i];
+          for (int i = 0; i < h1; ++i) packed[4 * H + (size_t)i * H + j] = W2[j * h1 + i];   // transposed: W2T[i][j]
         }
         h->mlp_bout = theta[boff[3]];
         h->mlp_H = H;

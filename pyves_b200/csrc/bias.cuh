@@ -336,7 +336,7 @@ template <typename T, int RB, int NRB, int UNR> struct BiasLegendre2DSmem {
 //   H == 0 : two hidden layers (no matmul left after folding), any width (padded to 4):
 //            streamed, no per-thread arrays.       shared (T): u[W] c[W] wout[W]
 //   H  > 0 : three hidden layers = one H x H matmul, widths padded to H.
-//                                                  shared (T): u[H] c[H] wout[H] b2[H] W2[H][H]
+//                                                  shared (T): u[H] c[H] wout[H] b2[H] W2T[H][H]  (W2T[i][j] = W2[j][i])
 // A single hidden layer is the reference's degenerate linear case V = u0 s + bout.
 template <typename T> struct MlpParams {
   int axis;
@@ -395,42 +395,50 @@ template <typename T, int H, int ACT> struct BiasMlp {
         }
       }
     } else {
+      // input sweep: every hidden unit i of the folded first layer is evaluated once, (h_i, dh_i/ds),
+      // and immediately feeds all HH outputs (z_j, dz_j/ds) += W2[j][i] * (h_i, dh_i/ds): HH independent
+      // FFMA2 chains, the transposed weights W2T[i][.] come as 128-bit shared-memory broadcasts.
       constexpr int HH = H > 0 ? H : 4;
-      const Vec* uv = reinterpret_cast<const Vec*>(sm);
-      const Vec* cv = reinterpret_cast<const Vec*>(sm + HH);
-      Pair<T> HD[HH];                    // (h_i, dh_i/ds): one packed FMA per weight updates (z_j, dz_j/ds)
+      const T* b2 = sm + 3 * HH;
+      const T* WT = sm + 4 * HH;
+      Pair<T> Z[HH];
 #pragma unroll
-      for (int iv = 0; iv < HH / V; ++iv) {
-        const Vec u = uv[iv], c = cv[iv];
+      for (int jv = 0; jv < HH / V; ++jv) {
+        T b[V];
+        lds_vec(b2 + jv * V, b);
+#pragma unroll
+        for (int q = 0; q < V; ++q) Z[jv * V + q] = Pair<T>::make(b[q], T(0));
+      }
+#pragma unroll 1
+      for (int i0 = 0; i0 < HH; i0 += V) {
+        T u[V], c[V];
+        lds_vec(sm + i0, u);
+        lds_vec(sm + HH + i0, c);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          T d;
+          const T a = act_fn<T, ACT>(Math<T>::fma(u[k], s, c[k]), d);
+          const Pair<T> HD = Pair<T>::make(a, d * u[k]);
+#pragma unroll
+          for (int jv = 0; jv < HH / V; ++jv) {
+            T w[V];
+            lds_vec(WT + (i0 + k) * HH + jv * V, w);
+#pragma unroll
+            for (int q = 0; q < V; ++q) Pair<T>::acc_bcast(Z[jv * V + q], HD, w[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int jv = 0; jv < HH / V; ++jv) {
+        T wo[V];
+        lds_vec(sm + 2 * HH + jv * V, wo);
 #pragma unroll
         for (int q = 0; q < V; ++q) {
           T d;
-          const T a = act_fn<T, ACT>(Math<T>::fma(u.v[q], s, c.v[q]), d);
-          HD[iv * V + q] = Pair<T>::make(a, d * u.v[q]);
+          const T a = act_fn<T, ACT>(Z[jv * V + q].lo(), d);
+          val = Math<T>::fma(wo[q], a, val);
+          dval = Math<T>::fma(wo[q] * d, Z[jv * V + q].hi(), dval);
         }
-      }
-      const T* wout = sm + 2 * HH;
-      const T* b2 = sm + 3 * HH;
-      const Vec* W = reinterpret_cast<const Vec*>(sm + 4 * HH);
-      const Pair<T> one = Pair<T>::make(T(1), T(1));
-#pragma unroll 2
-      for (int j = 0; j < HH; ++j) {
-        Pair<T> Z0 = Pair<T>::make(b2[j], T(0)), Z1 = Pair<T>::make(T(0), T(0));
-#pragma unroll
-        for (int iv = 0; iv < HH / V; ++iv) {
-          const Vec w = W[j * (HH / V) + iv];
-#pragma unroll
-          for (int q = 0; q < V; ++q) {
-            if (q & 1) Z1 = Pair<T>::fma_bcast(HD[iv * V + q], w.v[q], Z1);
-            else Z0 = Pair<T>::fma_bcast(HD[iv * V + q], w.v[q], Z0);
-          }
-        }
-        const Pair<T> Z = Pair<T>::fma(Z0, one, Z1);
-        T d;
-        const T a = act_fn<T, ACT>(Z.lo(), d);
-        const T wo = wout[j];
-        val = Math<T>::fma(wo, a, val);
-        dval = Math<T>::fma(wo * d, Z.hi(), dval);
       }
     }
     const T g = dval * P.inv_range;
