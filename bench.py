@@ -172,7 +172,7 @@ def run_ours(args):
         iteration(False)
     torch.cuda.synchronize()
     barrier()
-    mon = ClockMonitor(local)
+    mon = ClockMonitor(local, period=float(os.environ.get("PYVES_CLOCK_PERIOD", "0.02")))
     mon.start()
     l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

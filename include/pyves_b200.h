@@ -154,6 +154,13 @@ int pyves_moments(pyves_t* h, const void* pos, int64_t n, int ncols, const void*
 int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim, int axis, const double* range,
                     const int* nbins, const void* row_weights, double* counts, int on_host, void* stream);
 
+/* Domain of the ensemble averages of pyves_moments for the Legendre / path-CV bases.  0 (default): every
+ * row counts, rows outside the basis interval enter with their clamped coordinate, exactly what
+ * LegendreBasis1D.forward does to them (ves/basis.py:143).  1: rows outside the interval get weight 0, i.e.
+ * <f>_V conditional on the box -- the estimator of the VES functional restricted to the support of the
+ * target distribution (ves/target.py:24-31 defines p on [-1, 1] only; README.md:10-31). */
+int pyves_set_moment_domain(pyves_t* h, int inside_only);
+
 /* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel;
  * 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed again) */
 int pyves_set_tuning(pyves_t* h, int variant);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pyves_moments": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
+    "pyves_set_moment_domain": (_i, [_vp, _i]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -204,6 +205,11 @@ class Ensemble:
 
     def set_tuning(self, variant):
         self._ck(self.lib.pyves_set_tuning(self.h, variant))
+
+    def set_moment_domain(self, inside_only):
+        """True: ``moments()`` averages over the rows inside the basis interval only (conditional
+        ensemble average on the support of the target); False (default): every row, clamped."""
+        self._ck(self.lib.pyves_set_moment_domain(self.h, int(bool(inside_only))))
 
     def set_bias_none(self):
         self._ck(self.lib.pyves_set_bias_none(self.h))

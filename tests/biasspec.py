@@ -64,6 +64,23 @@ def oracle_basis(spec, pos):
     raise KeyError(k)
 
 
+def oracle_inside(spec, pos):
+    """Rows whose scaled coordinate lies inside the basis interval on every axis the basis uses
+    (the rows pyves_set_moment_domain(1) keeps)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    k = spec["kind"]
+    if k == "leg1d":
+        return legendre.scale_clamp(pos[:, AX[spec["axis"]]], spec["min"], spec["max"])[1].astype(bool)
+    if k == "leg2d":
+        m = spec["minmax"]
+        return (legendre.scale_clamp(pos[:, 0], m[0], m[1])[1].astype(bool)
+                & legendre.scale_clamp(pos[:, 1], m[2], m[3])[1].astype(bool))
+    if k == "pathcv":
+        s, _, _, _ = pathcv.path_cv(pos, spec["x_i"], spec["y_i"], spec["lam"])
+        return (2 * s - 1 >= -1) & (2 * s - 1 <= 1)
+    raise KeyError(k)
+
+
 def total_force_fn(pot_kind, pot_params, spec):
     def f(x):
         return potentials.force(pot_kind, x, pot_params) + oracle_energy_force(spec, x)[1]

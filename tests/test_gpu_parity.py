@@ -359,6 +359,43 @@ def test_moments_vs_oracle(case):
         e.close()
 
 
+@pytest.mark.parametrize("case", [c for c in MOMENT_CASES if c[0] in ("leg1d12y", "leg2d16", "leg2d_5x9", "leg2d32")],
+                         ids=lambda c: c[0])
+def test_moments_inside_domain(case):
+    """pyves_set_moment_domain(1): rows outside the basis interval get weight 0 (conditional averages on
+    the support of the target), on the CUDA-core kernels and on the tcgen05 covariance (leg2d16)."""
+    tag, mk, cov = case
+    rng = np.random.default_rng(zlib.crc32(tag.encode()) + 1)
+    spec = mk(rng)
+    n = 4099
+    pos = np.stack([rng.uniform(-3.2, 3.2, n), rng.uniform(-2.6, 2.6, n)], 1)
+    w = rng.uniform(0, 2, n)
+    fr = biasspec.oracle_basis(spec, pos)
+    from oracle import ves
+    for prec, tol, dt in PREC:
+        e = biasspec.make_ensemble(n, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+        p_dev = pos.astype(e.np_dtype).astype(np.float64)              # mask what the device sees
+        inside = biasspec.oracle_inside(spec, p_dev)
+        assert 0.2 * n < inside.sum() < 0.9 * n
+        tpos = torch.tensor(pos, dtype=dt, device=DEV)
+        e.set_state(tpos.T.contiguous(), None)
+        e.set_moment_domain(True)
+        for weights in (None, w):
+            tws = None if weights is None else torch.tensor(weights, dtype=dt, device=DEV)
+            wm = inside.astype(np.float64) * (1.0 if weights is None else weights)
+            sw_r, sf_r, sff_r = ves.moments(fr, wm)
+            sw, sf, sff = e.moments(row_weights=tws, cov=cov)
+            assert abs(float(sw.cpu()[0]) - sw_r) / sw_r < (1e-12 if prec == "fp64" else 1e-6)
+            scale = np.maximum(np.abs(fr).T @ wm, 1.0)
+            assert np.max(np.abs(sf.cpu().numpy() - sf_r) / scale) < tol, (tag, prec)
+            if cov:
+                assert np.max(np.abs(sff.cpu().numpy() - sff_r)) / max(1.0, np.max(np.abs(sff_r))) < max(tol, 2e-3 if prec == "fp32" else 0), (tag, prec)
+        e.set_moment_domain(False)
+        sw, _, _ = e.moments()
+        assert float(sw.cpu()[0]) == n
+        e.close()
+
+
 def test_moments_mlp_rejects_covariance():
     rng = np.random.default_rng(0)
     e = biasspec.make_ensemble(8, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, rng_spec("mlp", rng, sizes=[4, 4]))

@@ -37,7 +37,9 @@ def main():
     second = len(sys.argv) > 6 and sys.argv[6] == "second"
     b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd", {"mu": mu, "averaging": "ewma", "decay": decay, "second_order": second, "precondition": pre},
                               target_update_every=10)
-    sim = SingleParticleSimulation(pot, n_walkers=n, seed=20221019, timestep=tstep)
+    scheme = sys.argv[11] if len(sys.argv) > 11 else "openmm_langevin"
+    inbox = len(sys.argv) > 12 and sys.argv[12] == "inbox"
+    sim = SingleParticleSimulation(pot, n_walkers=n, seed=20221019, timestep=tstep, scheme=scheme)
     sim.place_walkers(xmin=-2.5, xmax=2.5, ymin=-2, ymax=2)
     ens = sim.ens
     b.force.apply(ens)
@@ -49,7 +51,12 @@ def main():
     for chunk in range(nup // rep):
         for _ in range(rep):
             ens.step(stride)
-            sw, sf, sff = ens.moments(cov=second)
+            if inbox:
+                pos, _ = ens.get_state()
+                wrow = ((pos[0].abs() <= 2.5) & (pos[1].abs() <= 2.0)).to(pos.dtype)
+                sw, sf, sff = ens.moments(row_weights=wrow, cov=second)
+            else:
+                sw, sf, sff = ens.moments(cov=second)
             b.update_from_moments(sw, sf, sff)
             b.force.apply(ens)
         done += rep
