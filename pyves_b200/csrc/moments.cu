@@ -141,13 +141,31 @@ __global__ void __launch_bounds__(kMomThreads) moments1_kernel(const RowSource<T
   }
 }
 
-// out[m] = sum_g part[g][m] in fixed order (deterministic)
-__global__ void reduce_partials_kernel(const double* __restrict__ part, int64_t G, int64_t M, double* __restrict__ out) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
+// out[m] = sum_g part[g][m] (m < M) and out_w[0] = sum_g part_w[g], in a fixed order (deterministic):
+// one warp per column, lane l adds the partials g = l, l + 32, ... (independent loads, all in flight
+// together), then a butterfly over the lanes.  A single thread walking the G = 592 partials of a column
+// was a chain of 592 dependent L2 round trips (~100 us per call, as long as the moment kernel itself).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ part, int64_t G, int64_t M,
+                                                              double* __restrict__ out, const double* __restrict__ part_w,
+                                                              double* __restrict__ out_w) {
+  const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col > M || (col == M && part_w == nullptr)) return;
+  const double* src = col < M ? part + col : part_w;
+  const int64_t stride = col < M ? M : 1;
   double s = 0.0;
-  for (int64_t g = 0; g < G; ++g) s += part[g * M + m];
-  out[m] = s;
+  for (int64_t g = lane; g < G; g += 32) s += src[g * stride];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (col < M) out[col] = s;
+    else out_w[0] = s;
+  }
+}
+
+static inline void launch_reduce_partials(const double* part, int64_t G, int64_t M, double* out, const double* part_w,
+                                          double* out_w, cudaStream_t st) {
+  const int64_t cols = M + (part_w != nullptr ? 1 : 0);
+  reduce_partials_kernel<<<(unsigned)((cols + 7) / 8), 256, 0, st>>>(part, G, M, out, part_w, out_w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,9 +380,8 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
       if (e != cudaSuccess) return e;
     }
     kern<<<G, kMomThreads, sm, st>>>(S, B, part_f, part_w);
-    reduce_partials_kernel<<<(K + 127) / 128, 128, 0, st>>>(part_f, G, K, sum_wf);
-    reduce_partials_kernel<<<1, 32, 0, st>>>(part_w, G, 1, sum_w);
-    *launches += 3;
+    launch_reduce_partials(part_f, G, K, sum_wf, part_w, sum_w, st);
+    *launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -530,9 +547,8 @@ cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M,
     if (e != cudaSuccess) return e;
   }
   kern<<<G, kMomThreads, sm, st>>>(S, M, units_in, part, part_w);
-  reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(part, G, P, sum_wf);
-  reduce_partials_kernel<<<1, 32, 0, st>>>(part_w, G, 1, sum_w);
-  *launches += 3;
+  launch_reduce_partials(part, G, P, sum_wf, part_w, sum_w, st);
+  *launches += 2;
   return cudaGetLastError();
 }
 
