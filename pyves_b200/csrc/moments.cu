@@ -1,3 +1,5 @@
+#include <cstring>
+
 #include "moments.cuh"
 
 namespace pv {
@@ -204,6 +206,15 @@ __global__ void __launch_bounds__(kMomThreads) moments2_kernel(const RowSource<T
       acc[i][j] = T(0);
       acc64[i][j] = 0.0;
     }
+  // factor indices (a, b) of the 64 + 64 basis functions of this pair tile: no divisions in the row loop
+  __shared__ short idx_a[2][kPairTile], idx_b[2][kPairTile];
+  if (threadIdx.x < 2 * kPairTile) {
+    const int side = threadIdx.x / kPairTile, kk = threadIdx.x % kPairTile;
+    const int kf = (side ? kB0 : kA0) + kk;
+    idx_a[side][kk] = (short)(kf < K ? kf / B.kb : 0);
+    idx_b[side][kk] = (short)(kf < K ? kf % B.kb : 0);
+  }
+  __syncthreads();
   const int64_t ntiles = (S.n + R - 1) / R;
   int since_flush = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -225,17 +236,10 @@ __global__ void __launch_bounds__(kMomThreads) moments2_kernel(const RowSource<T
     __syncthreads();
     // fA[r][kk] = w_r f_{kA0+kk}(r);  fB[r][ll] = f_{kB0+ll}(r);  f_k = FA_a FB_b
     for (int e = threadIdx.x; e < R * kPairTile; e += kMomThreads) {
-      const int r = e / kPairTile, kk = e - r * kPairTile;
-      const int ka_ = kA0 + kk, kb_ = kB0 + kk;
+      const int r = e / kPairTile, kk = e % kPairTile;
       T va = T(0), vb = T(0);
-      if (ka_ < K) {
-        const int a = ka_ / B.kb, b = ka_ - a * B.kb;
-        va = wrow[r] * ta[r * kap + a] * (B.kb > 1 ? tb[r * kbp + b] : T(1));
-      }
-      if (kb_ < K) {
-        const int a = kb_ / B.kb, b = kb_ - a * B.kb;
-        vb = ta[r * kap + a] * (B.kb > 1 ? tb[r * kbp + b] : T(1));
-      }
+      if (kA0 + kk < K) va = wrow[r] * ta[r * kap + idx_a[0][kk]] * (B.kb > 1 ? tb[r * kbp + idx_b[0][kk]] : T(1));
+      if (kB0 + kk < K) vb = ta[r * kap + idx_a[1][kk]] * (B.kb > 1 ? tb[r * kbp + idx_b[1][kk]] : T(1));
       fA[e] = va;
       fB[e] = vb;
     }
@@ -287,9 +291,11 @@ __global__ void __launch_bounds__(kMomThreads) moments2_kernel(const RowSource<T
       out[(ty * 4 + i) * kPairTile + tx * 4 + j] = acc64[i][j] + (double)acc[i][j];
 }
 
-// sum_wff[k][l] (and mirror) = sum over row chunks of the pair-tile partials
-__global__ void reduce_cov_kernel(const double* __restrict__ part, int G, int npt, int K64, int K,
-                                  double* __restrict__ out) {
+// sum_wff[k][l] (and mirror) = sum over row chunks of the pair-tile partials, fixed order: LPO lanes per
+// output element split the G partials (independent loads in flight), then a butterfly over those lanes.
+template <int LPO>
+__global__ void __launch_bounds__(256) reduce_cov_kernel(const double* __restrict__ part, int G, int npt, int K64, int K,
+                                                          double* __restrict__ out) {
   const int pt = blockIdx.y;
   int ti = 0, rem = pt;
   while (rem >= K64 - ti) {
@@ -297,12 +303,17 @@ __global__ void reduce_cov_kernel(const double* __restrict__ part, int G, int np
     ++ti;
   }
   const int tj = ti + rem;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= kPairTile * kPairTile) return;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) / LPO;   // grid.x covers kPairTile^2 * LPO threads exactly
+  const int sub = threadIdx.x % LPO;
   const int k = ti * kPairTile + e / kPairTile, l = tj * kPairTile + e % kPairTile;
-  if (k >= K || l >= K) return;
+  if (k >= K || l >= K) return;                                  // uniform over the LPO lanes of one element
   double s = 0.0;
-  for (int g = 0; g < G; ++g) s += part[((int64_t)g * npt + pt) * (kPairTile * kPairTile) + e];
+  for (int g = sub; g < G; g += LPO) s += part[((int64_t)g * npt + pt) * (kPairTile * kPairTile) + e];
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned mask = LPO == 32 ? 0xffffffffu : (((1u << LPO) - 1u) << (lane & ~(unsigned)(LPO - 1)));
+#pragma unroll
+  for (int o = LPO / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+  if (sub != 0) return;
   if (ti == tj) {
     if (l >= k) {   // use the upper triangle of a diagonal tile for both halves: exact symmetry
       out[(int64_t)k * K + l] = s;
@@ -311,6 +322,109 @@ __global__ void reduce_cov_kernel(const double* __restrict__ part, int G, int np
   } else {
     out[(int64_t)k * K + l] = s;
     out[(int64_t)l * K + k] = s;
+  }
+}
+
+static void launch_reduce_cov(const double* part, int G, int npt, int K64, int K, double* out, cudaStream_t st) {
+  const int E = kPairTile * kPairTile;
+  if (G >= 64) reduce_cov_kernel<32><<<dim3(E * 32 / 256, npt), 256, 0, st>>>(part, G, npt, K64, K, out);
+  else if (G >= 8) reduce_cov_kernel<8><<<dim3(E * 8 / 256, npt), 256, 0, st>>>(part, G, npt, K64, K, out);
+  else reduce_cov_kernel<1><<<dim3(E / 256, npt), 256, 0, st>>>(part, G, npt, K64, K, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small bases (K <= 32: the 1D Legendre biases of configs[0] / configs[2], K = 6 / 13): first and second
+// moments in one pass.  The 64 x 64 pair-tile kernel above pads such a basis 25-fold (0.6 ms per 10^6 rows,
+// a quarter of the 500 MD steps of configs[2]).  Here every thread stages the K basis values of one row
+// (f_0 = P_0 = 1), then thread t owns the pair p = t % NPP (k <= l) on the row slice t / NPP of the tile;
+// per-tile FP32 sums are promoted to FP64, the slices are merged in shared memory in a fixed order.
+constexpr int kSmallK = 32;
+constexpr int kSmallRows = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kMomThreads) moments_small_kernel(const RowSource<T> S, const BasisParams<T> B, int NPP,
+                                                                    double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = B.ka * B.kb, Kp = K | 1, NP = K * (K + 1) / 2;
+  T* f = reinterpret_cast<T*>(smem_raw);            // [kSmallRows][Kp] basis values
+  T* fw = f + kSmallRows * Kp;                      // [kSmallRows][Kp] weight * basis values
+  const int tid = threadIdx.x;
+  const int p = tid % NPP, slice = tid / NPP, nslices = kMomThreads / NPP;
+  int pk = 0, pl = 0;
+  {   // pair index -> (k, l), k <= l, row-major over the upper triangle
+    int rem = p;
+    while (pk < K && rem >= K - pk) {
+      rem -= K - pk;
+      ++pk;
+    }
+    pl = pk + rem;
+  }
+  const bool owner = p < NP && slice < nslices;
+  double acc = 0.0;
+  const int64_t ntiles = (S.n + kSmallRows - 1) / kSmallRows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r = tile * kSmallRows + tid;
+    {
+      T fa[kSmallK], fb[kSmallK], wt = T(0);
+      if (r < S.n) {
+        row_factors(S, B, r, fa, fb, wt);
+      } else {
+        for (int a = 0; a < B.ka; ++a) fa[a] = T(0);
+        for (int b = 0; b < B.kb; ++b) fb[b] = T(0);
+      }
+      for (int a = 0; a < B.ka; ++a)
+        for (int b = 0; b < B.kb; ++b) {
+          const T v = B.kb > 1 ? fa[a] * fb[b] : fa[a];
+          f[tid * Kp + a * B.kb + b] = v;
+          fw[tid * Kp + a * B.kb + b] = wt * v;
+        }
+    }
+    __syncthreads();
+    if (owner) {
+      T s0 = T(0), s1 = T(0);
+      const int rows_per = kSmallRows / nslices;
+      const T* fk = fw + (slice * rows_per) * Kp + pk;
+      const T* fl = f + (slice * rows_per) * Kp + pl;
+      for (int q = 0; q < rows_per; q += 2) {
+        s0 = Math<T>::fma(fk[q * Kp], fl[q * Kp], s0);
+        s1 = Math<T>::fma(fk[(q + 1) * Kp], fl[(q + 1) * Kp], s1);
+      }
+      acc += (double)(s0 + s1);
+    }
+    __syncthreads();
+  }
+  double* red = reinterpret_cast<double*>(smem_raw);   // [nslices][NPP] (the row tables are free now)
+  if (slice < nslices) red[slice * NPP + p] = acc;
+  __syncthreads();
+  if (tid < NP) {
+    double t = 0.0;
+    for (int q = 0; q < nslices; ++q) t += red[q * NPP + tid];
+    part[(int64_t)blockIdx.x * NP + tid] = t;
+  }
+}
+
+// sums the block partials (one warp per pair) and scatters: sum_wff (both triangles), sum_wf = row 0, sum_w = [0][0]
+__global__ void __launch_bounds__(256) reduce_small_kernel(const double* __restrict__ part, int G, int K, double* __restrict__ sum_w,
+                                                           double* __restrict__ sum_wf, double* __restrict__ sum_wff) {
+  const int NP = K * (K + 1) / 2;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= NP) return;
+  double s = 0.0;
+  for (int g = lane; g < G; g += 32) s += part[(int64_t)g * NP + p];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  int k = 0, rem = p;
+  while (rem >= K - k) {
+    rem -= K - k;
+    ++k;
+  }
+  const int l = k + rem;
+  sum_wff[(int64_t)k * K + l] = s;
+  sum_wff[(int64_t)l * K + k] = s;
+  if (k == 0) {
+    sum_wf[l] = s;
+    if (l == 0) sum_w[0] = s;
   }
 }
 
@@ -367,6 +481,26 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
     if (sum_wff) cudaMemsetAsync(sum_wff, 0, sizeof(double) * K * K, st);
     return cudaGetLastError();
   }
+  if (sum_wff != nullptr && K <= kSmallK) {   // one pass for first and second moments
+    const int NP = K * (K + 1) / 2;
+    int NPP = 32;
+    while (NPP < NP && NPP < kMomThreads) NPP <<= 1;          // pairs padded to a power of two <= 256
+    if (NP > kMomThreads) NPP = 0;
+    if (NPP) {
+      const int64_t tiles = (S.n + kSmallRows - 1) / kSmallRows;
+      const int G = (int)(tiles < kMaxBlocks ? tiles : kMaxBlocks);
+      const size_t sm = (size_t)2 * kSmallRows * (K | 1) * sizeof(T);
+      auto kern = moments_small_kernel<T>;
+      if (sm > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+      }
+      kern<<<G, kMomThreads, sm, st>>>(S, B, NPP, scratch);
+      reduce_small_kernel<<<(NP + 7) / 8, 256, 0, st>>>(scratch, G, K, sum_w, sum_wf, sum_wff);
+      *launches += 2;
+      return cudaGetLastError();
+    }
+  }
   {
     constexpr int R = Tile<T>::kRows1;
     const int64_t tiles = (S.n + R - 1) / R;
@@ -404,7 +538,7 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
       if (e != cudaSuccess) return e;
     }
     kern<<<dim3(G, npt), kMomThreads, sm, st>>>(S, B, K64, part);
-    reduce_cov_kernel<<<dim3(kPairTile * kPairTile / 256, npt), 256, 0, st>>>(part, G, npt, K64, K, sum_wff);
+    launch_reduce_cov(part, G, npt, K64, K, sum_wff, st);
     *launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -519,6 +653,327 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp_kernel(const RowSourc
   if (threadIdx.x == 0) part_w[blockIdx.x] = wred;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path of the MLP parameter-gradient moments (widths multiples of 4, <= 128).  The version above
+// runs forward + backward on one thread per row (1 warp of 8 busy) and read-modify-writes every
+// parameter partial in global memory once per 32 rows; measured on B200 for 10^6 rows: 17 ms for the
+// 3 x 48 net and 107 ms for the reference example's [128, 128] (8 x the 500 MD steps between updates).
+// Here a block keeps a tile of R rows in shared memory ([unit][R + 4]) and
+//   phase 1: all 256 threads run each Linear as a small GEMM (4 units x 8 rows per thread, weights as
+//            128-bit broadcast loads through L1, activations as 128-bit shared loads), forward and backward;
+//   phase 2: the outer products delta_l h_{l-1}^T of ONE "big" layer (nin, nout > 1; blockIdx.y selects it)
+//            are accumulated in a TS x TS register tile per thread (strided ownership: conflict-free
+//            shared loads) over ALL tiles of the block and written once; biases and the 1 -> h / h -> 1
+//            weights ("small" parameters) are handled by the blockIdx.y == 0 blocks.
+struct MlpPlan {
+  int L;                       // number of Linear layers
+  int nin[10], nout[10];
+  int hoff[10], doff[10];      // unit offsets of the inputs / outputs of Linear l
+  int poff[10];                // parameter offset of W_l (bias follows at poff + nin * nout)
+  int nbig, big[10];           // layers with nin > 1 and nout > 1
+  int nsmall;                  // biases + weights of the layers with nin == 1 or nout == 1
+  int units_in, units_out;
+};
+
+template <typename T> struct Mlp2 {
+  static constexpr int kRows = 256 / sizeof(T);      // 64 / 32
+  static constexpr int kStride = kRows + 4;          // row stride in shared memory (bank spread)
+  static constexpr int V = 16 / sizeof(T);
+  static constexpr int kRG = kRows / 8;              // row groups of 8
+};
+constexpr int kMlp2Blocks = 148 * 2;
+constexpr int kMlp2Small = 4;                        // small parameters per thread (<= 1024 in total)
+
+template <typename T> PV_DEV void ldg_vec(const T* p, T (&v)[16 / sizeof(T)]) {
+  if (sizeof(T) == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = (T)q.x; v[1] = (T)q.y; v[2] = (T)q.z; v[3] = (T)q.w;
+  } else {
+    const double2 q = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = (T)q.x; v[1] = (T)q.y;
+  }
+}
+template <typename T> PV_DEV void lds8(const T* p, T (&v)[8]) {
+  constexpr int V = 16 / sizeof(T);
+#pragma unroll
+  for (int c = 0; c < 8 / V; ++c) {
+    T t[V];
+    lds_vec(p + c * V, t);
+#pragma unroll
+    for (int q = 0; q < V; ++q) v[c * V + q] = t[q];
+  }
+}
+
+template <typename T, int TS>
+__global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSource<T> S, const MlpGradParams<T> M, const MlpPlan P,
+                                                                   double* __restrict__ part, double* __restrict__ part_w) {
+  using X = Mlp2<T>;
+  constexpr int R = X::kRows, RS = X::kStride, RG = X::kRG;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* h = reinterpret_cast<T*>(smem_raw);        // inputs of each Linear: [unit][RS]
+  T* d = h + (size_t)P.units_in * RS;           // gates, then deltas, at the outputs of each Linear: [unit][RS]
+  T* wrow = d + (size_t)P.units_out * RS;       // [R] row weights
+  const int tid = threadIdx.x;
+  const int y = blockIdx.y;
+  const int bl = P.nbig > 0 ? P.big[y] : -1;
+  const int tj = tid >> 4, ti = tid & 15;
+
+  T acc[TS][TS];
+#pragma unroll
+  for (int a = 0; a < TS; ++a)
+#pragma unroll
+    for (int b = 0; b < TS; ++b) acc[a][b] = T(0);
+  // small parameters of this thread (y == 0 only): gradient = sum_r d[srow_d][r] * (srow_h >= 0 ? h[srow_h][r] : 1)
+  int srow_d[kMlp2Small], srow_h[kMlp2Small], sidx[kMlp2Small];
+  T sacc[kMlp2Small];
+#pragma unroll
+  for (int q = 0; q < kMlp2Small; ++q) {
+    sacc[q] = T(0);
+    sidx[q] = -1;
+    srow_d[q] = srow_h[q] = 0;
+    int sp = tid + q * kMomThreads;
+    if (y == 0 && sp < P.nsmall) {
+      for (int l = 0; l < P.L; ++l) {
+        const int nw = P.nin[l] * P.nout[l];
+        const bool small_w = P.nin[l] == 1 || P.nout[l] == 1;
+        if (small_w) {
+          if (sp < nw) {
+            const int j = sp / P.nin[l], i = sp - j * P.nin[l];
+            srow_d[q] = P.doff[l] + j; srow_h[q] = P.hoff[l] + i; sidx[q] = P.poff[l] + sp;
+            break;
+          }
+          sp -= nw;
+        }
+        if (sp < P.nout[l]) {
+          srow_d[q] = P.doff[l] + sp; srow_h[q] = -1; sidx[q] = P.poff[l] + nw + sp;
+          break;
+        }
+        sp -= P.nout[l];
+      }
+    }
+  }
+  double wsum = 0.0;
+
+  const int64_t ntiles = (S.n + R - 1) / R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0g = tile * R;
+    // inputs: scaled coordinate and row weight (0 for the dead rows of the last tile)
+    if (tid < R) {
+      const int64_t gr = r0g + tid;
+      T sv = T(0), wt = T(0);
+      if (gr < S.n) {
+        const T q = (M.axis && S.ncols > 1) ? S.pos[gr * S.stride_row + S.stride_col] : S.pos[gr * S.stride_row];
+        sv = (q - M.lo) * M.inv_range;
+        wt = S.w != nullptr ? S.w[gr] : T(1);
+      }
+      h[tid] = sv;
+      wrow[tid] = wt;
+      d[(P.doff[P.L - 1]) * RS + tid] = wt;     // delta of the single output unit
+      wsum += (double)wt;
+    }
+    __syncthreads();
+    // ---- phase 1, forward (the last Linear's output is not needed)
+    for (int l = 0; l + 1 < P.L; ++l) {
+      const int nin = P.nin[l], nout = P.nout[l];
+      const T* W = M.theta + P.poff[l];
+      const T* bias = W + nin * nout;
+      const T* hin = h + (size_t)P.hoff[l] * RS;
+      T* hout = h + (size_t)P.hoff[l + 1] * RS;
+      T* gate = d + (size_t)P.doff[l] * RS;
+      const bool activate = l >= 1;               // ves/basis.py:197-205 (no activation after the first Linear)
+      const int items = (nout / 4) * RG;
+      for (int item = tid; item < items; item += kMomThreads) {
+        const int jg = item / RG, rg = item - jg * RG;
+        const int j0 = jg * 4, r0 = rg * 8;
+        T z[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const T bj = __ldg(bias + j0 + a);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) z[a][c] = bj;
+        }
+        if (nin == 1) {
+          T hv[8];
+          lds8(hin + r0, hv);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const T w = __ldg(W + j0 + a);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[a][c] = Math<T>::fma(w, hv[c], z[a][c]);
+          }
+        } else {
+          for (int i = 0; i < nin; i += X::V) {
+            T w[4][X::V];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ldg_vec(W + (size_t)(j0 + a) * nin + i, w[a]);
+#pragma unroll
+            for (int bb = 0; bb < X::V; ++bb) {
+              T hv[8];
+              lds8(hin + (size_t)(i + bb) * RS + r0, hv);
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) z[a][c] = Math<T>::fma(w[a][bb], hv[c], z[a][c]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            T g = T(1), v = z[a][c];
+            if (activate) v = M.act == PYVES_ACT_RELU ? act_fn<T, PYVES_ACT_RELU>(v, g) : act_fn<T, PYVES_ACT_TANH>(v, g);
+            hout[(size_t)(j0 + a) * RS + r0 + c] = v;
+            gate[(size_t)(j0 + a) * RS + r0 + c] = g;
+          }
+      }
+      __syncthreads();
+    }
+    // ---- phase 1, backward: delta_{l-1} = gate_{l-1} * (W_l^T delta_l)
+    for (int l = P.L - 1; l >= 1; --l) {
+      const int nin = P.nin[l], nout = P.nout[l];
+      const T* W = M.theta + P.poff[l];
+      const T* dl = d + (size_t)P.doff[l] * RS;
+      T* dprev = d + (size_t)P.doff[l - 1] * RS;
+      const int items = (nin / 4) * RG;
+      for (int item = tid; item < items; item += kMomThreads) {
+        const int ig = item / RG, rg = item - ig * RG;
+        const int i0 = ig * 4, r0 = rg * 8;
+        T sacc4[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sacc4[a][c] = T(0);
+        for (int j = 0; j < nout; ++j) {
+          T w[4];
+          if (sizeof(T) == 4) {
+            T t[X::V];
+            ldg_vec(W + (size_t)j * nin + i0, t);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) w[a] = t[a % X::V];
+          } else {
+            T t0[X::V], t1[X::V];
+            ldg_vec(W + (size_t)j * nin + i0, t0);
+            ldg_vec(W + (size_t)j * nin + i0 + 2, t1);
+            w[0] = t0[0]; w[1] = t0[1 % X::V]; w[2] = t1[0]; w[3] = t1[1 % X::V];
+          }
+          T dv[8];
+          lds8(dl + (size_t)j * RS + r0, dv);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sacc4[a][c] = Math<T>::fma(w[a], dv[c], sacc4[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dprev[(size_t)(i0 + a) * RS + r0 + c] *= sacc4[a][c];
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: outer products of the big layer of this block, register tile, strided ownership
+    if (bl >= 0) {
+      const int nin = P.nin[bl], nout = P.nout[bl];
+      const T* dl = d + (size_t)P.doff[bl] * RS;
+      const T* hl = h + (size_t)P.hoff[bl] * RS;
+      for (int r = 0; r < R; r += X::V) {
+        T dv[TS][X::V], hv[TS][X::V];
+#pragma unroll
+        for (int a = 0; a < TS; ++a) {
+          const int j = tj + 16 * a;
+          if (j < nout) lds_vec(dl + (size_t)j * RS + r, dv[a]);
+          else
+#pragma unroll
+            for (int q = 0; q < X::V; ++q) dv[a][q] = T(0);
+        }
+#pragma unroll
+        for (int b = 0; b < TS; ++b) {
+          const int i = ti + 16 * b;
+          if (i < nin) lds_vec(hl + (size_t)i * RS + r, hv[b]);
+          else
+#pragma unroll
+            for (int q = 0; q < X::V; ++q) hv[b][q] = T(0);
+        }
+#pragma unroll
+        for (int a = 0; a < TS; ++a)
+#pragma unroll
+          for (int b = 0; b < TS; ++b)
+#pragma unroll
+            for (int q = 0; q < X::V; ++q) acc[a][b] = Math<T>::fma(dv[a][q], hv[b][q], acc[a][b]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kMlp2Small; ++q) {
+      if (sidx[q] >= 0) {
+        const T* dr = d + (size_t)srow_d[q] * RS;
+        T s0 = T(0);
+        if (srow_h[q] >= 0) {
+          const T* hr = h + (size_t)srow_h[q] * RS;
+          for (int r = 0; r < R; ++r) s0 = Math<T>::fma(dr[r], hr[r], s0);
+        } else {
+          for (int r = 0; r < R; ++r) s0 += dr[r];
+        }
+        sacc[q] += s0;
+      }
+    }
+    __syncthreads();
+  }
+
+  double* mypart = part + (int64_t)blockIdx.x * M.n_params;
+  if (bl >= 0) {
+    const int nin = P.nin[bl], nout = P.nout[bl];
+#pragma unroll
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+      for (int b = 0; b < TS; ++b) {
+        const int j = tj + 16 * a, i = ti + 16 * b;
+        if (j < nout && i < nin) mypart[P.poff[bl] + j * nin + i] = (double)acc[a][b];
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < kMlp2Small; ++q)
+    if (sidx[q] >= 0) mypart[sidx[q]] = (double)sacc[q];
+  if (y == 0) {
+    __shared__ double wred[kMomThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((tid & 31) == 0) wred[tid >> 5] = wsum;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < kMomThreads / 32; ++i) t += wred[i];
+      part_w[blockIdx.x] = t;
+    }
+  }
+}
+
+// true when the fast kernel applies; fills the plan
+template <typename T> static bool make_mlp_plan(const MlpGradParams<T>& M, MlpPlan& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.L = M.n_layers;
+  if (P.L < 2 || P.L > 10 || M.sizes[0] != 1 || M.sizes[P.L] != 1) return false;
+  int hoff = 0, doff = 0, poff = 0, wmax = 0;
+  for (int l = 0; l < P.L; ++l) {
+    const int nin = M.sizes[l], nout = M.sizes[l + 1];
+    P.nin[l] = nin; P.nout[l] = nout; P.hoff[l] = hoff; P.doff[l] = doff; P.poff[l] = poff;
+    if ((l == 0) != (nin == 1) || (l == P.L - 1) != (nout == 1)) return false;   // hidden widths >= 4
+    if (nin > 1 && nin % 4 != 0) return false;
+    if (nout > 1 && nout % 4 != 0) return false;
+    if (nin > 128 || nout > 128) return false;
+    if (poff % 4 != 0) return false;                      // 128-bit weight loads
+    if (nin > 1 && nout > 1) P.big[P.nbig++] = l;
+    else P.nsmall += nin * nout;
+    P.nsmall += nout;
+    if (nin > wmax) wmax = nin;
+    if (nout > wmax) wmax = nout;
+    hoff += nin; doff += nout; poff += nin * nout + nout;
+  }
+  P.units_in = hoff;
+  P.units_out = doff;
+  if (P.nsmall > kMlp2Small * kMomThreads) return false;
+  const size_t sm = ((size_t)(P.units_in + P.units_out) * Mlp2<T>::kStride + Mlp2<T>::kRows) * sizeof(T);
+  return sm <= 200 * 1024;
+}
+
 template <typename T>
 cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M, double* sum_w, double* sum_wf,
                                double* scratch, cudaStream_t st, int* launches) {
@@ -527,6 +982,25 @@ cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M,
   if (S.n == 0) {
     cudaMemsetAsync(sum_w, 0, sizeof(double), st);
     cudaMemsetAsync(sum_wf, 0, sizeof(double) * P, st);
+    return cudaGetLastError();
+  }
+  MlpPlan plan;
+  if (make_mlp_plan<T>(M, plan)) {
+    using X = Mlp2<T>;
+    const int64_t tiles2 = (S.n + X::kRows - 1) / X::kRows;
+    const int G2 = (int)(tiles2 < kMlp2Blocks ? tiles2 : kMlp2Blocks);
+    double* part2 = scratch;
+    double* part_w2 = scratch + (size_t)kMaxBlocks * P;
+    const size_t sm2 = ((size_t)(plan.units_in + plan.units_out) * X::kStride + X::kRows) * sizeof(T);
+    int wmax = 0;
+    for (int l = 0; l <= M.n_layers; ++l) wmax = M.sizes[l] > wmax ? M.sizes[l] : wmax;
+    auto kern2 = wmax <= 32 ? moments_mlp2_kernel<T, 2> : (wmax <= 64 ? moments_mlp2_kernel<T, 4> : moments_mlp2_kernel<T, 8>);
+    cudaError_t e2 = cudaSuccess;
+    if (sm2 > 48 * 1024) e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    if (e2 != cudaSuccess) return e2;
+    kern2<<<dim3(G2, plan.nbig > 0 ? plan.nbig : 1), kMomThreads, sm2, st>>>(S, M, plan, part2, part_w2);
+    launch_reduce_partials(part2, G2, P, sum_wf, part_w2, sum_w, st);
+    *launches += 2;
     return cudaGetLastError();
   }
   int units_in = 0, units_out = 0;

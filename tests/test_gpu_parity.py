@@ -321,6 +321,8 @@ MOMENT_CASES = [
     ("leg2d32", lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31), False),
     ("pathcv", lambda r: dict(kind="pathcv", degree=6, x_i=np.linspace(-2, 2, 30), y_i=np.linspace(-1, 1.5, 30), lam=20.0, weights=r.standard_normal(7), phi=0.0), True),
     ("mlp48x3", lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), False),
+    ("mlp128x2", lambda r: rng_spec("mlp", r, sizes=[128, 128]), False),          # the reference example's net (deepves...:102)
+    ("mlp_32_64_tanh", lambda r: rng_spec("mlp", r, sizes=[32, 64], act=1), False),
     ("mlp_tanh", lambda r: rng_spec("mlp", r, sizes=[7, 9], act=1), False),
     ("mlp_one", lambda r: rng_spec("mlp", r, sizes=[16]), False),
 ]
