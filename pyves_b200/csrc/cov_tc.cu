@@ -2,7 +2,7 @@
 // FP32 accumulate in TMEM) -- the one GEMM-shaped step of the path (textbook VES Hessian
 // beta Cov_V(f); the reference only names the option, README.md:24).
 //
-// One CTA per SM.  Per trip a CTA turns 32 walkers into a [256 basis functions] x [32 walkers] TF32
+// One CTA per SM and per (row chunk, 256 x 256 output tile).  Per trip a CTA turns walkers into [256 basis functions] x [32 walkers] TF32
 // tile written straight into shared memory in the canonical K-major SWIZZLE_128B UMMA layout (the
 // basis matrix B[N, K] never exists in HBM), then one elected thread issues
 //     D0[128 x 256] += F[0:128, :] F^T        D1[128 x 256] += F[128:256, :] F^T
@@ -20,8 +20,6 @@ namespace {
 constexpr int kTcThreads = 256;
 constexpr int kTcRows = 32;                 // walkers per tile = 128 bytes of TF32 = one swizzle atom
 constexpr int kTcK = 256;                   // padded number of basis functions (UMMA N, 2 x UMMA M)
-constexpr int kTileBytes = kTcK * kTcRows * 4;   // 32 KB
-constexpr int kTabStride = 33;
 
 PV_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -58,56 +56,63 @@ PV_DEV void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumu
 PV_DEV void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-PV_DEV uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+// Round to nearest TF32 (10-bit mantissa).  cvt.rna.tf32.f32 compiles to ~6 half-rate ALU instructions per value
+// (inf / nan guards, add, mask), which made the tile generation ALU bound; the tensor core ignores the low 13
+// mantissa bits anyway, so adding half a TF32 ulp to the bit pattern is the same rounding for the finite,
+// bounded products |P_a P_b| <= 1 written here, in one integer add.
+PV_DEV uint32_t to_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
+
+// The shared-memory struct is reached through a pointer rounded up to 1024 bytes, so the compiler falls back to
+// generic loads and stores; these keep the hot accesses in the shared window.
+PV_DEV float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
+PV_DEV float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+PV_DEV void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+PV_DEV void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// Legendre recursion P_{n+1} = A_n s P_n - B_n P_{n-1}: A_n = (2n+1)/(n+1), B_n = n/(n+1)
+__constant__ float c_leg_a[PYVES_MAX_DEGREE + 1] = {1.000000000e+00f, 1.500000000e+00f, 1.666666667e+00f, 1.750000000e+00f, 1.800000000e+00f, 1.833333333e+00f, 1.857142857e+00f, 1.875000000e+00f, 1.888888889e+00f, 1.900000000e+00f, 1.909090909e+00f, 1.916666667e+00f, 1.923076923e+00f, 1.928571429e+00f, 1.933333333e+00f, 1.937500000e+00f, 1.941176471e+00f, 1.944444444e+00f, 1.947368421e+00f, 1.950000000e+00f, 1.952380952e+00f, 1.954545455e+00f, 1.956521739e+00f, 1.958333333e+00f, 1.960000000e+00f, 1.961538462e+00f, 1.962962963e+00f, 1.964285714e+00f, 1.965517241e+00f, 1.966666667e+00f, 1.967741935e+00f, 1.968750000e+00f, 1.969696970e+00f, 1.970588235e+00f, 1.971428571e+00f, 1.972222222e+00f, 1.972972973e+00f, 1.973684211e+00f, 1.974358974e+00f, 1.975000000e+00f, 1.975609756e+00f, 1.976190476e+00f, 1.976744186e+00f, 1.977272727e+00f, 1.977777778e+00f, 1.978260870e+00f, 1.978723404e+00f, 1.979166667e+00f, 1.979591837e+00f, 1.980000000e+00f, 1.980392157e+00f, 1.980769231e+00f, 1.981132075e+00f, 1.981481481e+00f, 1.981818182e+00f, 1.982142857e+00f, 1.982456140e+00f, 1.982758621e+00f, 1.983050847e+00f, 1.983333333e+00f, 1.983606557e+00f, 1.983870968e+00f, 1.984126984e+00f, 1.984375000e+00f};
+__constant__ float c_leg_b[PYVES_MAX_DEGREE + 1] = {0.000000000e+00f, 5.000000000e-01f, 6.666666667e-01f, 7.500000000e-01f, 8.000000000e-01f, 8.333333333e-01f, 8.571428571e-01f, 8.750000000e-01f, 8.888888889e-01f, 9.000000000e-01f, 9.090909091e-01f, 9.166666667e-01f, 9.230769231e-01f, 9.285714286e-01f, 9.333333333e-01f, 9.375000000e-01f, 9.411764706e-01f, 9.444444444e-01f, 9.473684211e-01f, 9.500000000e-01f, 9.523809524e-01f, 9.545454545e-01f, 9.565217391e-01f, 9.583333333e-01f, 9.600000000e-01f, 9.615384615e-01f, 9.629629630e-01f, 9.642857143e-01f, 9.655172414e-01f, 9.666666667e-01f, 9.677419355e-01f, 9.687500000e-01f, 9.696969697e-01f, 9.705882353e-01f, 9.714285714e-01f, 9.722222222e-01f, 9.729729730e-01f, 9.736842105e-01f, 9.743589744e-01f, 9.750000000e-01f, 9.756097561e-01f, 9.761904762e-01f, 9.767441860e-01f, 9.772727273e-01f, 9.777777778e-01f, 9.782608696e-01f, 9.787234043e-01f, 9.791666667e-01f, 9.795918367e-01f, 9.800000000e-01f, 9.803921569e-01f, 9.807692308e-01f, 9.811320755e-01f, 9.814814815e-01f, 9.818181818e-01f, 9.821428571e-01f, 9.824561404e-01f, 9.827586207e-01f, 9.830508475e-01f, 9.833333333e-01f, 9.836065574e-01f, 9.838709677e-01f, 9.841269841e-01f, 9.843750000e-01f};
+
+constexpr int kSubBytes = kTcK * kTcRows * 4;    // one [256 basis functions] x [32 walkers] sub-tile, 32 KB
+constexpr int kSuperRows = 64;                   // walkers per table build
+constexpr int kTabRS = kSuperRows + 4;           // table row stride (floats): conflict-free 128-bit reads
+constexpr int kTabRows = 2 * (PYVES_MAX_DEGREE + 1);
 
 struct CovSmem {
-  alignas(1024) unsigned char tile[2][kTileBytes];
-  float tab[kTcRows * kTabStride];
+  alignas(1024) unsigned char tile[2][2 * kSubBytes];   // 2 stages x 2 sub-tiles
+  alignas(16) float tab[2][kTabRows * kTabRS];          // tab[.][a][r] = P_a(sx_r) (a < ka), tab[.][ka + b][r] = P_b(sy_r)
   alignas(8) uint64_t stage_bar[2];
   alignas(8) uint64_t done_bar;
   uint32_t tmem_base;
 };
 
-// Legendre tables of one row: tab[r][a] = P_a(sx) (a < ka), tab[r][ka + b] = P_b(sy) (b < kb)
-PV_DEV void row_table(const RowSource<float>& S, const BasisParams<float>& B, int64_t r, bool live, float* t) {
-  if (!live) {
-    for (int a = 0; a < B.ka + B.kb; ++a) t[a] = 0.f;
-    return;
-  }
-  const float x = S.pos[r * S.stride_row];
-  const float y = S.pos[r * S.stride_row + S.stride_col];
-  bool in_a, in_b;
-  const float s[2] = {scale_clamp(x, B.ca, B.iha, in_a), scale_clamp(y, B.cb, B.ihb, in_b)};
-  if (B.inside_only && !(in_a && in_b)) {   // weight 0: the row contributes nothing to B^T B
-    for (int a = 0; a < B.ka + B.kb; ++a) t[a] = 0.f;
-    return;
-  }
-  const int k[2] = {B.ka, B.kb};
-  for (int ax = 0; ax < 2; ++ax) {
-    float pm = 1.f, p = s[ax];
-    t[0] = 1.f;
-    if (k[ax] > 1) t[1] = p;
-    for (int n = 1; n + 1 < k[ax]; ++n) {
-      const float fn = (float)n;
-      const float pn = ((2.f * fn + 1.f) * s[ax] * p - fn * pm) / (fn + 1.f);
-      t[n + 1] = pn;
-      pm = p;
-      p = pn;
-    }
-    t += k[ax];
-  }
-}
-
+// Output tiling: C is cut into 256 x 256 tiles (tm <= tn); blockIdx.y picks the tile, blockIdx.x the chunk of
+// rows.  A diagonal tile needs ONE operand tile F_m (A = B = F_m): a trip covers 64 walkers as two
+// [256 x 32] sub-tiles.  An off-diagonal tile needs F_m and F_n: a trip covers 32 walkers, sub-tile 0 = F_m,
+// sub-tile 1 = F_n.  Either way a stage is 64 KB and every thread writes 2 x 32 values per trip.
 __global__ void __launch_bounds__(kTcThreads, 1)
-cov_tf32_kernel(const RowSource<float> S, const BasisParams<float> B, float* __restrict__ part) {
+cov_tf32_kernel(const RowSource<float> S, const BasisParams<float> B, int T256, int64_t rows_per_chunk, float* __restrict__ part) {
   extern __shared__ unsigned char smem_raw[];
   CovSmem& sm = *reinterpret_cast<CovSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = B.ka * B.kb;
+  int tm = 0, rem = blockIdx.y;
+  while (rem >= T256 - tm) {
+    rem -= T256 - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const bool diag = tm == tn;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
@@ -124,79 +129,150 @@ cov_tf32_kernel(const RowSource<float> S, const BasisParams<float> B, float* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
 
-  // this thread owns basis function k = tid: row tid of the [256][32] tile
-  const int k = tid;
-  const bool kvalid = k < K;
-  const int fa = kvalid ? k / B.kb : 0, fb = kvalid ? B.ka + (k - (k / B.kb) * B.kb) : 0;
-  const uint32_t row_off = (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u;
+  // this thread owns row `tid` of both sub-tiles: basis function k = (fa, fb) factors, or none (zero row)
+  int fa[2], fb[2];
+  bool kvalid[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int k = ((q == 1 && !diag) ? tn : tm) * kTcK + tid;
+    kvalid[q] = k < K;
+    fa[q] = kvalid[q] ? k / B.kb : 0;
+    fb[q] = kvalid[q] ? B.ka + (k - (k / B.kb) * B.kb) : 0;
+  }
+  const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
 
-  const int64_t ntiles = (S.n + kTcRows - 1) / kTcRows;
-  int trip = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++trip) {
-    const int s = trip & 1;
-    const int use = trip >> 1;
-    if (use >= 1) mbar_wait(&sm.stage_bar[s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage are done
-    // per-row Legendre tables (one warp), then every thread fills its own swizzled 128-byte row
-    if (warp == 1) {
-      const int64_t r = tile * kTcRows + lane;
-      row_table(S, B, r, r < S.n, sm.tab + lane * kTabStride);
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t row_end = (row_begin + rows_per_chunk) < S.n ? (row_begin + rows_per_chunk) : S.n;
+  // Pipeline per 64 walkers: [table build, threads 0-127] -> sync -> [all threads fill a stage] -> sync ->
+  // [thread kIssuer queues the MMAs].  The coordinates of the NEXT 64 walkers are loaded one iteration ahead,
+  // the table is double buffered (no third barrier), and the MMA issuer sits in a warp that builds no tables,
+  // so the tensor core works on stage s while the other warps already generate stage s ^ 1.
+  constexpr int kIssuer = 192;
+  const int rr = tid & (kSuperRows - 1), ax = (tid >> 6) & 1;
+  float px = 0.f, py = 0.f;
+  bool plive = false;
+  auto prefetch = [&](int64_t r0) {
+    const int64_t r = r0 + rr;
+    plive = tid < 2 * kSuperRows && r < row_end;
+    if (plive) {
+      px = S.pos[r * S.stride_row];
+      py = S.pos[r * S.stride_row + S.stride_col];
     }
-    __syncthreads();
-    {
-      unsigned char* base = sm.tile[s] + row_off;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 v;
-        uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = c * 4 + q;
-          const float f = kvalid ? sm.tab[r * kTabStride + fa] * sm.tab[r * kTabStride + fb] : 0.f;
-          pv[q] = to_tf32(f);
+  };
+  prefetch(row_begin);
+  int trip = 0;   // stage uses so far
+  int it = 0;
+  for (int64_t r0 = row_begin; r0 < row_end; r0 += kSuperRows, ++it) {
+    const uint32_t tab = smem_u32(sm.tab[it & 1]);
+    // ---- Legendre tables of 64 walkers: thread = (walker, axis), no divisions
+    if (tid < 2 * kSuperRows) {
+      const int kn = ax ? B.kb : B.ka;
+      const uint32_t t = tab + (uint32_t)(((ax ? B.ka : 0) * kTabRS + rr) * 4);
+      bool live = plive;
+      float sv = 0.f;
+      if (live) {
+        bool in_a, in_b;
+        const float sx = scale_clamp(px, B.ca, B.iha, in_a), sy = scale_clamp(py, B.cb, B.ihb, in_b);
+        if (B.inside_only && !(in_a && in_b)) live = false;   // weight 0: the row contributes nothing to F F^T
+        sv = ax ? sy : sx;
+      }
+      prefetch(r0 + kSuperRows);                               // in flight during the recursion and the fill
+      if (live) {
+        float pm = 1.f, p = sv;
+        sts32(t, 1.f);
+        if (kn > 1) sts32(t + kTabRS * 4, p);
+        for (int n = 1; n + 1 < kn; ++n) {
+          const float pn = fmaf(c_leg_a[n] * sv, p, -c_leg_b[n] * pm);   // uniform index: constant-bank operands
+          sts32(t + (uint32_t)((n + 1) * kTabRS * 4), pn);
+          pm = p;
+          p = pn;
         }
-        *reinterpret_cast<uint4*>(base + ((c ^ (k & 7)) << 4)) = v;   // Swizzle<3,4,3>: 16-byte chunk index ^ (row % 8)
+      } else {
+        for (int n = 0; n < kn; ++n) sts32(t + (uint32_t)(n * kTabRS * 4), 0.f);
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = smem_u32(sm.tile[s]);
-      const uint64_t db = umma_desc_k_sw128(a0);
+    // ---- one trip (diagonal: 64 walkers) or two trips (off-diagonal: 32 walkers each)
+    const int ntr = diag ? 1 : 2;
+    for (int hh = 0; hh < ntr; ++hh, ++trip) {
+      const int s = trip & 1, use = trip >> 1;
+      if (use >= 1) mbar_wait(&sm.stage_bar[s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage are done
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const uint64_t da = umma_desc_k_sw128(a0 + (uint32_t)m * 128u * 128u);   // rows 128 m .. 128 m + 127
+      for (int q = 0; q < 2; ++q) {
+        const int rbase = diag ? 32 * q : 32 * hh;
+        const uint32_t ta = tab + (uint32_t)((fa[q] * kTabRS + rbase) * 4);
+        const uint32_t tb = tab + (uint32_t)((fb[q] * kTabRS + rbase) * 4);
+        const uint32_t base = smem_u32(sm.tile[s]) + (uint32_t)q * kSubBytes + row_off;
+        if (kvalid[q]) {
+          float4 a4[8], b4[8];     // all 16 loads in flight before the first use (the asm loads are not reordered)
 #pragma unroll
-        for (int kk = 0; kk < kTcRows / 8; ++kk)       // K = 8 TF32 = 32 bytes per instruction: +2 in 16-byte units
-          umma_tf32(tmem + (uint32_t)m * 256u, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), (trip > 0 || kk > 0) ? 1u : 0u);
+          for (int c = 0; c < 8; ++c) {
+            a4[c] = lds128(ta + c * 16);
+            b4[c] = lds128(tb + c * 16);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = make_uint4(to_tf32(a4[c].x * b4[c].x), to_tf32(a4[c].y * b4[c].y), to_tf32(a4[c].z * b4[c].z),
+                                       to_tf32(a4[c].w * b4[c].w));
+            sts128(base + (uint32_t)((c ^ (tid & 7)) << 4), v);   // Swizzle<3,4,3>: 16-byte chunk index ^ (row % 8)
+          }
+        } else {     // padding rows of the last tile (k >= K)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sts128(base + (uint32_t)(c << 4), make_uint4(0u, 0u, 0u, 0u));
+        }
       }
-      umma_commit(&sm.stage_bar[s]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      __syncthreads();
+      if (tid == kIssuer) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(sm.tile[s]);
+        const int nsub = diag ? 2 : 1;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const uint32_t abase = a0 + (uint32_t)(diag ? sub : 0) * kSubBytes;
+          const uint32_t bbase = a0 + (uint32_t)(diag ? sub : 1) * kSubBytes;
+          const uint64_t db = umma_desc_k_sw128(bbase);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const uint64_t da = umma_desc_k_sw128(abase + (uint32_t)m * 128u * 128u);   // rows 128 m .. 128 m + 127
+#pragma unroll
+            for (int kk = 0; kk < kTcRows / 8; ++kk)       // K = 8 TF32 = 32 bytes per instruction: +2 in 16-byte units
+              umma_tf32(tmem + (uint32_t)m * 256u, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2),
+                        (trip > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&sm.stage_bar[s]);
+      }
     }
   }
-  // all MMAs done?
-  if (tid == 0) umma_commit(&sm.done_bar);
+  // all MMAs done?  (the issuer's commit covers every MMA it queued before)
+  if (tid == kIssuer) umma_commit(&sm.done_bar);
   mbar_wait(&sm.done_bar, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // TMEM -> registers -> per-CTA partial [256][256] floats.  Warp w reads lanes 32 (w % 4) .. +31 of
-  // accumulator w / 4; thread = one row of D.
-  if (trip > 0) {
+  // TMEM -> registers -> partial [256][256] floats of this (chunk, tile).  Warp w reads lanes 32 (w % 4) .. +31
+  // of accumulator w / 4; thread = one row of D.
+  {
     const int acc = warp >> 2, lq = warp & 3;
-    float* out = part + ((size_t)blockIdx.x * kTcK + (size_t)(acc * 128 + lq * 32 + lane)) * kTcK;
+    float* out = part + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * kTcK + (size_t)(acc * 128 + lq * 32 + lane)) * kTcK;
 #pragma unroll 1
     for (int c0 = 0; c0 < kTcK; c0 += 32) {
       uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * 256 + c0);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (trip > 0) {
+        const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * 256 + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0u;      // a chunk without rows contributes zeros
+      }
 #pragma unroll
       for (int q = 0; q < 32; q += 4)
         *reinterpret_cast<uint4*>(out + c0 + q) = make_uint4(v[q], v[q + 1], v[q + 2], v[q + 3]);
@@ -207,38 +283,68 @@ cov_tf32_kernel(const RowSource<float> S, const BasisParams<float> B, float* __r
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// out[k][l] (FP64, K x K) = sum over CTAs of part[cta][k][l]; symmetrised exactly
-__global__ void cov_tc_reduce_kernel(const float* __restrict__ part, int G, int K, double* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= K * K) return;
-  const int k = idx / K, l = idx - k * K;
-  if (l < k) return;
-  double s = 0.0;
-  for (int g = 0; g < G; ++g)
-    s += 0.5 * ((double)part[((size_t)g * kTcK + k) * kTcK + l] + (double)part[((size_t)g * kTcK + l) * kTcK + k]);
-  out[(size_t)k * K + l] = s;
-  out[(size_t)l * K + k] = s;
+// out[k][l] (FP64, K x K) = sum over the row chunks of part[chunk][tile][i][j]; diagonal tiles are symmetrised
+// exactly, off-diagonal tiles are mirrored.  One thread per element of the upper triangle, four independent
+// partial sums (fixed order).
+__global__ void __launch_bounds__(256) cov_tc_reduce_kernel(const float* __restrict__ part, int G, int T256, int K,
+                                                            double* __restrict__ out) {
+  const int tile = blockIdx.y;
+  int tm = 0, rem = tile;
+  while (rem >= T256 - tm) {
+    rem -= T256 - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = e / kTcK, j = e % kTcK;
+  const int k = tm * kTcK + i, l = tn * kTcK + j;
+  if (k >= K || l >= K || l < k) return;
+  const int ntile = gridDim.y;
+  const size_t stride = (size_t)ntile * kTcK * kTcK;
+  const float* p0 = part + ((size_t)tile * kTcK + i) * kTcK + j;
+  const float* p1 = part + ((size_t)tile * kTcK + j) * kTcK + i;   // transposed element (diagonal tiles)
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  if (tm == tn) {
+    for (int g = 0; g < G; ++g) s[g & 3] += 0.5 * ((double)p0[g * stride] + (double)p1[g * stride]);
+  } else {
+    for (int g = 0; g < G; ++g) s[g & 3] += (double)p0[g * stride];
+  }
+  const double t = (s[0] + s[1]) + (s[2] + s[3]);
+  out[(size_t)k * K + l] = t;
+  out[(size_t)l * K + k] = t;
 }
 
 }  // namespace
 
 bool cov_tc_supported(const RowSource<float>& S, const BasisParams<float>& B) {
   const int K = B.ka * B.kb;
-  return S.w == nullptr && B.kind == PYVES_BIAS_LEGENDRE_2D && K > 128 && K <= kTcK && S.ncols >= 2;
+  return S.w == nullptr && B.kind == PYVES_BIAS_LEGENDRE_2D && K > 128 && K <= 4096 && S.ncols >= 2;
 }
 
-size_t cov_tc_scratch_floats(int n_sm) { return (size_t)n_sm * kTcK * kTcK; }
+static void cov_tc_grid(int K, int64_t n, int n_sm, int& T256, int& ntile, int& chunks, int64_t& rows_per_chunk) {
+  T256 = (K + kTcK - 1) / kTcK;
+  ntile = T256 * (T256 + 1) / 2;
+  chunks = n_sm / ntile;
+  if (chunks < 1) chunks = 1;
+  const int64_t supers = (n + kSuperRows - 1) / kSuperRows;
+  if (chunks > supers) chunks = (int)supers;
+  rows_per_chunk = ((supers + chunks - 1) / chunks) * kSuperRows;
+}
+
+// chunks * ntile <= max(n_sm, ntile) partial tiles of 256 x 256 floats (ntile <= 136 for K <= 4096)
+size_t cov_tc_scratch_floats(int n_sm) { return (size_t)(n_sm > 136 ? n_sm : 136) * kTcK * kTcK; }
 
 cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B, double* sum_wff, float* scratch, int n_sm,
                           cudaStream_t st, int* launches) {
   const int K = B.ka * B.kb;
-  const int64_t ntiles = (S.n + kTcRows - 1) / kTcRows;
-  const int G = (int)(ntiles < n_sm ? ntiles : n_sm);
+  int T256, ntile, chunks;
+  int64_t rows_per_chunk;
+  cov_tc_grid(K, S.n, n_sm, T256, ntile, chunks, rows_per_chunk);
   const size_t smem = sizeof(CovSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(cov_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  cov_tf32_kernel<<<G, kTcThreads, smem, st>>>(S, B, scratch);
-  cov_tc_reduce_kernel<<<(K * K + 255) / 256, 256, 0, st>>>(scratch, G, K, sum_wff);
+  cov_tf32_kernel<<<dim3(chunks, ntile), kTcThreads, smem, st>>>(S, B, T256, rows_per_chunk, scratch);
+  cov_tc_reduce_kernel<<<dim3(kTcK * kTcK / 256, ntile), 256, 0, st>>>(scratch, chunks, T256, K, sum_wff);
   *launches += 2;
   return cudaGetLastError();
 }

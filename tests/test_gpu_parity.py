@@ -452,14 +452,16 @@ def test_equilibrium_sampling_double_well_fes():
     e.close()
 
 
-def test_covariance_tensor_core_path():
-    """K = 256 (16 x 16) covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM):
-    agrees with the FP64 oracle to TF32 rounding (2^-11 per factor, averaging out over rows) and with the
-    CUDA-core kernel; symmetric exactly; row 0 reproduces the first moments (f_0 = 1)."""
+@pytest.mark.parametrize("deg,sizes", [(15, (31, 10007, 300000)), (19, (10007,)), (31, (77, 5003))], ids=["K256", "K400", "K1024"])
+def test_covariance_tensor_core_path(deg, sizes):
+    """K > 128 covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM), tiled into
+    256 x 256 output tiles (K = 400: padded tiles, K = 1024: 10 upper-triangular tiles): agrees with the FP64
+    oracle to TF32 rounding (2^-11 per factor, averaging out over rows) and with the CUDA-core kernel;
+    symmetric exactly; row 0 reproduces the first moments (f_0 = 1)."""
     from oracle import ves
     rng = np.random.default_rng(12)
-    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
-    for n in (31, 10007, 300000):
+    spec = rng_spec("leg2d", rng, deg_x=deg, deg_y=deg)
+    for n in sizes:
         pos = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2.5, 2.5, n)], 1)
         fr = biasspec.oracle_basis(spec, pos)
         sw_r, sf_r, sff_r = ves.moments(fr)
