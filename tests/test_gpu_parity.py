@@ -243,6 +243,49 @@ def test_trajectory_parity_philox_and_chunking():
             assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
 
 
+def test_full_size_sharding_invariance():
+    """BASELINE.json configs[1] at full size (10^6 walkers, 16 x 16 bias): the ensemble cut into two shards with
+    global walker offsets reproduces the single-handle run bit for bit (Philox counters use global ids), and the
+    shard moments add up to the ensemble's (FP64 fixed-order reductions): the properties the multi-GPU path
+    relies on.  Also linearity of the bias in its coefficients at this size."""
+    rng = np.random.default_rng(21)
+    n, half, seed, nsteps = 1000000, 400000, 20221019, 24
+    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    spec2 = dict(spec, weights=rng.standard_normal(spec["weights"].shape) * 0.3)
+    both = dict(spec, weights=spec["weights"] + spec2["weights"])
+
+    def run(count, offset, sp):
+        e = biasspec.make_ensemble(count, 2, seed, "fp32", potentials.DOUBLE_WELL_2D, None, sp)
+        e.set_walker_offset(offset)
+        assert e.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1.0 / (8.3145e-3 * 300)) == 0
+        e.init_velocities()
+        e.step(nsteps)
+        x, v = e.get_state()
+        sw, sf, _ = e.moments()
+        return e, x, v, sw.cpu().numpy(), sf.cpu().numpy()
+
+    e, x, v, sw, sf = run(n, 0, spec)
+    ea, xa, va, swa, sfa = run(half, 0, spec)
+    eb, xb, vb, swb, sfb = run(n - half, half, spec)
+    assert torch.equal(x[:, :half], xa) and torch.equal(x[:, half:], xb)
+    assert torch.equal(v[:, :half], va) and torch.equal(v[:, half:], vb)
+    assert sw[0] == n and swa[0] + swb[0] == n and abs(sf[0] - n) < 1e-6           # f_0 = P_0 P_0 = 1
+    assert np.max(np.abs(sfa + sfb - sf)) < 1e-6 * n
+    # linearity: E(w1 + w2) = E(w1) + E(w2), F likewise (FP32 evaluation, 10^6 rows)
+    pos = x.T.contiguous()
+    E1, F1 = e.eval_bias(pos)
+    biasspec.apply(e, spec2)
+    E2, F2 = e.eval_bias(pos)
+    biasspec.apply(e, both)
+    E12, F12 = e.eval_bias(pos)
+    scale = float(torch.max(torch.abs(E1)) + torch.max(torch.abs(E2)))
+    assert float(torch.max(torch.abs(E12 - (E1 + E2)))) < 2e-5 * scale
+    fscale = float(torch.max(torch.abs(F1)) + torch.max(torch.abs(F2)))
+    assert float(torch.max(torch.abs(F12 - (F1 + F2)))) < 2e-5 * fscale
+    for h in (e, ea, eb):
+        h.close()
+
+
 def test_general_kernel_3d_middle_record():
     """dims = 3 (z simulated, 1000 z^2), both schemes, trajectory recording (frame t before step t)."""
     rng = np.random.default_rng(3)
