@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--fes-updates", type=int, default=600,
                     help="untimed VES updates (100 MD steps each) run after the timed region before the FES RMSE is taken; 0 = skip")
     ap.add_argument("--seed", type=int, default=20221019)
+    ap.add_argument("--update", default="device", choices=["device", "host"],
+                    help="coefficient update of the resident-state loop: 'device' = optimiser, target refresh and coefficient "
+                         "hand-over on the GPU (DeviceUpdater), 'host' = numpy optimiser + re-upload (VESBias_Ensemble)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -154,6 +157,9 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    from pyves_b200.bias import DeviceUpdater
+    upd = DeviceUpdater(bias, ens) if args.update == "device" else None
+
     def iteration(timed):
         flush.zero_()                                            # evict the 126 MB L2 between iterations
         if timed:
@@ -164,8 +170,11 @@ def run_ours(args):
             b.record()
             step_events.append((a, b))
         sw, sf, _ = reduce_moments(*ens.moments())               # one NCCL allreduce of 1 + K doubles
-        bias.update_from_moments(sw, sf)                         # host optimiser on K coefficients
-        bias.force.apply(ens)                                    # re-upload the coefficients
+        if upd is not None:
+            upd.update(sw, sf)                                   # optimiser + target + coefficient hand-over, all enqueued
+        else:
+            bias.update_from_moments(sw, sf)                     # host optimiser on K coefficients
+            bias.force.apply(ens)                                # re-upload the coefficients
 
     peak = _lib.fp32_fma_peak(local) if rank == 0 else None     # before the timed region
     for _ in range(args.warmup):
@@ -190,6 +199,11 @@ def run_ours(args):
     elapsed = float(elapsed)
     value = n_total * args.stride * args.steps / elapsed
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
+
+    if upd is not None:                                          # hand the state back to the host-side objects
+        upd.sync_to_host()
+        upd.close()
+        bias.force.apply(ens)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     e2e = None
@@ -244,7 +258,10 @@ def run_ours(args):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "FFMA micro-benchmark run in this process (pyves_fp32_fma_peak); nominal 74.4",
                     "flops_per_walker_step": flops, "kernel_ms": kern_ms,
-                    "kernel_share_of_step": kern_ms * args.steps / (elapsed * 1e3), "traffic": None}
+                    "kernel_share_of_step": kern_ms * args.steps / (elapsed * 1e3),
+                    "traffic": 16.04e6 * args.walkers / 1e6 if args.basis == 16 else None,
+                    "traffic_note": "dram__bytes_read + dram__bytes_write per launch, ncu --set full capture "
+                                    "profiles/r01b_ncu_step_kernel.md (16 B of state per walker; the 16 MB written back stay in L2)"}
         out = {"metric": "walker-steps/s (2D double well, Legendre bias)", "value": value, "unit": "walker-steps/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -252,7 +269,8 @@ def run_ours(args):
                                       "(gamma 10, 100x100), averaged SGD update every %d steps, %d walkers per GPU"
                                       % (args.basis, args.basis, args.stride, args.walkers),
                           "walkers_total": n_total, "md_steps_per_bench_step": args.stride, "parallelism": "walkers sharded, dp%d" % world,
-                          "l2": "flushed between steps (256 MiB memset); state 16 MB/GPU is read once per 500 MD steps"},
+                          "l2": "flushed between steps (256 MiB memset); state 16 MB/GPU is read once per 500 MD steps",
+                          "update": args.update},
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
         if e2e:
             out["e2e"] = e2e

@@ -154,6 +154,14 @@ int pyves_moments(pyves_t* h, const void* pos, int64_t n, int ncols, const void*
 int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim, int axis, const double* range,
                     const int* nbins, const void* row_weights, double* counts, int on_host, void* stream);
 
+/* Same as pyves_set_bias_legendre2d with the coefficients read from DEVICE memory (FP64, row-major
+ * [deg_x + 1][deg_y + 1]) in stream order: the coefficient update of a device-resident optimiser reaches the
+ * step kernels without a host round trip (the per-update TorchScript save / TorchForce reload of
+ * ves/bias.py:249-253 + ves/langevin_dynamics.py:153-159 becomes one conversion kernel and, for the static
+ * 8 x 8 / 16 x 16 kernels, a device-to-device copy into their __constant__ weights).  w_dev is read when the
+ * stream reaches the call; the caller keeps it alive and unchanged until then. */
+int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const double* minmax, const double* w_dev, void* stream);
+
 /* Domain of the ensemble averages of pyves_moments for the Legendre / path-CV bases.  0 (default): every
  * row counts, rows outside the basis interval enter with their clamped coordinate, exactly what
  * LegendreBasis1D.forward does to them (ves/basis.py:143).  1: rows outside the interval get weight 0, i.e.

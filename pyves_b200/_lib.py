@@ -57,6 +57,7 @@ SIGNATURES = {
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
     "pyves_set_moment_domain": (_i, [_vp, _i]),
+    "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -226,6 +227,19 @@ class Ensemble:
             raise ValueError("weights must have (deg_x + 1) * (deg_y + 1) entries")
         m, mp = _darr(minmax)
         self._ck(self.lib.pyves_set_bias_legendre2d(self.h, deg_x, deg_y, mp, p))
+
+    def set_bias_legendre2d_device(self, deg_x, deg_y, minmax, w_dev):
+        """Coefficients from a CUDA float64 tensor [deg_x + 1, deg_y + 1] (or flat), read in stream order:
+        no host round trip between the optimiser and the next launch."""
+        import torch
+        if not (torch.is_tensor(w_dev) and w_dev.is_cuda and w_dev.dtype == torch.float64 and w_dev.is_contiguous()):
+            raise ValueError("w_dev must be a contiguous CUDA float64 tensor")
+        if w_dev.numel() != (deg_x + 1) * (deg_y + 1):
+            raise ValueError("weights must have (deg_x + 1) * (deg_y + 1) entries")
+        if w_dev.device.index != self.device:
+            raise ValueError("w_dev lives on another device")
+        m, mp = _darr(minmax)
+        self._ck(self.lib.pyves_set_bias_legendre2d_device(self.h, deg_x, deg_y, mp, ctypes.c_void_p(w_dev.data_ptr()), self.stream))
 
     def set_bias_mlp(self, axis, lo, hi, sizes, act, theta):
         a, p = _darr(theta)

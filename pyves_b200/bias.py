@@ -379,3 +379,97 @@ class VESBias_Ensemble(NNBias):
         V, _ = ens.eval_bias(tpos, want_force=False)
         F = -V.cpu().numpy() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
         return F - F.min()
+
+
+class DeviceUpdater:
+    """Device-resident update loop of a ``VESBias_Ensemble`` (``LegendreBasis2D`` model, first-order
+    ``averaged_sgd``): gradient, preconditioned averaged-SGD step, well-tempered target refresh and target
+    averages are K-sized CUDA tensor operations enqueued on the current stream, and the new coefficients reach
+    the step kernels through ``pyves_set_bias_legendre2d_device`` -- no device-to-host read, no host optimiser,
+    no re-upload between two launches, so the GPU never waits for Python.  Numerically it is the same update
+    as ``VESBias_Ensemble.update_from_moments`` (FP64), which remains the reference implementation;
+    ``sync_to_host()`` copies coefficients, optimiser state and target back into the bias object.
+
+    Replaces, for the ensemble, the per-update path ``bias.update`` -> TorchScript save -> ``TorchForce`` reload
+    -> ``context.reinitialize`` of ``ves/langevin_dynamics.py:147-159`` + ``ves/bias.py:206-253``.
+    """
+
+    def __init__(self, bias, ens):
+        if not isinstance(bias.model, LegendreBasis2D):
+            raise ValueError("DeviceUpdater needs a LegendreBasis2D model")
+        if bias.optimizer_type != 'averaged_sgd' or bias.optimizer.second_order or bias.grad_avg is not None:
+            raise ValueError("DeviceUpdater implements the first-order averaged_sgd update without gradient averaging")
+        self.bias, self.ens = bias, ens
+        m, o = bias.model, bias.optimizer
+        self.dev = torch.device("cuda", ens.device)
+        self.deg = (m.degree_x, m.degree_y)
+        self.minmax = (m.min_x, m.max_x, m.min_y, m.max_y)
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.alpha = torch.tensor(o.alpha, **f64)
+        self.abar = torch.tensor(o.abar, **f64)
+        self.scale = None if o.scale is None else torch.tensor(o.scale, **f64)
+        self.mu, self.decay, self.averaging, self.n = o.mu, o.decay, o.averaging, o.n
+        self.n_updates = bias.n_updates
+        # target: nodes in real coordinates, density, node averages of the basis functions (FP64 evaluator handle)
+        self.ev = _lib.Ensemble(1, dims=2, precision="fp64", device=ens.device)
+        self.tpos = torch.tensor(bias._target_positions(), **f64).contiguous()
+        self.p = torch.tensor(np.asarray(bias.target.p, dtype=np.float64), **f64)
+        self.refreshable = hasattr(bias.target, "bias_factor")
+        self.cell = 4.0 / float(len(bias.target.p))
+        self.ev.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        self.f_target = self._target_average()
+        ens.set_moment_domain(bias.sample_domain == 'box')
+        ens.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        if self.refreshable:
+            self._refreshed_density()       # result discarded: loads the kernels of the refresh path (CUDA loads lazily)
+
+    def _target_average(self):
+        q = (self.p / self.p.sum()).contiguous()            # Target_2D.quadrature_weights
+        sw, sf, _ = self.ev.moments(pos=self.tpos, row_weights=q)
+        return sf / sw
+
+    def update(self, sum_w, sum_wf):
+        """One update from ensemble sums on the device (already reduced over all GPUs).  Enqueue only."""
+        grad = self.f_target - sum_wf / sum_w
+        d = grad if self.scale is None else grad * self.scale
+        self.alpha = self.alpha - self.mu * d
+        self.n += 1
+        if self.averaging == 'ewma':
+            self.abar = self.decay * self.abar + (1.0 - self.decay) * self.alpha
+        else:
+            self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
+        self.abar = self.abar.contiguous()
+        self.n_updates += 1
+        self.ens.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        b = self.bias
+        if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
+            self.p = self._refreshed_density()
+            self.f_target = self._target_average()
+
+    def _refreshed_density(self):
+        """Target_WellTempered_2D.update on the device: p' ~ exp(-(beta / gamma) F), F = -V - kT ln p."""
+        b = self.bias
+        self.ev.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        V, _ = self.ev.eval_bias(self.tpos, want_force=False)
+        F = -V - torch.log(torch.clamp(self.p, min=1e-300)) / b.beta
+        q = torch.exp(-(b.beta / b.target.bias_factor) * (F - F.min()))
+        return q / (q.sum() * self.cell)
+
+    def sync_to_host(self):
+        """Copy the device state back into the bias object (coefficients, optimiser, target)."""
+        b, o = self.bias, self.bias.optimizer
+        o.alpha = self.alpha.cpu().numpy().copy()
+        o.abar = self.abar.cpu().numpy().copy()
+        o.n = self.n
+        b.n_updates = self.n_updates
+        with torch.no_grad():
+            off = 0
+            for prm in b.model.parameters():
+                prm.copy_(torch.from_numpy(o.abar[off:off + prm.numel()].reshape(tuple(prm.shape))))
+                off += prm.numel()
+        if self.refreshable:
+            b.target._p = self.p.cpu().numpy().copy()
+        b._f_target = self.f_target.cpu().numpy().copy()
+
+    def close(self):
+        self.ev.close()

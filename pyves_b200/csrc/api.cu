@@ -14,6 +14,9 @@
 using namespace pv;
 
 static std::atomic<int64_t> g_launches{0};
+// which handle's weights the __constant__ array currently holds, per device (serial << 32 | version)
+std::atomic<uint64_t> g_const_owner[64];
+std::atomic<uint64_t> g_handle_serial{1};
 static thread_local std::string g_err;
 
 struct pyves_ctx {
@@ -41,6 +44,12 @@ struct pyves_ctx {
   double l2_mm[4] = {-1, 1, -1, 1};
   std::vector<double> l2_w;
   void* l2_w_dev = nullptr;
+  // device-resident coefficients (pyves_set_bias_legendre2d_device)
+  bool l2_dev_mode = false;      // weights live on the device only: the host copy l2_w is stale
+  void* l2_wt_dev = nullptr;     // transposed element-type copy wt[ky][kx] (source of the __constant__ upload)
+  size_t l2_dev_count = 0;       // elements allocated in l2_w_dev / l2_wt_dev
+  uint64_t l2_version = 0;       // bumped by every device update
+  uint64_t serial = 0;           // unique per handle (owner tag of the __constant__ weights)
   // MLP
   int mlp_axis = 0, mlp_act = 0;
   double mlp_lo = 0, mlp_hi = 1;
@@ -199,6 +208,16 @@ template <typename T, int KX, int KY> Legendre2DStaticTParams<T, KX, KY> l2_stat
   return P;
 }
 
+template <typename T, int KX, int KY> Legendre2DStaticTCParams<T, KX, KY> l2_static_tc_params(const pyves_ctx* h) {
+  const Legendre2DSmemParams<T> S = l2_params<T>(h);
+  Legendre2DStaticTCParams<T, KX, KY> P;
+  P.cx = S.cx;
+  P.ihx = S.ihx;
+  P.cy = S.cy;
+  P.ihy = S.ihy;
+  return P;
+}
+
 template <typename T> MlpParams<T> mlp_params(const pyves_ctx* h) {
   MlpParams<T> P;
   P.axis = h->mlp_axis;
@@ -321,12 +340,22 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
       const Legendre2DSmemParams<T> BP = l2_params<T>(h);
       if (pk == PYVES_POT_DOUBLE_WELL_2D) {
+        if (h->l2_dev_mode && ((kx == 8 && ky == 8) || (kx == 16 && ky == 16)) && h->device < 64) {
+          // coefficients were set from a device pointer: the kernels read them from the __constant__ array
+          const uint64_t tag = (h->serial << 32) | (h->l2_version & 0xffffffffull);
+          if (g_const_owner[h->device].load() != tag) {
+            CU(upload_static_weights<T>(static_cast<const T*>(h->l2_wt_dev), kx * ky, st));
+            g_const_owner[h->device].store(tag);
+          }
+          if (kx == 8) return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8, true>, 2, 1>(h, A, l2_static_tc_params<T, 8, 8>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, true>, 1, 1>(h, A, l2_static_tc_params<T, 16, 16>(h), st);
+        }
         // variant 1 selects the row-major functor (kept for tuning runs); default = column sweep
-        if (kx == 8 && ky == 8) {
+        if (kx == 8 && ky == 8 && !h->l2_dev_mode) {
           if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 8, 8>, 2, 1>(h, A, l2_static_params<T, 8, 8>(h), st);
           return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8>, 2, 1>(h, A, l2_static_t_params<T, 8, 8>(h), st);
         }
-        if (kx == 16 && ky == 16) {
+        if (kx == 16 && ky == 16 && !h->l2_dev_mode) {
           if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
           return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
         }
@@ -434,6 +463,24 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
   return PYVES_OK;
 }
 
+// Which handle's weights the __constant__ array of this process currently holds, per device
+// (handle serial << 32 | version); a launch in device mode re-copies its 1 KB when it is not the owner.
+
+template <typename T> static int set_l2_device(pyves_ctx* h, const double* w_dev, int kx, int ky, cudaStream_t st) {
+  const size_t K = (size_t)kx * ky;
+  if (h->l2_dev_count != K || !h->l2_w_dev || !h->l2_wt_dev) {
+    if (h->l2_w_dev) cudaFree(h->l2_w_dev);
+    if (h->l2_wt_dev) cudaFree(h->l2_wt_dev);
+    h->l2_w_dev = h->l2_wt_dev = nullptr;
+    CU(cudaMalloc(&h->l2_w_dev, K * sizeof(T)));
+    CU(cudaMalloc(&h->l2_wt_dev, K * sizeof(T)));
+    h->l2_dev_count = K;
+  }
+  CU(launch_convert_weights2d<T>(w_dev, kx, ky, static_cast<T*>(h->l2_w_dev), static_cast<T*>(h->l2_wt_dev), st));
+  g_launches++;
+  return PYVES_OK;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -458,6 +505,7 @@ int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_
   h = new (std::nothrow) pyves_ctx();
   if (!h) return fail(nullptr, PYVES_ENOMEM, "out of host memory");
   h->device = device;
+  h->serial = g_handle_serial.fetch_add(1);
   h->n = n_walkers;
   h->dims = dims;
   h->seed = seed;
@@ -482,7 +530,7 @@ int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_
 int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
-  void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
+  void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
                   h->scratch, h->stage, h->fail_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -610,6 +658,32 @@ int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm
   h->l2_w.assign(w, w + K);
   const int rc = upload(h, &h->l2_w_dev, w, K);
   if (rc) return rc;
+  h->l2_dev_mode = false;
+  h->l2_dev_count = 0;           // upload() reallocated l2_w_dev
+  h->bias_kind = PYVES_BIAS_LEGENDRE_2D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const double* mm, const double* w_dev, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (deg_x < 0 || deg_x > PYVES_MAX_DEGREE || deg_y < 0 || deg_y > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degrees must be in [0, 63]");
+  if (!mm || !w_dev || !(mm[1] > mm[0]) || !(mm[3] > mm[2])) return fail(h, PYVES_EINVAL, "need max > min per axis and weights");
+  DeviceGuard g(h->device);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, w_dev) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    return fail(h, PYVES_EINVAL, "w_dev must be a device pointer (FP64, [deg_x + 1][deg_y + 1])");
+  }
+  h->l2_dx = deg_x;
+  h->l2_dy = deg_y;
+  std::memcpy(h->l2_mm, mm, sizeof(h->l2_mm));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rc = h->prec == PYVES_F64 ? set_l2_device<double>(h, w_dev, deg_x + 1, deg_y + 1, st)
+                                      : set_l2_device<float>(h, w_dev, deg_x + 1, deg_y + 1, st);
+  if (rc) return rc;
+  h->l2_dev_mode = true;
+  h->l2_version++;
+  h->l2_w.clear();               // no host copy in this mode
   h->bias_kind = PYVES_BIAS_LEGENDRE_2D;
   return PYVES_OK;
 }

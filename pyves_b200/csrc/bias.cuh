@@ -9,6 +9,8 @@
 //   stage(P, smem)               cooperative fill of shared memory (all threads; caller syncs)
 //   grad<WANT_E>(P, smem, x, y, e, gx, gy)   ACCUMULATES dV/dx, dV/dy (and V when WANT_E)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pv {
@@ -174,8 +176,27 @@ template <typename T, int KX, int KY> struct Legendre2DStaticTParams {
   T wt[KY * KX];   // wt[j * KX + i] = w_ij
 };
 
-template <typename T, int KX, int KY> struct BiasLegendre2DStaticT {
-  using Params = Legendre2DStaticTParams<T, KX, KY>;
+// Device-resident coefficient updates (pyves_set_bias_legendre2d_device): kernel parameters come from the
+// host, so the static functor can instead read its weights from a __constant__ array that is refreshed with a
+// stream-ordered device-to-device cudaMemcpyToSymbolAsync -- same constant-bank operands (bank 3 instead of
+// the parameter bank 0), no host round trip between two launches.  One copy per translation unit; the kernels
+// and launch_upload_static_weights of langevin_inst.cu (group 0) share theirs.
+constexpr int kConstWeights = 256;
+static __constant__ float c_wt_f32[kConstWeights];
+static __constant__ double c_wt_f64[kConstWeights];
+template <typename T> PV_DEV const T* const_weights();
+template <> PV_DEV const float* const_weights<float>() { return c_wt_f32; }
+template <> PV_DEV const double* const_weights<double>() { return c_wt_f64; }
+
+template <typename T, int KX, int KY> struct Legendre2DStaticTCParams {
+  T cx, ihx, cy, ihy;
+};
+
+template <typename T, int KX, int KY, bool CONSTSYM = false> struct BiasLegendre2DStaticT {
+  using Params = typename std::conditional<CONSTSYM, Legendre2DStaticTCParams<T, KX, KY>, Legendre2DStaticTParams<T, KX, KY>>::type;
+  static_assert(!CONSTSYM || KX * KY <= kConstWeights, "constant weight array too small");
+  template <bool C = CONSTSYM> static PV_DEV typename std::enable_if<C, T>::type weight(const Params&, int idx) { return const_weights<T>()[idx]; }
+  template <bool C = CONSTSYM> static PV_DEV typename std::enable_if<!C, T>::type weight(const Params& P, int idx) { return P.wt[idx]; }
   static_assert(KX >= 2 && KY >= 2, "static sizes start at 2 x 2");
   static size_t smem_bytes(const Params&) { return 0; }
   static PV_DEV void stage(const Params&, void*) {}
@@ -189,7 +210,7 @@ template <typename T, int KX, int KY> struct BiasLegendre2DStaticT {
     {
       const Pair<T> Q1 = Pair<T>::make(sy, T(1));
 #pragma unroll
-      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, weight(P, 1 * KX + i), Pair<T>::make(weight(P, i), T(0)));
     }
 #pragma unroll
     for (int j = 2; j < KY; ++j) {
@@ -198,7 +219,7 @@ template <typename T, int KX, int KY> struct BiasLegendre2DStaticT {
       pm = p; p = pn; dpm = dp; dp = dpn;
       const Pair<T> Q = Pair<T>::make(p, dp);
 #pragma unroll
-      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, weight(P, j * KX + i), AB[i]);
     }
     // row sweep: (dV/dsx, dV/dsy) = sum_i (P'_i(x'), P_i(x')) * (A_i, B_i), two chains
     Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));

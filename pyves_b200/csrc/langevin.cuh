@@ -229,6 +229,10 @@ langevin_general_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const 
   }
 }
 
+// copies n converted weights (device, element type T, transposed wt[j][i]) into the __constant__ array the
+// BiasLegendre2DStaticT<.., true> kernels read (same translation unit as those kernels); stream ordered
+template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n, cudaStream_t st);
+
 // launchers implemented in the langevin_*.cu translation units
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 cudaError_t launch_langevin2d(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,

@@ -28,6 +28,13 @@ PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8 PV_COMMA true>, 2, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA true>, 1, 1)
+template <> cudaError_t upload_static_weights<T>(const T* dev_src, int n, cudaStream_t st) {
+  if (n > kConstWeights) return cudaErrorInvalidValue;
+  if (sizeof(T) == 4) return cudaMemcpyToSymbolAsync(c_wt_f32, dev_src, (size_t)n * sizeof(T), 0, cudaMemcpyDeviceToDevice, st);
+  return cudaMemcpyToSymbolAsync(c_wt_f64, dev_src, (size_t)n * sizeof(T), 0, cudaMemcpyDeviceToDevice, st);
+}
 #elif PV_GROUP == 1  // slip bond, Szabo-Berezhkovskii
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)

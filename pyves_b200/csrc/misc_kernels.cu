@@ -269,9 +269,26 @@ cudaError_t fp32_fma_peak(double* tflops, int packed) {
   return cudaGetLastError();
 }
 
+template <typename T>
+__global__ void convert_weights2d_kernel(const double* __restrict__ w64, int kx, int ky, T* __restrict__ w_rm, T* __restrict__ w_t) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kx * ky) return;
+  const int i = idx / ky, j = idx - i * ky;
+  const T v = (T)w64[idx];
+  w_rm[idx] = v;
+  w_t[j * kx + i] = v;
+}
+
+template <typename T>
+cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm, T* w_t, cudaStream_t st) {
+  convert_weights2d_kernel<T><<<(kx * ky + 255) / 256, 256, 0, st>>>(w64, kx, ky, w_rm, w_t);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 #define PV_INST(T)                                                                                                 \
   template cudaError_t launch_eval_bias<T>(const T*, int64_t, int, T*, T*, const BiasAnyParams<T>&, cudaStream_t); \
+  template cudaError_t launch_convert_weights2d<T>(const double*, int, int, T*, T*, cudaStream_t);                 \
   template cudaError_t launch_energies<T>(const T*, const T*, int64_t, int, T*, T*, T, T, const PotParams<T>&,     \
                                           const BiasAnyParams<T>&, cudaStream_t);                                  \
   template cudaError_t launch_init_positions<T>(T*, int64_t, int, uint64_t, const double*, double, int,            \

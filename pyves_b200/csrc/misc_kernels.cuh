@@ -9,6 +9,11 @@ namespace pv {
 template <typename T>
 cudaError_t launch_eval_bias(const T* pos, int64_t n, int ncols, T* E, T* F, const BiasAnyParams<T>& BP, cudaStream_t st);
 
+// device-resident coefficient update: w64[kx][ky] (FP64, device) -> row-major T copy w_rm[kx][ky] (runtime
+// functors, eval) and transposed T copy w_t[ky][kx] (static column-sweep functors)
+template <typename T>
+cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm, T* w_t, cudaStream_t st);
+
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>
 cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,

@@ -286,3 +286,50 @@ def test_ensemble_second_order_slip_bond():
     assert rmse < 0.3, rmse
     pos = sim.get_state().positions
     assert (pos[:, 0] < -2).mean() > 0.2 and (pos[:, 0] > 4).mean() > 0.2
+
+
+def test_device_resident_update_matches_host_update():
+    """DeviceUpdater (optimiser, well-tempered target refresh and coefficient hand-over all on the device,
+    pyves_set_bias_legendre2d_device) reproduces VESBias_Ensemble.update_from_moments: same coefficients, target
+    and walkers after 24 updates, for the static 16 x 16 kernels (weights in the __constant__ array) and a
+    runtime-size basis (weights in a device buffer)."""
+    from pyves_b200 import _lib
+    from pyves_b200.bias import DeviceUpdater
+    kT = 8.3145e-3 * 300
+    for deg in (15, 9):
+        runs = []
+        for mode in ("host", "device"):
+            model = basis.LegendreBasis2D(deg, deg, -2.5, 2.5, -2.0, 2.0)
+            tgt = target.Target_WellTempered_2D(40, 40, 10.0)
+            b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd",
+                                      {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=5)
+            ens = _lib.Ensemble(30000, dims=2, seed=7, precision="fp32")
+            ens.set_integrator(1.0, 8.31446261815324e-3 * 300, 20.0, 0.01)
+            ens.set_potential(_lib.POT_DOUBLE_WELL_2D)
+            assert ens.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1 / kT) == 0
+            ens.init_velocities()
+            if mode == "host":
+                b.force.apply(ens)
+                for _ in range(24):
+                    ens.step(20)
+                    sw, sf, _ = ens.moments()
+                    b.update_from_moments(sw, sf)
+                    b.force.apply(ens)
+            else:
+                upd = DeviceUpdater(b, ens)
+                for _ in range(24):
+                    ens.step(20)
+                    sw, sf, _ = ens.moments()
+                    upd.update(sw, sf)
+                upd.sync_to_host()
+                upd.close()
+            x, _ = ens.get_state(host=True)
+            runs.append((b.optimizer.abar.copy(), b.optimizer.alpha.copy(), np.asarray(tgt.p).copy(), x, b.n_updates))
+            ens.close()
+        (a0, al0, p0, x0, n0), (a1, al1, p1, x1, n1) = runs
+        assert n0 == n1 == 24
+        scale = np.max(np.abs(a0))
+        assert scale > 0.1
+        assert np.max(np.abs(a0 - a1)) < 1e-9 * scale and np.max(np.abs(al0 - al1)) < 1e-9 * np.max(np.abs(al0))
+        assert np.max(np.abs(p0 - p1)) < 1e-9 * np.max(p0)
+        assert np.array_equal(x0, x1)
