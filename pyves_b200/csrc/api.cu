@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -50,6 +51,7 @@ struct pyves_ctx {
   size_t l2_dev_count = 0;       // elements allocated in l2_w_dev / l2_wt_dev
   uint64_t l2_version = 0;       // bumped by every device update
   uint64_t serial = 0;           // unique per handle (owner tag of the __constant__ weights)
+  std::map<void**, size_t> alloc_count;   // element counts of the buffers managed by upload()
   // MLP
   int mlp_axis = 0, mlp_act = 0;
   double mlp_lo = 0, mlp_hi = 1;
@@ -128,10 +130,17 @@ int ensure_stage(pyves_ctx* h, size_t bytes) {
 
 // upload a double host array as the handle's element type
 int upload(pyves_ctx* h, void** dev, const double* src, size_t count) {
-  if (*dev) cudaFree(*dev);
-  *dev = nullptr;
-  if (count == 0) return PYVES_OK;
-  CU(cudaMalloc(dev, count * h->esz));
+  // the buffer is reused when the size is unchanged (coefficient updates): cudaFree would synchronise the device
+  auto it = h->alloc_count.find(dev);
+  const bool reuse = *dev != nullptr && it != h->alloc_count.end() && it->second == count && count > 0;
+  if (!reuse) {
+    if (*dev) cudaFree(*dev);
+    *dev = nullptr;
+    h->alloc_count.erase(dev);
+    if (count == 0) return PYVES_OK;
+    CU(cudaMalloc(dev, count * h->esz));
+    h->alloc_count[dev] = count;
+  }
   if (h->prec == PYVES_F64) {
     CU(cudaMemcpy(*dev, src, count * sizeof(double), cudaMemcpyHostToDevice));
   } else {
@@ -472,6 +481,7 @@ template <typename T> static int set_l2_device(pyves_ctx* h, const double* w_dev
     if (h->l2_w_dev) cudaFree(h->l2_w_dev);
     if (h->l2_wt_dev) cudaFree(h->l2_wt_dev);
     h->l2_w_dev = h->l2_wt_dev = nullptr;
+    h->alloc_count.erase(&h->l2_w_dev);
     CU(cudaMalloc(&h->l2_w_dev, K * sizeof(T)));
     CU(cudaMalloc(&h->l2_wt_dev, K * sizeof(T)));
     h->l2_dev_count = K;
