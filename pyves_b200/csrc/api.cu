@@ -297,6 +297,14 @@ int run_fast(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP
   return PYVES_OK;
 }
 
+template <typename T, class Pot, class Bias>
+int run_pair(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP, cudaStream_t st) {
+  if (h->variant == 1) return run_fast<T, Pot, Bias, 2, 1>(h, A, BP, st);   // scalar two-walker kernel (tuning runs)
+  CU((launch_langevin2d_pair<T, Pot, Bias, 1>(A, integrator_params<T>(h), pot_params<T>(h), BP, make_keys(h->seed), st)));
+  g_launches++;
+  return PYVES_OK;
+}
+
 template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaStream_t st) {
   if (h->bias_kind == PYVES_BIAS_MLP_1D) {
     for (int w : h->mlp_sizes)
@@ -334,16 +342,16 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
   switch (h->bias_kind) {
     case PYVES_BIAS_NONE: {
       typename BiasNone<T>::Params BP;
-      if (pk == PYVES_POT_DOUBLE_WELL_2D) return run_fast<T, DW, BiasNone<T>, 2, 1>(h, A, BP, st);
-      if (pk == PYVES_POT_SLIP_BOND_2D) return run_fast<T, SL, BiasNone<T>, 2, 1>(h, A, BP, st);
-      if (pk == PYVES_POT_SZABO_BEREZHKOVSKII) return run_fast<T, SB, BiasNone<T>, 2, 1>(h, A, BP, st);
-      return run_fast<T, GP, BiasNone<T>, 2, 1>(h, A, BP, st);
+      if (pk == PYVES_POT_DOUBLE_WELL_2D) return run_pair<T, DW, BiasNone<T>>(h, A, BP, st);
+      if (pk == PYVES_POT_SLIP_BOND_2D) return run_pair<T, SL, BiasNone<T>>(h, A, BP, st);
+      if (pk == PYVES_POT_SZABO_BEREZHKOVSKII) return run_pair<T, SB, BiasNone<T>>(h, A, BP, st);
+      return run_pair<T, GP, BiasNone<T>>(h, A, BP, st);
     }
     case PYVES_BIAS_LEGENDRE_1D: {
       const Legendre1DParams<T> BP = l1_params<T>(h);
-      if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_fast<T, DW, BiasLegendre1D<T, 5>, 2, 1>(h, A, BP, st);
-      if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_fast<T, SL, BiasLegendre1D<T, 12>, 2, 1>(h, A, BP, st);
-      return run_fast<T, GP, BiasLegendre1D<T, 0>, 2, 1>(h, A, BP, st);
+      if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair<T, DW, BiasLegendre1D<T, 5>>(h, A, BP, st);
+      if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair<T, SL, BiasLegendre1D<T, 12>>(h, A, BP, st);
+      return run_pair<T, GP, BiasLegendre1D<T, 0>>(h, A, BP, st);
     }
     case PYVES_BIAS_LEGENDRE_2D: {
       const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;

@@ -83,6 +83,59 @@ template <typename T, int DEG> struct BiasLegendre1D {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Two walkers per thread in packed form (lo = walker a, hi = walker b), for the light biases whose step is
+// issue bound: every FP32 operation of the pair is ONE packed FP32x2 instruction.  The default evaluates the
+// scalar functor half by half.
+template <class Bias, typename T> struct BiasPair {
+  static PV_DEV void grad2(const typename Bias::Params& P, const void* smem, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) {
+    T e = T(0), ax = gx.lo(), ay = gy.lo(), bx = gx.hi(), by = gy.hi();
+    Bias::template grad<false>(P, smem, x.lo(), y.lo(), e, ax, ay);
+    Bias::template grad<false>(P, smem, x.hi(), y.hi(), e, bx, by);
+    gx = Pair<T>::make(ax, bx);
+    gy = Pair<T>::make(ay, by);
+  }
+};
+
+template <typename T> struct BiasPair<BiasNone<T>, T> {
+  static PV_DEV void grad2(const typename BiasNone<T>::Params&, const void*, Pair<T>, Pair<T>, Pair<T>&, Pair<T>&) {}
+};
+
+template <typename T, int DEG> struct BiasPair<BiasLegendre1D<T, DEG>, T> {
+  using Q = Pair<T>;
+  static PV_DEV void grad2(const Legendre1DParams<T>& P, const void*, Q x, Q y, Q& gx, Q& gy) {
+    const Q q = P.axis ? y : x;
+    const Q sraw = Q::mul_bcast(Q::add_bcast(q, -P.centre), P.inv_half);
+    const T s0 = sraw.lo(), s1 = sraw.hi();
+    const bool in0 = (s0 >= T(-1)) && (s0 <= T(1)), in1 = (s1 >= T(-1)) && (s1 <= T(1));
+    const Q s = Q::make(Math<T>::min(Math<T>::max(s0, T(-1)), T(1)), Math<T>::min(Math<T>::max(s1, T(-1)), T(1)));
+    const int deg = DEG > 0 ? DEG : P.degree;
+    Q pm = Q::make(T(1), T(1)), p = s, dpm = Q::make(T(0), T(0)), dp = Q::make(T(1), T(1));
+    Q g = deg >= 1 ? Q::make(P.w[1], P.w[1]) : Q::make(T(0), T(0));
+    if (DEG > 0) {
+#pragma unroll
+      for (int n = 1; n < DEG; ++n) {
+        const Q pn = Q::fma(Q::mul_bcast(s, leg_a<T>(n)), p, Q::mul_bcast(pm, -leg_b<T>(n)));
+        const Q dpn = Q::fma_bcast(p, leg_c<T>(n), dpm);
+        g = Q::fma_bcast(dpn, P.w[n + 1], g);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+      }
+    } else {
+      for (int n = 1; n < deg; ++n) {
+        const T fn = T(n), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
+        const Q pn = Q::fma(Q::mul_bcast(s, c * inv), p, Q::mul_bcast(pm, -fn * inv));
+        const Q dpn = Q::fma_bcast(p, c, dpm);
+        g = Q::fma_bcast(dpn, P.w[n + 1], g);
+        pm = p; p = pn; dpm = dp; dp = dpn;
+      }
+    }
+    g = Q::mul_bcast(g, P.inv_half);
+    const Q gm = Q::make(in0 ? g.lo() : T(0), in1 ? g.hi() : T(0));
+    if (P.axis) gy = Q::add(gy, gm);
+    else gx = Q::add(gx, gm);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // 2D tensor-product Legendre basis, V = sum_ij w_ij P_i(x') P_j(y')  (per-axis
 // conventions of ves/basis.py:143-147).  Fills Py[0..KY), dPy[0..KY) by recursion.
 template <typename T, int KY> PV_DEV void legendre_fill(T s, T (&P)[KY], T (&dP)[KY]) {

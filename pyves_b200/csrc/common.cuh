@@ -71,6 +71,18 @@ template <> struct Pair<float> {
     const Pair ww = make(w, w);
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(ww.v));
   }
+  static PV_DEV Pair mul(Pair a, Pair b) {
+    Pair d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+  }
+  static PV_DEV Pair mul_bcast(Pair a, float w) { return mul(a, make(w, w)); }
+  static PV_DEV Pair add(Pair a, Pair b) {
+    Pair d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+  }
+  static PV_DEV Pair add_bcast(Pair a, float w) { return add(a, make(w, w)); }
 };
 
 template <> struct Pair<double> {
@@ -81,6 +93,10 @@ template <> struct Pair<double> {
   static PV_DEV Pair fma_bcast(Pair a, double w, Pair c) { return Pair{::fma(a.x, w, c.x), ::fma(a.y, w, c.y)}; }
   static PV_DEV Pair fma(Pair a, Pair b, Pair c) { return Pair{::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)}; }
   static PV_DEV void acc_bcast(Pair& acc, Pair a, double w) { acc.x = ::fma(a.x, w, acc.x); acc.y = ::fma(a.y, w, acc.y); }
+  static PV_DEV Pair mul(Pair a, Pair b) { return Pair{a.x * b.x, a.y * b.y}; }
+  static PV_DEV Pair mul_bcast(Pair a, double w) { return Pair{a.x * w, a.y * w}; }
+  static PV_DEV Pair add(Pair a, Pair b) { return Pair{a.x + b.x, a.y + b.y}; }
+  static PV_DEV Pair add_bcast(Pair a, double w) { return Pair{a.x + w, a.y + w}; }
 };
 
 // 128-bit broadcast load of loop-invariant coefficients from shared memory.  It is `asm volatile` on

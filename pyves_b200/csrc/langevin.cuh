@@ -130,6 +130,126 @@ langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotPar
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed fast path for the light biases (none, Legendre 1D): two walkers per thread held as Pair<T> (lo, hi),
+// so the potential, the bias recursion, the Box-Muller scaling and the integrator are packed FP32x2
+// instructions -- one issue slot per two walkers.  These steps are issue bound (77 instructions per walker-step
+// for 49 FMA-pipe cycles in the scalar kernel); Philox and the MUFU calls stay scalar.  Same arithmetic per
+// walker as langevin2d_kernel (each half of an FFMA2 is an IEEE FMA).
+template <typename T> PV_DEV void box_muller_pair(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, Pair<T>& z0, Pair<T>& z1);
+
+template <> PV_DEV void box_muller_pair<float>(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, Pair<float>& z0, Pair<float>& z1) {
+  using Q = Pair<float>;
+  const Q u1 = Q::fma_bcast(Q::make(__uint2float_rn(a0), __uint2float_rn(b0)), 2.3283064365386963e-10f,
+                            Q::make(1.1641532182693481e-10f, 1.1641532182693481e-10f));
+  float la, lb;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"(u1.lo()));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lb) : "f"(u1.hi()));
+  const Q m2ln = Q::mul_bcast(Q::make(la, lb), -1.3862943611198906f);
+  float ra, rb;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(m2ln.lo()));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(m2ln.hi()));
+  const Q th = Q::fma_bcast(Q::make(__uint2float_rn(a1), __uint2float_rn(b1)), 1.4629180792671596e-09f,
+                            Q::make(-3.1415926528583340f, -3.1415926528583340f));
+  float sa, ca, sb, cb;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sa) : "f"(th.lo()));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(ca) : "f"(th.lo()));
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sb) : "f"(th.hi()));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cb) : "f"(th.hi()));
+  const Q rad = Q::make(ra, rb);
+  z0 = Q::mul(rad, Q::make(ca, cb));
+  z1 = Q::mul(rad, Q::make(sa, sb));
+}
+
+template <> PV_DEV void box_muller_pair<double>(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, Pair<double>& z0, Pair<double>& z1) {
+  double za0, za1, zb0, zb1;
+  box_muller(a0, a1, za0, za1);
+  box_muller(b0, b1, zb0, zb1);
+  z0 = Pair<double>::make(za0, zb0);
+  z1 = Pair<double>::make(za1, zb1);
+}
+
+template <typename T, class Pot, class Bias, int MINB, bool INJECT>
+__global__ void __launch_bounds__(kStepThreads, MINB)
+langevin2d_pair_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotParams<T> PP,
+                       const typename Bias::Params BP, const RngKeys K) {
+  using Q = Pair<T>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Bias::stage(BP, smem);
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (kStepThreads * 2) + threadIdx.x;
+  int64_t w[2];
+  bool live[2];
+  T x0[2], y0[2], vx0[2], vy0[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int64_t idx = base + (int64_t)k * kStepThreads;
+    live[k] = idx < A.n;
+    w[k] = live[k] ? idx : A.n - 1;
+    x0[k] = A.pos[w[k]];
+    y0[k] = A.pos[A.n + w[k]];
+    vx0[k] = A.vel[w[k]];
+    vy0[k] = A.vel[A.n + w[k]];
+  }
+  Q X = Q::make(x0[0], x0[1]), Y = Q::make(y0[0], y0[1]), VX = Q::make(vx0[0], vx0[1]), VY = Q::make(vy0[0], vy0[1]);
+
+  auto advance = [&](Q ZX, Q ZY) {
+    Q GX = Q::make(T(0), T(0)), GY = GX;
+    PotPair<Pot, T>::grad2(PP, X, Y, GX, GY);
+    BiasPair<Bias, T>::grad2(BP, smem, X, Y, GX, GY);
+    VX = Q::fma_bcast(ZX, I.c_over_sqrtm, Q::fma_bcast(GX, -I.b_over_m, Q::mul_bcast(VX, I.a)));
+    VY = Q::fma_bcast(ZY, I.c_over_sqrtm, Q::fma_bcast(GY, -I.b_over_m, Q::mul_bcast(VY, I.a)));
+    X = Q::fma_bcast(VX, I.dt, X);
+    Y = Q::fma_bcast(VY, I.dt, Y);
+  };
+  // noise of steps 2c and 2c+1 for both walkers: Z[0], Z[1] = (zx, zy) of the even step, Z[2], Z[3] of the odd one
+  auto draw = [&](int64_t t_even, Q (&Z)[4]) {
+    if (INJECT) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t ts = t_even + (q >> 1) - A.step0;
+        const bool ok = ts >= 0 && ts < A.nsteps;
+        Z[q] = Q::make(ok ? A.noise[(ts * 2 + (q & 1)) * A.n + w[0]] : T(0), ok ? A.noise[(ts * 2 + (q & 1)) * A.n + w[1]] : T(0));
+      }
+    } else {
+      const uint4 ra = philox_call(A.gid0 + (uint64_t)w[0], (uint64_t)(t_even >> 1), kStreamDyn2, K);
+      const uint4 rb = philox_call(A.gid0 + (uint64_t)w[1], (uint64_t)(t_even >> 1), kStreamDyn2, K);
+      box_muller_pair<T>(ra.x, ra.y, rb.x, rb.y, Z[0], Z[1]);
+      box_muller_pair<T>(ra.z, ra.w, rb.z, rb.w, Z[2], Z[3]);
+    }
+  };
+
+  int64_t t = A.step0;
+  const int64_t end = A.step0 + A.nsteps;
+  if ((t & 1) && t < end) {   // odd head: second half of its Philox call
+    Q Z[4];
+    draw(t - 1, Z);
+    advance(Z[2], Z[3]);
+    ++t;
+  }
+  for (; t + 1 < end; t += 2) {
+    Q Z[4];
+    draw(t, Z);
+    advance(Z[0], Z[1]);
+    advance(Z[2], Z[3]);
+  }
+  if (t < end) {              // even tail: first half of its Philox call
+    Q Z[4];
+    draw(t, Z);
+    advance(Z[0], Z[1]);
+  }
+  const T xo[2] = {X.lo(), X.hi()}, yo[2] = {Y.lo(), Y.hi()}, vxo[2] = {VX.lo(), VX.hi()}, vyo[2] = {VY.lo(), VY.hi()};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (live[k]) {
+      A.pos[w[k]] = xo[k];
+      A.pos[A.n + w[k]] = yo[k];
+      A.vel[w[k]] = vxo[k];
+      A.vel[A.n + w[k]] = vyo[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // General path: 2 or 3 dimensions, both schemes, optional trajectory recording, one walker per
 // thread, any potential (PotGeneric) and any bias (BiasAny).  Used for reference-format runs
 // (n_walkers = 1, z simulated, traj.dat) and for the cases the fast table does not cover.
@@ -240,6 +360,21 @@ cudaError_t launch_langevin2d(const StepArgs<T>& A, const IntegratorParams<T>& I
 template <typename T, int D>
 cudaError_t launch_langevin_general(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
                                     const BiasAnyParams<T>& BP, const RngKeys& K, cudaStream_t st);
+
+template <typename T, class Pot, class Bias, int MINB>
+cudaError_t launch_langevin2d_pair(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                   const typename Bias::Params& BP, const RngKeys& K, cudaStream_t st);
+
+template <typename T, class Pot, class Bias, int MINB>
+cudaError_t launch_langevin2d_pair_impl(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,
+                                        const typename Bias::Params& BP, const RngKeys& K, cudaStream_t st) {
+  auto kern = A.noise != nullptr ? langevin2d_pair_kernel<T, Pot, Bias, MINB, true> : langevin2d_pair_kernel<T, Pot, Bias, MINB, false>;
+  const size_t sm = Bias::smem_bytes(BP);
+  const int64_t per_block = (int64_t)kStepThreads * 2;
+  const unsigned grid = (unsigned)((A.n + per_block - 1) / per_block);
+  kern<<<grid, kStepThreads, sm, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
 
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 cudaError_t launch_langevin2d_impl(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,

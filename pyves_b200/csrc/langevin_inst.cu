@@ -19,11 +19,20 @@ using T = PV_T;
       const typename BIAS::Params& BP, const RngKeys& K, cudaStream_t st) {                               \
     return launch_langevin2d_impl<T, POT, BIAS, WPT, MINB>(A, I, PP, BP, K, st);                          \
   }
+#define PV_PAIR(POT, BIAS, MINB)                                                                          \
+  template <>                                                                                             \
+  cudaError_t launch_langevin2d_pair<T, POT, BIAS, MINB>(                                                 \
+      const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,                         \
+      const typename BIAS::Params& BP, const RngKeys& K, cudaStream_t st) {                               \
+    return launch_langevin2d_pair_impl<T, POT, BIAS, MINB>(A, I, PP, BP, K, st);                          \
+  }
 #define PV_COMMA ,
 
 #if PV_GROUP == 0   // double well: the BASELINE.json headline family
 PV_FAST(PotDoubleWell2D<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5>, 2, 1)
+PV_PAIR(PotDoubleWell2D<T>, BiasNone<T>, 1)
+PV_PAIR(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5>, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
@@ -40,12 +49,17 @@ PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)
 PV_FAST(PotSlipBond2D<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12>, 2, 1)
+PV_PAIR(PotSlipBond2D<T>, BiasNone<T>, 1)
+PV_PAIR(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12>, 1)
+PV_PAIR(PotSzaboBerezhkovskii<T>, BiasNone<T>, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_RELU>, 1, 1)
 #elif PV_GROUP == 2  // any potential x each bias family
 PV_FAST(PotGeneric<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 2, 1)
+PV_PAIR(PotGeneric<T>, BiasNone<T>, 1)
+PV_PAIR(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 16 PV_COMMA 1 PV_COMMA 7>, 1, 3)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)

@@ -13,7 +13,25 @@ template <typename T> struct PotParams {
 
 // Each functor: grad<WANT_E>(P, x, y, e, gx, gy) ACCUMULATES dU/dx, dU/dy (and U when WANT_E).
 
+// Two walkers per thread in packed form (Pair<T>: lo = walker a, hi = walker b; FP32x2 instructions for float):
+// grad2 returns the gradient pairs.  Functors without a packed implementation are evaluated half by half.
+template <class Pot, typename T, typename = void> struct PotPair {
+  static PV_DEV void grad2(const PotParams<T>& P, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) {
+    T e = T(0), ax = T(0), ay = T(0), bx = T(0), by = T(0);
+    Pot::template grad<false>(P, x.lo(), y.lo(), e, ax, ay);
+    Pot::template grad<false>(P, x.hi(), y.hi(), e, bx, by);
+    gx = Pair<T>::make(ax, bx);
+    gy = Pair<T>::make(ay, by);
+  }
+};
+
 template <typename T> struct PotDoubleWell2D {   // 10 (x^4 - 4 x^2 + 0.7 x) + 5 y^2
+  static PV_DEV void grad2(const PotParams<T>&, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) {
+    const Pair<T> x2 = Pair<T>::mul(x, x);
+    const Pair<T> t = Pair<T>::fma_bcast(x2, T(40), Pair<T>::make(T(-80), T(-80)));
+    gx = Pair<T>::fma(x, t, Pair<T>::make(T(7), T(7)));
+    gy = Pair<T>::mul_bcast(y, T(10));
+  }
   template <bool WANT_E> static PV_DEV void grad(const PotParams<T>&, T x, T y, T& e, T& gx, T& gy) {
     const T x2 = x * x;
     gx += x * Math<T>::fma(T(40), x2, T(-80)) + T(7);
@@ -23,6 +41,15 @@ template <typename T> struct PotDoubleWell2D {   // 10 (x^4 - 4 x^2 + 0.7 x) + 5
 };
 
 template <typename T> struct PotSlipBond2D {     // ((y-y0)^2/ys - ysh)^2 + (x-y-xy0)^2/xys - fx x - fy y
+  static PV_DEV void grad2(const PotParams<T>& P, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) {
+    using Q = Pair<T>;
+    const Q dy = Q::add_bcast(y, -P.p[2]);
+    const Q t = Q::fma_bcast(Q::mul(dy, dy), P.p[3], Q::make(-P.p[4], -P.p[4]));
+    const Q u = Q::add_bcast(Q::add(x, Q::mul_bcast(y, T(-1))), -P.p[5]);
+    const Q du = Q::mul_bcast(u, T(2) * P.p[6]);
+    gx = Q::add_bcast(du, -P.p[0]);
+    gy = Q::add_bcast(Q::add(Q::mul(Q::mul_bcast(t, T(4) * P.p[3]), dy), Q::mul_bcast(du, T(-1))), -P.p[1]);
+  }
   template <bool WANT_E> static PV_DEV void grad(const PotParams<T>& P, T x, T y, T& e, T& gx, T& gy) {
     // p: fx fy y0 1/ys ysh xy0 1/xys
     const T dy = y - P.p[2];
@@ -49,6 +76,14 @@ template <typename T> struct PotSzaboBerezhkovskii {   // Omega2/2 (x-y)^2 + pie
     gy -= coupling;
     if (WANT_E) e += (mid ? T(-0.5) * w2 * x * x : T(0.5) * w2 * xs * xs - P.p[3]) + T(0.5) * W2 * (x - y) * (x - y);
   }
+};
+
+// functors with a packed implementation
+template <typename T> struct PotPair<PotDoubleWell2D<T>, T, void> {
+  static PV_DEV void grad2(const PotParams<T>& P, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) { PotDoubleWell2D<T>::grad2(P, x, y, gx, gy); }
+};
+template <typename T> struct PotPair<PotSlipBond2D<T>, T, void> {
+  static PV_DEV void grad2(const PotParams<T>& P, Pair<T> x, Pair<T> y, Pair<T>& gx, Pair<T>& gy) { PotSlipBond2D<T>::grad2(P, x, y, gx, gy); }
 };
 
 // Runtime-dispatched potential for every kind (warp-uniform switch).
