@@ -162,6 +162,11 @@ int pyves_histogram(pyves_t* h, const void* pos, int64_t n, int ncols, int ndim,
  * stream reaches the call; the caller keeps it alive and unchanged until then. */
 int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const double* minmax, const double* w_dev, void* stream);
 
+/* The 1D counterpart: degree + 1 FP64 coefficients in device memory.  The packed step kernels read them from
+ * their __constant__ array; consumers that take the coefficients by value (pyves_eval_bias, pyves_energies,
+ * the general step kernel) refresh a host copy first (one synchronous 8 (degree + 1)-byte read). */
+int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double min, double max, const double* w_dev, void* stream);
+
 /* Domain of the ensemble averages of pyves_moments for the Legendre / path-CV bases.  0 (default): every
  * row counts, rows outside the basis interval enter with their clamped coordinate, exactly what
  * LegendreBasis1D.forward does to them (ves/basis.py:143).  1: rows outside the interval get weight 0, i.e.

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pyves_set_tuning": (_i, [_vp, _i]),
     "pyves_set_moment_domain": (_i, [_vp, _i]),
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
+    "pyves_set_bias_legendre1d_device": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -227,6 +228,17 @@ class Ensemble:
             raise ValueError("weights must have (deg_x + 1) * (deg_y + 1) entries")
         m, mp = _darr(minmax)
         self._ck(self.lib.pyves_set_bias_legendre2d(self.h, deg_x, deg_y, mp, p))
+
+    def set_bias_legendre1d_device(self, axis, degree, lo, hi, w_dev):
+        """1D coefficients from a CUDA float64 tensor [degree + 1], read in stream order."""
+        import torch
+        if not (torch.is_tensor(w_dev) and w_dev.is_cuda and w_dev.dtype == torch.float64 and w_dev.is_contiguous()):
+            raise ValueError("w_dev must be a contiguous CUDA float64 tensor")
+        if w_dev.numel() != degree + 1:
+            raise ValueError("weights must have degree + 1 entries")
+        if w_dev.device.index != self.device:
+            raise ValueError("w_dev lives on another device")
+        self._ck(self.lib.pyves_set_bias_legendre1d_device(self.h, axis, degree, lo, hi, ctypes.c_void_p(w_dev.data_ptr()), self.stream))
 
     def set_bias_legendre2d_device(self, deg_x, deg_y, minmax, w_dev):
         """Coefficients from a CUDA float64 tensor [deg_x + 1, deg_y + 1] (or flat), read in stream order:

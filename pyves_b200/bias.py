@@ -382,56 +382,80 @@ class VESBias_Ensemble(NNBias):
 
 
 class DeviceUpdater:
-    """Device-resident update loop of a ``VESBias_Ensemble`` (``LegendreBasis2D`` model, first-order
-    ``averaged_sgd``): gradient, preconditioned averaged-SGD step, well-tempered target refresh and target
-    averages are K-sized CUDA tensor operations enqueued on the current stream, and the new coefficients reach
-    the step kernels through ``pyves_set_bias_legendre2d_device`` -- no device-to-host read, no host optimiser,
-    no re-upload between two launches, so the GPU never waits for Python.  Numerically it is the same update
-    as ``VESBias_Ensemble.update_from_moments`` (FP64), which remains the reference implementation;
-    ``sync_to_host()`` copies coefficients, optimiser state and target back into the bias object.
+    """Device-resident update loop of a ``VESBias_Ensemble`` (``LegendreBasis1D`` / ``LegendreBasis2D`` model,
+    ``averaged_sgd`` first or second order): gradient, (Hessian-corrected, preconditioned) averaged-SGD step,
+    well-tempered target refresh and target averages are K-sized CUDA tensor operations enqueued on the current
+    stream, and the new coefficients reach the step kernels through ``pyves_set_bias_legendre{1d,2d}_device`` --
+    no device-to-host read, no host optimiser, no re-upload between two launches, so the GPU never waits for
+    Python.  Numerically it is the same update as ``VESBias_Ensemble.update_from_moments`` (FP64), which remains
+    the reference implementation; ``sync_to_host()`` copies coefficients, optimiser state and target back into
+    the bias object.
 
     Replaces, for the ensemble, the per-update path ``bias.update`` -> TorchScript save -> ``TorchForce`` reload
     -> ``context.reinitialize`` of ``ves/langevin_dynamics.py:147-159`` + ``ves/bias.py:206-253``.
     """
 
     def __init__(self, bias, ens):
-        if not isinstance(bias.model, LegendreBasis2D):
-            raise ValueError("DeviceUpdater needs a LegendreBasis2D model")
-        if bias.optimizer_type != 'averaged_sgd' or bias.optimizer.second_order or bias.grad_avg is not None:
-            raise ValueError("DeviceUpdater implements the first-order averaged_sgd update without gradient averaging")
+        m = bias.model
+        if not isinstance(m, (LegendreBasis1D, LegendreBasis2D)):
+            raise ValueError("DeviceUpdater needs a LegendreBasis1D or LegendreBasis2D model")
+        if bias.optimizer_type != 'averaged_sgd' or bias.grad_avg is not None:
+            raise ValueError("DeviceUpdater implements the averaged_sgd update without gradient averaging")
         self.bias, self.ens = bias, ens
-        m, o = bias.model, bias.optimizer
+        o = bias.optimizer
         self.dev = torch.device("cuda", ens.device)
-        self.deg = (m.degree_x, m.degree_y)
-        self.minmax = (m.min_x, m.max_x, m.min_y, m.max_y)
+        self.two_d = isinstance(m, LegendreBasis2D)
         f64 = dict(dtype=torch.float64, device=self.dev)
         self.alpha = torch.tensor(o.alpha, **f64)
         self.abar = torch.tensor(o.abar, **f64)
         self.scale = None if o.scale is None else torch.tensor(o.scale, **f64)
         self.mu, self.decay, self.averaging, self.n = o.mu, o.decay, o.averaging, o.n
+        self.second_order = bool(o.second_order)
         self.n_updates = bias.n_updates
         # target: nodes in real coordinates, density, node averages of the basis functions (FP64 evaluator handle)
         self.ev = _lib.Ensemble(1, dims=2, precision="fp64", device=ens.device)
         self.tpos = torch.tensor(bias._target_positions(), **f64).contiguous()
         self.p = torch.tensor(np.asarray(bias.target.p, dtype=np.float64), **f64)
         self.refreshable = hasattr(bias.target, "bias_factor")
-        self.cell = 4.0 / float(len(bias.target.p))
-        self.ev.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        if self.two_d:
+            self.cell = 4.0 / float(len(bias.target.p))
+        else:
+            x = np.asarray(bias.target.x, dtype=np.float64)
+            self.dx = float(x[1] - x[0])
+            tw = np.ones(len(x))
+            tw[0] = tw[-1] = 0.5                               # trapezoid rule of Target_x.quadrature_weights
+            self.trap = torch.tensor(tw, **f64)
+        self._upload(self.ev)
         self.f_target = self._target_average()
         ens.set_moment_domain(bias.sample_domain == 'box')
-        ens.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        self._upload(ens)
         if self.refreshable:
             self._refreshed_density()       # result discarded: loads the kernels of the refresh path (CUDA loads lazily)
 
+    def _upload(self, handle):
+        m = self.bias.model
+        if self.two_d:
+            handle.set_bias_legendre2d_device(m.degree_x, m.degree_y, (m.min_x, m.max_x, m.min_y, m.max_y), self.abar)
+        else:
+            handle.set_bias_legendre1d_device(_axis_id(m.axis), m.degree, float(m.min), float(m.max), self.abar)
+
     def _target_average(self):
-        q = (self.p / self.p.sum()).contiguous()            # Target_2D.quadrature_weights
+        q = self.p if self.two_d else self.p * self.trap        # Target_2D / Target_x .quadrature_weights
+        q = (q / q.sum()).contiguous()
         sw, sf, _ = self.ev.moments(pos=self.tpos, row_weights=q)
         return sf / sw
 
-    def update(self, sum_w, sum_wf):
+    def update(self, sum_w, sum_wf, sum_wff=None):
         """One update from ensemble sums on the device (already reduced over all GPUs).  Enqueue only."""
-        grad = self.f_target - sum_wf / sum_w
-        d = grad if self.scale is None else grad * self.scale
+        mean = sum_wf / sum_w
+        d = self.f_target - mean
+        if self.second_order:
+            if sum_wff is None:
+                raise ValueError("the second-order step needs the second moments (ens.moments(cov=True))")
+            hess = self.bias.beta * (sum_wff / sum_w - torch.outer(mean, mean))      # optim.gradient_hessian
+            d = d + hess @ (self.alpha - self.abar)
+        if self.scale is not None:
+            d = d * self.scale
         self.alpha = self.alpha - self.mu * d
         self.n += 1
         if self.averaging == 'ewma':
@@ -440,20 +464,22 @@ class DeviceUpdater:
             self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
         self.abar = self.abar.contiguous()
         self.n_updates += 1
-        self.ens.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        self._upload(self.ens)
         b = self.bias
         if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
             self.p = self._refreshed_density()
             self.f_target = self._target_average()
 
     def _refreshed_density(self):
-        """Target_WellTempered_2D.update on the device: p' ~ exp(-(beta / gamma) F), F = -V - kT ln p."""
+        """Target_WellTempered_{x,2D}.update on the device: p' ~ exp(-(beta / gamma) F), F = -V - kT ln p."""
         b = self.bias
-        self.ev.set_bias_legendre2d_device(self.deg[0], self.deg[1], self.minmax, self.abar)
+        self._upload(self.ev)
         V, _ = self.ev.eval_bias(self.tpos, want_force=False)
         F = -V - torch.log(torch.clamp(self.p, min=1e-300)) / b.beta
         q = torch.exp(-(b.beta / b.target.bias_factor) * (F - F.min()))
-        return q / (q.sum() * self.cell)
+        if self.two_d:
+            return q / (q.sum() * self.cell)
+        return q / (torch.sum(q * self.trap) * self.dx)
 
     def sync_to_host(self):
         """Copy the device state back into the bias object (coefficients, optimiser, target)."""

@@ -50,6 +50,10 @@ struct pyves_ctx {
   void* l2_wt_dev = nullptr;     // transposed element-type copy wt[ky][kx] (source of the __constant__ upload)
   size_t l2_dev_count = 0;       // elements allocated in l2_w_dev / l2_wt_dev
   uint64_t l2_version = 0;       // bumped by every device update
+  bool l1_dev_mode = false;      // pyves_set_bias_legendre1d_device: l1_w (host) may be stale
+  bool l1_host_stale = false;
+  void* l1_wt_dev = nullptr;     // element-type copy, kMaxK1 entries
+  double* l1_w64_dev = nullptr;  // FP64 copy (host refresh for the consumers that take weights by value)
   uint64_t serial = 0;           // unique per handle (owner tag of the __constant__ weights)
   std::map<void**, size_t> alloc_count;   // element counts of the buffers managed by upload()
   // MLP
@@ -305,11 +309,32 @@ int run_pair(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP
   return PYVES_OK;
 }
 
+// Device-mode 1D weights reach the pair kernels through the __constant__ array; every other consumer takes the
+// weights by value from the host copy, which is refreshed here (synchronous, rare: eval_bias / energies /
+// general kernel on a handle whose coefficients were set from the device).
+int refresh_l1_host(pyves_ctx* h) {
+  if (!h->l1_dev_mode || !h->l1_host_stale) return PYVES_OK;
+  double tmp[kMaxK1];
+  CU(cudaMemcpy(tmp, h->l1_w64_dev, (size_t)(h->l1_degree + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  std::memset(h->l1_w, 0, sizeof(h->l1_w));
+  for (int i = 0; i <= h->l1_degree; ++i) h->l1_w[i] = tmp[i];
+  h->l1_host_stale = false;
+  return PYVES_OK;
+}
+
+template <typename T, class Pot, class Bias>
+int run_pair_c(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP, cudaStream_t st) {
+  CU((launch_langevin2d_pair<T, Pot, Bias, 1>(A, integrator_params<T>(h), pot_params<T>(h), BP, make_keys(h->seed), st)));
+  g_launches++;
+  return PYVES_OK;
+}
+
 template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaStream_t st) {
   if (h->bias_kind == PYVES_BIAS_MLP_1D) {
     for (int w : h->mlp_sizes)
       if (w > kGenH) return fail(h, PYVES_EUNSUPPORTED, "MLP hidden width > 128 is not supported");
   }
+  { const int rc = refresh_l1_host(h); if (rc) return rc; }
   if (h->dims == 2) {
     CU((launch_langevin_general<T, 2>(A, integrator_params<T>(h), pot_params<T>(h), any_params<T>(h), make_keys(h->seed), st)));
   } else {
@@ -348,6 +373,18 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       return run_pair<T, GP, BiasNone<T>>(h, A, BP, st);
     }
     case PYVES_BIAS_LEGENDRE_1D: {
+      if (h->l1_dev_mode && h->variant != 1 && h->device < 64) {   // weights in the __constant__ array
+        const uint64_t tag = (h->serial << 32) | (h->l2_version & 0xffffffffull);
+        if (g_const_owner[h->device].load() != tag) {
+          CU(upload_static_weights<T>(static_cast<const T*>(h->l1_wt_dev), h->l1_degree + 1, st));
+          g_const_owner[h->device].store(tag);
+        }
+        const Legendre1DParams<T> CP = l1_params<T>(h);            // centre / scale / axis / degree; weights unused
+        if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair_c<T, DW, BiasLegendre1D<T, 5, true>>(h, A, CP, st);
+        if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair_c<T, SL, BiasLegendre1D<T, 12, true>>(h, A, CP, st);
+        return run_pair_c<T, GP, BiasLegendre1D<T, 0, true>>(h, A, CP, st);
+      }
+      { const int rc = refresh_l1_host(h); if (rc) return rc; }
       const Legendre1DParams<T> BP = l1_params<T>(h);
       if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair<T, DW, BiasLegendre1D<T, 5>>(h, A, BP, st);
       if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair<T, SL, BiasLegendre1D<T, 12>>(h, A, BP, st);
@@ -548,7 +585,7 @@ int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_
 int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
-  void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
+  void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->l1_wt_dev, h->l1_w64_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
                   h->scratch, h->stage, h->fail_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -660,6 +697,41 @@ int pyves_set_bias_legendre1d(pyves_t* h, int axis, int degree, double lo, doubl
   h->l1_hi = hi;
   std::memset(h->l1_w, 0, sizeof(h->l1_w));
   for (int i = 0; i <= degree; ++i) h->l1_w[i] = w[i];
+  h->l1_dev_mode = false;
+  h->l1_host_stale = false;
+  h->bias_kind = PYVES_BIAS_LEGENDRE_1D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double lo, double hi, const double* w_dev, void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  if (degree < 0 || degree > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degree must be in [0, 63]");
+  if (!(hi > lo) || !w_dev) return fail(h, PYVES_EINVAL, "need max > min and weights");
+  DeviceGuard g(h->device);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, w_dev) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    return fail(h, PYVES_EINVAL, "w_dev must be a device pointer (FP64, degree + 1 entries)");
+  }
+  if (!h->l1_wt_dev) {
+    CU(cudaMalloc(&h->l1_wt_dev, kMaxK1 * sizeof(double)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->l1_w64_dev), kMaxK1 * sizeof(double)));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->prec == PYVES_F64) {
+    CU(launch_convert_weights1d<double>(w_dev, degree + 1, static_cast<double*>(h->l1_wt_dev), h->l1_w64_dev, st));
+  } else {
+    CU(launch_convert_weights1d<float>(w_dev, degree + 1, static_cast<float*>(h->l1_wt_dev), h->l1_w64_dev, st));
+  }
+  g_launches++;
+  h->l1_axis = axis;
+  h->l1_degree = degree;
+  h->l1_lo = lo;
+  h->l1_hi = hi;
+  h->l1_dev_mode = true;
+  h->l1_host_stale = true;
+  h->l2_version++;               // shared version counter of the __constant__ owner tag
   h->bias_kind = PYVES_BIAS_LEGENDRE_1D;
   return PYVES_OK;
 }
@@ -944,6 +1016,7 @@ int pyves_eval_bias(pyves_t* h, const void* pos, int64_t n, int ncols, void* E, 
     dF = F ? base + pb : nullptr;
     dE = E ? base + 2 * pb : nullptr;
   }
+  { const int rc = refresh_l1_host(h); if (rc) return rc; }
   if (h->prec == PYVES_F64) {
     CU(launch_eval_bias<double>(static_cast<const double*>(dpos), n, ncols, static_cast<double*>(dE), static_cast<double*>(dF), any_params<double>(h), st));
   } else {
@@ -971,6 +1044,7 @@ int pyves_energies(pyves_t* h, void* PE, void* KE, int on_host, void* stream) {
     dPE = PE ? h->stage : nullptr;
     dKE = KE ? static_cast<char*>(h->stage) + eb : nullptr;
   }
+  { const int rc = refresh_l1_host(h); if (rc) return rc; }
   if (h->prec == PYVES_F64) {
     CU(launch_energies<double>(static_cast<const double*>(h->pos), static_cast<const double*>(h->vel), h->n, h->dims, static_cast<double*>(dPE), static_cast<double*>(dKE), h->mass, h->dt, pot_params<double>(h), any_params<double>(h), st));
   } else {

@@ -32,6 +32,19 @@ template <typename T> struct BiasNone {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Device-resident coefficient updates (pyves_set_bias_legendre{1d,2d}_device): kernel parameters come from the
+// host, so the static functors can instead read their weights from a __constant__ array that is refreshed with a
+// stream-ordered device-to-device cudaMemcpyToSymbolAsync -- same constant-bank operands (bank 3 instead of
+// the parameter bank 0), no host round trip between two launches.  One copy per translation unit; the kernels
+// and launch_upload_static_weights of langevin_inst.cu (group 0) share theirs.
+constexpr int kConstWeights = 256;
+static __constant__ float c_wt_f32[kConstWeights];
+static __constant__ double c_wt_f64[kConstWeights];
+template <typename T> PV_DEV const T* const_weights();
+template <> PV_DEV const float* const_weights<float>() { return c_wt_f32; }
+template <> PV_DEV const double* const_weights<double>() { return c_wt_f64; }
+
+// ------------------------------------------------------------------------------------------------
 // LegendreBasis1D (ves/basis.py:86-156).  DEG > 0: compile-time degree, recursion fully
 // unrolled, weights are constant-bank operands.  DEG == 0: runtime degree.
 template <typename T> struct Legendre1DParams {
@@ -42,8 +55,9 @@ template <typename T> struct Legendre1DParams {
   T w[kMaxK1];
 };
 
-template <typename T, int DEG> struct BiasLegendre1D {
+template <typename T, int DEG, bool CONSTSYM = false> struct BiasLegendre1D {
   using Params = Legendre1DParams<T>;
+  static PV_DEV T wgt(const Params& P, int n) { return CONSTSYM ? const_weights<T>()[n] : P.w[n]; }
   static size_t smem_bytes(const Params&) { return 0; }
   static PV_DEV void stage(const Params&, void*) {}
   template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
@@ -51,18 +65,18 @@ template <typename T, int DEG> struct BiasLegendre1D {
     const T s = scale_clamp(P.axis ? y : x, P.centre, P.inv_half, inside);
     const int deg = DEG > 0 ? DEG : P.degree;
     T pm = T(1), p = s, dpm = T(0), dp = T(1);
-    T E = P.w[0], g = T(0);
+    T E = wgt(P, 0), g = T(0);
     if (deg >= 1) {
-      E = Math<T>::fma(P.w[1], s, E);
-      g = P.w[1];
+      E = Math<T>::fma(wgt(P, 1), s, E);
+      g = wgt(P, 1);
     }
     if (DEG > 0) {
 #pragma unroll
       for (int n = 1; n < DEG; ++n) {
         const T pn = leg_a<T>(n) * s * p - leg_b<T>(n) * pm;
         const T dpn = Math<T>::fma(leg_c<T>(n), p, dpm);
-        g = Math<T>::fma(P.w[n + 1], dpn, g);
-        if (WANT_E) E = Math<T>::fma(P.w[n + 1], pn, E);
+        g = Math<T>::fma(wgt(P, n + 1), dpn, g);
+        if (WANT_E) E = Math<T>::fma(wgt(P, n + 1), pn, E);
         pm = p; p = pn; dpm = dp; dp = dpn;
       }
     } else {
@@ -70,8 +84,8 @@ template <typename T, int DEG> struct BiasLegendre1D {
         const T fn = T(n), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
         const T pn = (c * s * p - fn * pm) * inv;
         const T dpn = Math<T>::fma(c, p, dpm);
-        g = Math<T>::fma(P.w[n + 1], dpn, g);
-        if (WANT_E) E = Math<T>::fma(P.w[n + 1], pn, E);
+        g = Math<T>::fma(wgt(P, n + 1), dpn, g);
+        if (WANT_E) E = Math<T>::fma(wgt(P, n + 1), pn, E);
         pm = p; p = pn; dpm = dp; dp = dpn;
       }
     }
@@ -100,8 +114,9 @@ template <typename T> struct BiasPair<BiasNone<T>, T> {
   static PV_DEV void grad2(const typename BiasNone<T>::Params&, const void*, Pair<T>, Pair<T>, Pair<T>&, Pair<T>&) {}
 };
 
-template <typename T, int DEG> struct BiasPair<BiasLegendre1D<T, DEG>, T> {
+template <typename T, int DEG, bool CONSTSYM> struct BiasPair<BiasLegendre1D<T, DEG, CONSTSYM>, T> {
   using Q = Pair<T>;
+  using B1 = BiasLegendre1D<T, DEG, CONSTSYM>;
   static PV_DEV void grad2(const Legendre1DParams<T>& P, const void*, Q x, Q y, Q& gx, Q& gy) {
     const Q q = P.axis ? y : x;
     const Q sraw = Q::mul_bcast(Q::add_bcast(q, -P.centre), P.inv_half);
@@ -110,13 +125,13 @@ template <typename T, int DEG> struct BiasPair<BiasLegendre1D<T, DEG>, T> {
     const Q s = Q::make(Math<T>::min(Math<T>::max(s0, T(-1)), T(1)), Math<T>::min(Math<T>::max(s1, T(-1)), T(1)));
     const int deg = DEG > 0 ? DEG : P.degree;
     Q pm = Q::make(T(1), T(1)), p = s, dpm = Q::make(T(0), T(0)), dp = Q::make(T(1), T(1));
-    Q g = deg >= 1 ? Q::make(P.w[1], P.w[1]) : Q::make(T(0), T(0));
+    Q g = deg >= 1 ? Q::make(B1::wgt(P, 1), B1::wgt(P, 1)) : Q::make(T(0), T(0));
     if (DEG > 0) {
 #pragma unroll
       for (int n = 1; n < DEG; ++n) {
         const Q pn = Q::fma(Q::mul_bcast(s, leg_a<T>(n)), p, Q::mul_bcast(pm, -leg_b<T>(n)));
         const Q dpn = Q::fma_bcast(p, leg_c<T>(n), dpm);
-        g = Q::fma_bcast(dpn, P.w[n + 1], g);
+        g = Q::fma_bcast(dpn, B1::wgt(P, n + 1), g);
         pm = p; p = pn; dpm = dp; dp = dpn;
       }
     } else {
@@ -124,7 +139,7 @@ template <typename T, int DEG> struct BiasPair<BiasLegendre1D<T, DEG>, T> {
         const T fn = T(n), inv = T(1) / (fn + T(1)), c = T(2) * fn + T(1);
         const Q pn = Q::fma(Q::mul_bcast(s, c * inv), p, Q::mul_bcast(pm, -fn * inv));
         const Q dpn = Q::fma_bcast(p, c, dpm);
-        g = Q::fma_bcast(dpn, P.w[n + 1], g);
+        g = Q::fma_bcast(dpn, B1::wgt(P, n + 1), g);
         pm = p; p = pn; dpm = dp; dp = dpn;
       }
     }
@@ -228,18 +243,6 @@ template <typename T, int KX, int KY> struct Legendre2DStaticTParams {
   T cx, ihx, cy, ihy;
   T wt[KY * KX];   // wt[j * KX + i] = w_ij
 };
-
-// Device-resident coefficient updates (pyves_set_bias_legendre2d_device): kernel parameters come from the
-// host, so the static functor can instead read its weights from a __constant__ array that is refreshed with a
-// stream-ordered device-to-device cudaMemcpyToSymbolAsync -- same constant-bank operands (bank 3 instead of
-// the parameter bank 0), no host round trip between two launches.  One copy per translation unit; the kernels
-// and launch_upload_static_weights of langevin_inst.cu (group 0) share theirs.
-constexpr int kConstWeights = 256;
-static __constant__ float c_wt_f32[kConstWeights];
-static __constant__ double c_wt_f64[kConstWeights];
-template <typename T> PV_DEV const T* const_weights();
-template <> PV_DEV const float* const_weights<float>() { return c_wt_f32; }
-template <> PV_DEV const double* const_weights<double>() { return c_wt_f64; }
 
 template <typename T, int KX, int KY> struct Legendre2DStaticTCParams {
   T cx, ihx, cy, ihy;

@@ -39,6 +39,10 @@ PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8 PV_COMMA true>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA true>, 1, 1)
+// every kernel that reads the __constant__ weights lives in THIS translation unit (the array is per unit)
+PV_PAIR(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5 PV_COMMA true>, 1)
+PV_PAIR(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12 PV_COMMA true>, 1)
+PV_PAIR(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0 PV_COMMA true>, 1)
 template <> cudaError_t upload_static_weights<T>(const T* dev_src, int n, cudaStream_t st) {
   if (n > kConstWeights) return cudaErrorInvalidValue;
   if (sizeof(T) == 4) return cudaMemcpyToSymbolAsync(c_wt_f32, dev_src, (size_t)n * sizeof(T), 0, cudaMemcpyDeviceToDevice, st);

@@ -285,10 +285,26 @@ cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm,
   return cudaGetLastError();
 }
 
+template <typename T>
+__global__ void convert_weights1d_kernel(const double* __restrict__ w64, int n, T* __restrict__ w_t, double* __restrict__ keep64) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = w64[i];
+  w_t[i] = (T)v;
+  keep64[i] = v;
+}
+
+template <typename T>
+cudaError_t launch_convert_weights1d(const double* w64, int n, T* w_t, double* keep64, cudaStream_t st) {
+  convert_weights1d_kernel<T><<<1, 64, 0, st>>>(w64, n, w_t, keep64);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 #define PV_INST(T)                                                                                                 \
   template cudaError_t launch_eval_bias<T>(const T*, int64_t, int, T*, T*, const BiasAnyParams<T>&, cudaStream_t); \
   template cudaError_t launch_convert_weights2d<T>(const double*, int, int, T*, T*, cudaStream_t);                 \
+  template cudaError_t launch_convert_weights1d<T>(const double*, int, T*, double*, cudaStream_t);                 \
   template cudaError_t launch_energies<T>(const T*, const T*, int64_t, int, T*, T*, T, T, const PotParams<T>&,     \
                                           const BiasAnyParams<T>&, cudaStream_t);                                  \
   template cudaError_t launch_init_positions<T>(T*, int64_t, int, uint64_t, const double*, double, int,            \

@@ -14,6 +14,10 @@ cudaError_t launch_eval_bias(const T* pos, int64_t n, int ncols, T* E, T* F, con
 template <typename T>
 cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm, T* w_t, cudaStream_t st);
 
+// w64[n] (FP64, device) -> element-type copy (source of the __constant__ upload of the 1D functors) + FP64 keep
+template <typename T>
+cudaError_t launch_convert_weights1d(const double* w64, int n, T* w_t, double* keep64, cudaStream_t st);
+
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>
 cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,

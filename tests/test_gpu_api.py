@@ -288,48 +288,67 @@ def test_ensemble_second_order_slip_bond():
     assert (pos[:, 0] < -2).mean() > 0.2 and (pos[:, 0] > 4).mean() > 0.2
 
 
-def test_device_resident_update_matches_host_update():
-    """DeviceUpdater (optimiser, well-tempered target refresh and coefficient hand-over all on the device,
-    pyves_set_bias_legendre2d_device) reproduces VESBias_Ensemble.update_from_moments: same coefficients, target
-    and walkers after 24 updates, for the static 16 x 16 kernels (weights in the __constant__ array) and a
-    runtime-size basis (weights in a device buffer)."""
+def _device_vs_host(make_bias, pot_kind, pot_params, box, cov, n_updates=24, stride=20):
     from pyves_b200 import _lib
     from pyves_b200.bias import DeviceUpdater
     kT = 8.3145e-3 * 300
-    for deg in (15, 9):
-        runs = []
-        for mode in ("host", "device"):
-            model = basis.LegendreBasis2D(deg, deg, -2.5, 2.5, -2.0, 2.0)
-            tgt = target.Target_WellTempered_2D(40, 40, 10.0)
-            b = bias.VESBias_Ensemble(model, tgt, 1 / kT, "averaged_sgd",
-                                      {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=5)
-            ens = _lib.Ensemble(30000, dims=2, seed=7, precision="fp32")
-            ens.set_integrator(1.0, 8.31446261815324e-3 * 300, 20.0, 0.01)
-            ens.set_potential(_lib.POT_DOUBLE_WELL_2D)
-            assert ens.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1 / kT) == 0
-            ens.init_velocities()
-            if mode == "host":
+    runs = []
+    for mode in ("host", "device"):
+        b = make_bias()
+        ens = _lib.Ensemble(30000, dims=2, seed=7, precision="fp32")
+        ens.set_integrator(1.0, 8.31446261815324e-3 * 300, 20.0, 0.01)
+        ens.set_potential(pot_kind, pot_params)
+        assert ens.init_positions_mc(box, 1 / kT, ntrials=2000) == 0
+        ens.init_velocities()
+        if mode == "host":
+            b.force.apply(ens)
+            for _ in range(n_updates):
+                ens.step(stride)
+                sw, sf, sff = ens.moments(cov=cov)
+                b.update_from_moments(sw, sf, sff)
                 b.force.apply(ens)
-                for _ in range(24):
-                    ens.step(20)
-                    sw, sf, _ = ens.moments()
-                    b.update_from_moments(sw, sf)
-                    b.force.apply(ens)
-            else:
-                upd = DeviceUpdater(b, ens)
-                for _ in range(24):
-                    ens.step(20)
-                    sw, sf, _ = ens.moments()
-                    upd.update(sw, sf)
-                upd.sync_to_host()
-                upd.close()
-            x, _ = ens.get_state(host=True)
-            runs.append((b.optimizer.abar.copy(), b.optimizer.alpha.copy(), np.asarray(tgt.p).copy(), x, b.n_updates))
-            ens.close()
-        (a0, al0, p0, x0, n0), (a1, al1, p1, x1, n1) = runs
-        assert n0 == n1 == 24
-        scale = np.max(np.abs(a0))
-        assert scale > 0.1
-        assert np.max(np.abs(a0 - a1)) < 1e-9 * scale and np.max(np.abs(al0 - al1)) < 1e-9 * np.max(np.abs(al0))
-        assert np.max(np.abs(p0 - p1)) < 1e-9 * np.max(p0)
-        assert np.array_equal(x0, x1)
+        else:
+            upd = DeviceUpdater(b, ens)
+            for _ in range(n_updates):
+                ens.step(stride)
+                sw, sf, sff = ens.moments(cov=cov)
+                upd.update(sw, sf, sff)
+            E_dev, _ = ens.eval_bias(ens.get_state()[0].T.contiguous()[:64], want_force=False)   # by-value consumer in device mode
+            upd.sync_to_host()
+            upd.close()
+            b.force.apply(ens)                                                                   # back to host mode
+            E_host, _ = ens.eval_bias(ens.get_state()[0].T.contiguous()[:64], want_force=False)
+            assert torch.allclose(E_dev, E_host, rtol=1e-5, atol=1e-5)
+        x, _ = ens.get_state(host=True)
+        runs.append((b.optimizer.abar.copy(), b.optimizer.alpha.copy(), np.asarray(b.target.p).copy(), x, b.n_updates))
+        ens.close()
+    (a0, al0, p0, x0, n0), (a1, al1, p1, x1, n1) = runs
+    assert n0 == n1 == n_updates
+    scale = np.max(np.abs(a0))
+    assert scale > 0.05
+    assert np.max(np.abs(a0 - a1)) < 1e-9 * scale and np.max(np.abs(al0 - al1)) < 1e-9 * np.max(np.abs(al0))
+    assert np.max(np.abs(p0 - p1)) < 1e-9 * np.max(p0)
+    assert np.array_equal(x0, x1)
+
+
+def test_device_resident_update_matches_host_update():
+    """DeviceUpdater (optimiser, well-tempered target refresh and coefficient hand-over all on the device,
+    pyves_set_bias_legendre{1d,2d}_device) reproduces VESBias_Ensemble.update_from_moments: same coefficients,
+    target and walkers (bit for bit) after 24 updates -- static 16 x 16 kernels (weights in the __constant__
+    array), a runtime-size 2D basis (device buffer), a 1D basis with the second-order step (configs[2] shape)
+    and a 1D well-tempered target."""
+    from pyves_b200 import _lib
+    kT = 8.3145e-3 * 300
+    sgd = {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}
+    for deg in (15, 9):
+        _device_vs_host(lambda: bias.VESBias_Ensemble(basis.LegendreBasis2D(deg, deg, -2.5, 2.5, -2.0, 2.0),
+                                                      target.Target_WellTempered_2D(40, 40, 10.0), 1 / kT, "averaged_sgd", sgd,
+                                                      target_update_every=5),
+                        _lib.POT_DOUBLE_WELL_2D, (), (-2.5, 2.5, -2.0, 2.0), False)
+    _device_vs_host(lambda: bias.VESBias_Ensemble(basis.LegendreBasis1D(12, -3, 6, 'x', weights=np.zeros(13)), target.Target_Uniform_HardSwitch_x(200), 1 / kT,
+                                                  "averaged_sgd", {"mu": 0.5, "second_order": True, "averaging": "ewma", "decay": 0.8},
+                                                  target_update_every=0),
+                    _lib.POT_SLIP_BOND_2D, (0, 0, 1, 5, 4, 0, 2), (-8, 10, -6, 8), True)
+    _device_vs_host(lambda: bias.VESBias_Ensemble(basis.LegendreBasis1D(5, -2.5, 2.5, 'x', weights=np.zeros(6)), target.Target_WellTempered_x(100, 5.0), 1 / kT,
+                                                  "averaged_sgd", {"mu": 0.5, "averaging": "running"}, target_update_every=4),
+                    _lib.POT_DOUBLE_WELL_2D, (), (-2.5, 2.5, -2.0, 2.0), False)

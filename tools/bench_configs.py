@@ -88,18 +88,18 @@ def cfg2(iters):
 def cfg3(iters):
     n = 1250000                                              # 10^7 walkers over 8 GPUs
     e = ensemble(n, _lib.POT_SLIP_BOND_2D, (0, 0, 1, 5, 4, 0, 2), (-8, 10, -6, 8))
-    b = bias.VESBias_Ensemble(basis.LegendreBasis1D(12, -3, 6, 'x'), target.Target_Uniform_HardSwitch_x(200), BETA,
+    b = bias.VESBias_Ensemble(basis.LegendreBasis1D(12, -3, 6, 'x', weights=np.zeros(13)), target.Target_Uniform_HardSwitch_x(200), BETA,
                               "averaged_sgd", {"mu": 0.5, "second_order": True, "averaging": "ewma", "decay": 0.8}, target_update_every=0)
-    b.force.apply(e)
+    upd = bias.DeviceUpdater(b, e)
 
     def it():
         e.step(STRIDE)
         sw, sf, sff = e.moments(cov=True)
-        b.update_from_moments(sw, sf, sff)
-        b.force.apply(e)
+        upd.update(sw, sf, sff)
     t = timed(it, iters)
     parts = dict(steps_ms=timed(lambda: e.step(STRIDE), 3) * 1e3, moments_cov_ms=timed(lambda: e.moments(cov=True), 3) * 1e3)
-    emit(config="cfg3 slip bond + LegendreBasis1D(12), uniform target, 2nd-order averaged SGD (13x13 covariance)", walkers=n,
+    upd.close()
+    emit(config="cfg3 slip bond + LegendreBasis1D(12), uniform target, 2nd-order averaged SGD (13x13 covariance, device-resident update)", walkers=n,
          md_steps_per_iteration=STRIDE, ms_per_iteration=t * 1e3, walker_steps_per_s=n * STRIDE / t, **parts)
     e.close()
 
