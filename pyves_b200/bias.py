@@ -395,6 +395,11 @@ class DeviceUpdater:
     -> ``context.reinitialize`` of ``ves/langevin_dynamics.py:147-159`` + ``ves/bias.py:206-253``.
     """
 
+    @staticmethod
+    def supports(bias):
+        return (isinstance(bias, VESBias_Ensemble) and isinstance(bias.model, (LegendreBasis1D, LegendreBasis2D))
+                and bias.optimizer_type == 'averaged_sgd' and bias.grad_avg is None)
+
     def __init__(self, bias, ens):
         m = bias.model
         if not isinstance(m, (LegendreBasis1D, LegendreBasis2D)):

@@ -12,7 +12,9 @@ New keywords: ``n_walkers`` (ensemble size; sharded over the ranks of an initial
 ``torch.distributed`` process group), ``device``, ``precision`` ('fp32' | 'fp64'), ``scheme``
 ('openmm_langevin' | 'middle'), ``dims`` (2 drops the decoupled z coordinate, 3 keeps it),
 ``traj_walkers`` (how many walkers are recorded), ``sample_every`` (moment sampling stride of the
-ensemble VES update).  With ``n_walkers=1`` the behaviour and file contents follow the reference:
+ensemble VES update), ``device_update`` (keep optimiser state and coefficients of a ``VESBias_Ensemble`` on the
+GPU between updates, ``bias.DeviceUpdater``; the bias object is synchronised when the run returns and the
+per-update ``model_loc.iter{n}`` archive is not written).  With ``n_walkers=1`` the behaviour and file contents follow the reference:
 frame ``t`` is the position before step ``t`` (``:180-188``), ``bias.update(self.traj)`` runs at
 ``i == startafter`` and then whenever ``i % learnevery == 0`` (``:134-159``).
 """
@@ -24,6 +26,7 @@ import torch
 
 from . import _lib
 from .bias import Bias, VESBias_Ensemble
+from .bias import DeviceUpdater
 from .parallel import dist_info, reduce_moments, shard
 
 KB = 8.31446261815324e-3      # kJ/mol/K as OpenMM defines it (the integrator's kT)
@@ -69,7 +72,8 @@ class SingleParticleSimulation:
                  dims: int = None,
                  traj_walkers: int = 1,
                  sample_every: int = None,
-                 process_group=None):
+                 process_group=None,
+                 device_update: bool = False):
         # units as upstream: Da, K, 1/ps, fs
         self.mass = float(mass)
         self.temp = float(temp)
@@ -122,6 +126,8 @@ class SingleParticleSimulation:
         self.traj_in_mem = traj_in_mem
         self.traj_walkers = max(1, min(int(traj_walkers), self.n_walkers))
         self.sample_every = sample_every
+        self.device_update = bool(device_update)
+        self._updater = None
         self.biased = False
 
     # ------------------------------------------------------------------------------------------------
@@ -161,16 +167,23 @@ class SingleParticleSimulation:
             self.learnevery = learnevery
         self.bias = bias
         self.update_on = False
+        self._updater = None
 
     # ------------------------------------------------------------------------------------------------
     def _update_bias(self, i, ves_update_params):
         if isinstance(self.bias, VESBias_Ensemble):
             if i == self.startafter:
-                self.bias.force.apply(self.ens)      # defines the basis for the moment kernels; forces start now
+                if self.device_update and self._updater is None and DeviceUpdater.supports(self.bias):
+                    self._updater = DeviceUpdater(self.bias, self.ens)    # optimiser state + coefficients stay on the GPU
+                else:
+                    self.bias.force.apply(self.ens)  # defines the basis for the moment kernels; forces start now
             self._sample_moments()
             sw, sf, sff = reduce_moments(*self._acc, group=self.process_group)   # one allreduce per update
-            self.bias.update_from_moments(sw, sf, sff)
             self._acc = None
+            if self._updater is not None:
+                self._updater.update(sw, sf, sff)                         # enqueue only: no host round trip
+                return
+            self.bias.update_from_moments(sw, sf, sff)
         else:
             self.bias.update(self.traj, **ves_update_params)
         self.bias.force.apply(self.ens)
@@ -278,6 +291,12 @@ class SingleParticleSimulation:
                     self._sync_traj(frames)
             self._sync_traj(frames)
         finally:
+            if getattr(self, "_updater", None) is not None:       # coefficients, optimiser state, target back to the bias object
+                self._updater.sync_to_host()
+                self._updater.close()
+                self._updater = None
+                self.bias.force.apply(ens)
+                self.bias._export(self.bias.model_loc)
             self._ftraj = None
             if ftraj:
                 ftraj.close()

@@ -238,15 +238,17 @@ def test_dynamic_bias_update_cadence(tmp_path):
     assert not np.allclose(model.weights.detach().numpy(), 0)
 
 
-def test_ensemble_ves_converges_to_analytic_fes():
+@pytest.mark.parametrize("device_update", [False, True], ids=["host_update", "device_update"])
+def test_ensemble_ves_converges_to_analytic_fes(device_update):
     """Textbook VES with an ensemble: LegendreBasis1D on the 2D double well, uniform target, averaged SGD.
-    Converged F(x) = -V(x) agrees with the analytic projection (ves/visualization.py:185-201) within 0.1 kT."""
+    Converged F(x) = -V(x) agrees with the analytic projection (ves/visualization.py:185-201) within 0.1 kT;
+    with the host-side optimiser and with the device-resident update loop of the driver."""
     pot = potentials.DoubleWellPotential2D()
     kT = 8.3145e-3 * 300
     model = basis.LegendreBasis1D(6, -2.5, 2.5, weights=np.zeros(7))
     b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(401), 1 / kT, "averaged_sgd",
                               {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
-    sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=65536, seed=7, temp=300)
+    sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=65536, seed=7, temp=300, device_update=device_update)
     sim.place_walkers(xmin=-2.5, xmax=2.5, ymin=-2, ymax=2)
     sim.init_ves(b, startafter=100, learnevery=100)
     quiet(sim, nsteps=60001, chkevery=0, trajevery=0, energyevery=0, chkfile=None, trajfile=None, energyfile=None)
