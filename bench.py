@@ -200,21 +200,26 @@ def run_ours(args):
     value = n_total * args.stride * args.steps / elapsed
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
 
-    if upd is not None:                                          # hand the state back to the host-side objects
-        upd.sync_to_host()
-        upd.close()
-        bias.force.apply(ens)
-
     # ---- end to end through the C ABI with host buffers -------------------------------------------
+    # every iteration: walker state from pinned host memory -> GPU, the VES iteration, then the result (the 1 + K
+    # basis moments) and the new walker state back to the host.  With --update device the optimiser itself stays on
+    # the GPU (the coefficients are not a per-step input); with --update host it is the numpy optimiser + re-upload.
     e2e = None
     if not args.no_e2e:
         hpos = torch.empty((2, args.walkers), dtype=torch.float32).pin_memory().numpy()
         hvel = torch.empty((2, args.walkers), dtype=torch.float32).pin_memory().numpy()
+        hmom = torch.empty(K + 1, dtype=torch.float64).pin_memory()
         ens.get_state(out=(hpos, hvel))
 
         def e2e_iteration():
             ens.set_state(hpos, hvel)                            # H2D of this iteration's inputs
             ens.step(args.stride)
+            if upd is not None:
+                sw, sf, _ = reduce_moments(*ens.moments())
+                upd.update(sw, sf)
+                hmom.copy_(torch.cat([sw.reshape(-1), sf.reshape(-1)]), non_blocking=True)   # D2H of the result (moments)
+                ens.get_state(out=(hpos, hvel))                  # D2H of the walker state (synchronises)
+                return
             sw, sf, _ = ens.moments(host=True)                   # D2H of the result (moments)
             ens.get_state(out=(hpos, hvel))                      # D2H of the walker state
             if world > 1:
@@ -235,7 +240,12 @@ def run_ours(args):
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         state_bytes = 2 * 2 * args.walkers * 4
         e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
-               "h2d_bytes_per_step": state_bytes + K * 8, "d2h_bytes_per_step": state_bytes + (K + 1) * 8}
+               "h2d_bytes_per_step": state_bytes + (0 if upd is not None else K * 8), "d2h_bytes_per_step": state_bytes + (K + 1) * 8}
+
+    if upd is not None:                                          # hand the state back to the host-side objects
+        upd.sync_to_host()
+        upd.close()
+        bias.force.apply(ens)
 
     # ---- accuracy: continue the optimisation (untimed) and compare the FES with the analytic surface
     fes_out = None
