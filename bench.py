@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--update", default="device", choices=["device", "host"],
                     help="coefficient update of the resident-state loop: 'device' = optimiser, target refresh and coefficient "
                          "hand-over on the GPU (DeviceUpdater), 'host' = numpy optimiser + re-upload (VESBias_Ensemble)")
+    ap.add_argument("--e2e-chunks", type=int, default=4,
+                    help="e2e with --update device: the ensemble is cut into this many handles on their own streams so that the "
+                         "host<->device copies of one chunk overlap the step kernel of another (1 = one handle, serial copies)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -211,7 +214,45 @@ def run_ours(args):
         hmom = torch.empty(K + 1, dtype=torch.float64).pin_memory()
         ens.get_state(out=(hpos, hvel))
 
+        nch = args.e2e_chunks if (upd is not None and args.e2e_chunks > 1 and args.walkers % args.e2e_chunks == 0) else 1
+        if nch > 1:
+            # chunked pipeline: walkers are independent between updates, so the ensemble is split into nch handles
+            # (global walker ids preserved), each on its own stream; all copies are asynchronous from pinned memory
+            cn = args.walkers // nch
+            subs, streams, hp, hv = [], [torch.cuda.Stream(device=dev) for _ in range(nch)], [], []
+            for c in range(nch):
+                e = _lib.Ensemble(cn, dims=2, seed=args.seed, precision="fp32", device=local)
+                e.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
+                e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+                e.set_walker_offset(rank * args.walkers + c * cn)
+                e.step_counter = ens.step_counter
+                upd.add_handle(e)
+                subs.append(e)
+                hp.append(torch.from_numpy(np.ascontiguousarray(hpos[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
+                hv.append(torch.from_numpy(np.ascontiguousarray(hvel[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
+
+        def e2e_chunked():
+            main = torch.cuda.current_stream(dev)
+            mom = []
+            for c in range(nch):
+                streams[c].wait_stream(main)                     # the coefficient hand-over was enqueued on the main stream
+                with torch.cuda.stream(streams[c]):
+                    subs[c].set_state(hp[c], hv[c], async_copy=True)          # H2D of this chunk's inputs
+                    subs[c].step(args.stride)
+                    mom.append(subs[c].moments())
+                    subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)    # D2H of this chunk's walkers
+            for c in range(nch):
+                main.wait_stream(streams[c])
+            sw = sum(m[0] for m in mom)
+            sf = sum(m[1] for m in mom)
+            sw, sf, _ = reduce_moments(sw, sf)
+            upd.update(sw, sf)
+            hmom.copy_(torch.cat([sw.reshape(-1), sf.reshape(-1)]), non_blocking=True)       # D2H of the result (moments)
+            torch.cuda.synchronize(dev)                          # walker state and moments are on the host
+
         def e2e_iteration():
+            if nch > 1:
+                return e2e_chunked()
             ens.set_state(hpos, hvel)                            # H2D of this iteration's inputs
             ens.step(args.stride)
             if upd is not None:
@@ -240,7 +281,12 @@ def run_ours(args):
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         state_bytes = 2 * 2 * args.walkers * 4
         e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
-               "h2d_bytes_per_step": state_bytes + (0 if upd is not None else K * 8), "d2h_bytes_per_step": state_bytes + (K + 1) * 8}
+               "h2d_bytes_per_step": state_bytes + (0 if upd is not None else K * 8), "d2h_bytes_per_step": state_bytes + (K + 1) * 8,
+               "chunks": nch}
+        if nch > 1:
+            for e in subs:
+                upd.handles.remove(e)
+                e.close()
 
     if upd is not None:                                          # hand the state back to the host-side objects
         upd.sync_to_host()

@@ -109,7 +109,9 @@ int pyves_set_bias_harmonic(pyves_t* h, int axis, double k, double s0);
 int pyves_basis_size(const pyves_t* h, int64_t* K);
 
 /* ---- walker state: SoA, pos[dims][n], vel[dims][n] ---------------------------------- */
-/* context.setPositions / setState (:69-76) */
+/* context.setPositions / setState (:69-76).  on_host: 0 = device arrays; 1 = host arrays, returns when the copy
+ * is done; 2 = PINNED host arrays, copy enqueued on `stream`, the caller synchronises before reusing them
+ * (lets the copies of one handle overlap the kernels of another). */
 int pyves_set_state(pyves_t* h, const void* pos, const void* vel, int on_host, void* stream);
 /* context.getState(getPositions, getVelocities) (:201,208) */
 int pyves_get_state(pyves_t* h, void* pos, void* vel, int on_host, void* stream);

@@ -281,8 +281,9 @@ class Ensemble:
         return out.value
 
     # ------------------------------------------------------------------------------------------ state
-    def set_state(self, pos=None, vel=None):
-        """SoA arrays [dims, n]: CUDA tensors (device copy) or numpy arrays (host copy)."""
+    def set_state(self, pos=None, vel=None, async_copy=False):
+        """SoA arrays [dims, n]: CUDA tensors (device copy) or numpy arrays (host copy).  ``async_copy``: the numpy
+        arrays are PINNED, the copy is only enqueued on the current stream (synchronise before touching them)."""
         host = isinstance(pos if pos is not None else vel, np.ndarray)
         keep = []
         for t in (pos, vel):
@@ -292,9 +293,10 @@ class Ensemble:
                 keep.append(np.ascontiguousarray(t, dtype=self.np_dtype).reshape(self.dims, self.n))
             else:
                 keep.append(self._check(t, (self.dims, self.n)))
-        self._ck(self.lib.pyves_set_state(self.h, _ptr(keep[0]), _ptr(keep[1]), int(host), self.stream))
+        self._ck(self.lib.pyves_set_state(self.h, _ptr(keep[0]), _ptr(keep[1]), (2 if async_copy else 1) if host else 0, self.stream))
 
-    def get_state(self, host=False, out=None):
+    def get_state(self, host=False, out=None, async_copy=False):
+        """(pos, vel) as CUDA tensors, numpy arrays (``host``) or into ``out``; ``async_copy`` as in ``set_state``."""
         import torch
         if out is not None:
             pos, vel = out
@@ -305,7 +307,7 @@ class Ensemble:
             pos = torch.empty((self.dims, self.n), dtype=self.torch_dtype, device="cuda:%d" % self.device)
             vel = torch.empty_like(pos)
         host = isinstance(pos, np.ndarray)
-        self._ck(self.lib.pyves_get_state(self.h, _ptr(pos), _ptr(vel), int(host), self.stream))
+        self._ck(self.lib.pyves_get_state(self.h, _ptr(pos), _ptr(vel), (2 if async_copy else 1) if host else 0, self.stream))
         return pos, vel
 
     def init_positions_mc(self, box, beta, ntrials=100):

@@ -430,12 +430,19 @@ class DeviceUpdater:
             tw = np.ones(len(x))
             tw[0] = tw[-1] = 0.5                               # trapezoid rule of Target_x.quadrature_weights
             self.trap = torch.tensor(tw, **f64)
+        self.handles = [ens]                 # every handle that receives the coefficients (add_handle)
         self._upload(self.ev)
         self.f_target = self._target_average()
         ens.set_moment_domain(bias.sample_domain == 'box')
         self._upload(ens)
         if self.refreshable:
             self._refreshed_density()       # result discarded: loads the kernels of the refresh path (CUDA loads lazily)
+
+    def add_handle(self, ens):
+        """Another ensemble handle on the same device (a shard processed on its own stream) that shares the bias."""
+        ens.set_moment_domain(self.bias.sample_domain == 'box')
+        self._upload(ens)
+        self.handles.append(ens)
 
     def _upload(self, handle):
         m = self.bias.model
@@ -469,7 +476,8 @@ class DeviceUpdater:
             self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
         self.abar = self.abar.contiguous()
         self.n_updates += 1
-        self._upload(self.ens)
+        for hdl in self.handles:
+            self._upload(hdl)
         b = self.bias
         if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
             self.p = self._refreshed_density()

@@ -926,7 +926,7 @@ int pyves_set_state(pyves_t* h, const void* pos, const void* vel, int on_host, v
   const cudaMemcpyKind kind = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   if (pos) CU(cudaMemcpyAsync(h->pos, pos, bytes, kind, st));
   if (vel) CU(cudaMemcpyAsync(h->vel, vel, bytes, kind, st));
-  if (on_host) CU(cudaStreamSynchronize(st));
+  if (on_host == 1) CU(cudaStreamSynchronize(st));   // on_host == 2: pinned host buffers, the caller synchronises
   return PYVES_OK;
 }
 
@@ -938,7 +938,7 @@ int pyves_get_state(pyves_t* h, void* pos, void* vel, int on_host, void* stream)
   const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (pos) CU(cudaMemcpyAsync(pos, h->pos, bytes, kind, st));
   if (vel) CU(cudaMemcpyAsync(vel, h->vel, bytes, kind, st));
-  if (on_host) CU(cudaStreamSynchronize(st));
+  if (on_host == 1) CU(cudaStreamSynchronize(st));   // on_host == 2: pinned host buffers, the caller synchronises
   return PYVES_OK;
 }
 

@@ -354,3 +354,69 @@ def test_device_resident_update_matches_host_update():
     _device_vs_host(lambda: bias.VESBias_Ensemble(basis.LegendreBasis1D(5, -2.5, 2.5, 'x', weights=np.zeros(6)), target.Target_WellTempered_x(100, 5.0), 1 / kT,
                                                   "averaged_sgd", {"mu": 0.5, "averaging": "running"}, target_update_every=4),
                     _lib.POT_DOUBLE_WELL_2D, (), (-2.5, 2.5, -2.0, 2.0), False)
+
+
+def test_chunked_handles_async_copies_match_single_handle():
+    """The e2e pipeline of bench.py: the ensemble cut into handles on their own streams, state copied from / to
+    pinned host memory asynchronously (on_host = 2), one DeviceUpdater feeding all handles.  Walkers and
+    coefficients equal the single-handle run to rounding."""
+    from pyves_b200 import _lib
+    from pyves_b200.bias import DeviceUpdater
+    kT = 8.3145e-3 * 300
+    n, nch, stride, iters = 40000, 4, 30, 6
+
+    def make_bias():
+        return bias.VESBias_Ensemble(basis.LegendreBasis2D(15, 15, -2.5, 2.5, -2.0, 2.0), target.Target_WellTempered_2D(40, 40, 10.0),
+                                     1 / kT, "averaged_sgd", {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0},
+                                     target_update_every=3)
+
+    def make_ens(count, offset):
+        e = _lib.Ensemble(count, dims=2, seed=11, precision="fp32")
+        e.set_integrator(1.0, 8.31446261815324e-3 * 300, 20.0, 0.01)
+        e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+        e.set_walker_offset(offset)
+        return e
+
+    ref = make_ens(n, 0)
+    assert ref.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1 / kT) == 0
+    ref.init_velocities()
+    x0, v0 = ref.get_state(host=True)
+    b_ref = make_bias()
+    u_ref = DeviceUpdater(b_ref, ref)
+    for _ in range(iters):
+        ref.step(stride)
+        sw, sf, _ = ref.moments()
+        u_ref.update(sw, sf)
+    xr, vr = ref.get_state(host=True)
+    u_ref.sync_to_host()
+
+    cn = n // nch
+    subs = [make_ens(cn, c * cn) for c in range(nch)]
+    streams = [torch.cuda.Stream() for _ in range(nch)]
+    hp = [torch.from_numpy(np.ascontiguousarray(x0[:, c * cn:(c + 1) * cn])).pin_memory().numpy() for c in range(nch)]
+    hv = [torch.from_numpy(np.ascontiguousarray(v0[:, c * cn:(c + 1) * cn])).pin_memory().numpy() for c in range(nch)]
+    b = make_bias()
+    upd = DeviceUpdater(b, subs[0])
+    for e in subs[1:]:
+        upd.add_handle(e)
+    main = torch.cuda.current_stream()
+    for _ in range(iters):
+        mom = []
+        for c in range(nch):
+            streams[c].wait_stream(main)
+            with torch.cuda.stream(streams[c]):
+                subs[c].set_state(hp[c], hv[c], async_copy=True)
+                subs[c].step(stride)
+                mom.append(subs[c].moments())
+                subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)
+        for c in range(nch):
+            main.wait_stream(streams[c])
+        upd.update(sum(m[0] for m in mom), sum(m[1] for m in mom))
+        torch.cuda.synchronize()
+    upd.sync_to_host()
+    # the chunk moments are added in another order than the single-handle reduction (FP64, ~1e-16 relative), so a
+    # coefficient can round to the neighbouring FP32 value: walkers agree to FP32 rounding, not bit for bit
+    assert np.max(np.abs(np.concatenate(hp, axis=1) - xr)) < 1e-4 and np.max(np.abs(np.concatenate(hv, axis=1) - vr)) < 1e-3
+    assert np.max(np.abs(b.optimizer.abar - b_ref.optimizer.abar)) < 1e-7 * np.max(np.abs(b_ref.optimizer.abar))
+    for h in subs + [ref]:
+        h.close()
