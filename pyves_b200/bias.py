@@ -313,7 +313,7 @@ class VESBias_Ensemble(NNBias):
             cy, hy = (m.min_y + m.max_y) / 2, (m.max_y - m.min_y) / 2
             return np.stack([cx + hx * s[:, 0], cy + hy * s[:, 1]], axis=1)
         if isinstance(m, LegendreBasis2DPathCV):
-            raise NotImplementedError("ensemble VES along a path CV needs a target on the path; not provided yet")
+            raise NotImplementedError("path-CV targets live in the scaled path coordinate; see _pathcv_nodes")
         a = _axis_id(m.axis)
         pos = np.zeros((len(s), a + 1))
         if isinstance(m, NNBasis1D):
@@ -322,8 +322,23 @@ class VESBias_Ensemble(NNBias):
             pos[:, a] = (m.min + m.max) / 2 + (m.max - m.min) / 2 * s
         return pos
 
+    # ---- path CV: the target is a 1D target in the scaled path coordinate s' = 2 s - 1; f_k(s') = P_k(s') does not
+    # depend on where on the plane a node sits, so node averages and the bias at the nodes are plain Legendre sums
+    def _pathcv_nodes(self):
+        if getattr(self.target, "ndim", 1) != 1:
+            raise ValueError("LegendreBasis2DPathCV needs a 1D target (nodes in the scaled path coordinate)")
+        return np.polynomial.legendre.legvander(np.asarray(self.target.x, dtype=np.float64), self.model.degree)   # [M, K]
+
+    def _pathcv_bias_at_nodes(self):
+        w = self.model.weights.detach().cpu().numpy().astype(np.float64)
+        return self._pathcv_nodes() @ w
+
     def target_average(self, refresh=False):
         """<dV/dparam>_p by quadrature over the target nodes (CUDA moments kernel with node weights)."""
+        if isinstance(self.model, LegendreBasis2DPathCV):
+            if self._f_target is None or refresh:
+                self._f_target = self.target.quadrature_weights() @ self._pathcv_nodes()
+            return self._f_target
         if self._f_target is None or refresh or isinstance(self.model, NNBasis1D):
             ens, tpos = _device_eval(self.model, self._target_positions())
             q = torch.as_tensor(self.target.quadrature_weights(), device="cuda")
@@ -332,6 +347,10 @@ class VESBias_Ensemble(NNBias):
         return self._f_target
 
     def refresh_target(self):
+        if isinstance(self.model, LegendreBasis2DPathCV):
+            if self.target.update(self._pathcv_bias_at_nodes(), self.beta):
+                self._f_target = None
+            return
         ens, tpos = _device_eval(self.model, self._target_positions())
         V, _ = ens.eval_bias(tpos, want_force=False)
         if self.target.update(V.cpu().numpy(), self.beta):
@@ -375,6 +394,9 @@ class VESBias_Ensemble(NNBias):
 
     def fes(self, nodes_scaled=None):
         """F(s) = -V(s) - (1/beta) ln p(s) at the target nodes, shifted to min 0 (kJ/mol)."""
+        if isinstance(self.model, LegendreBasis2DPathCV):
+            F = -self._pathcv_bias_at_nodes() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
+            return F - F.min()
         ens, tpos = _device_eval(self.model, self._target_positions())
         V, _ = ens.eval_bias(tpos, want_force=False)
         F = -V.cpu().numpy() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta

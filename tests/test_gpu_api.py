@@ -427,3 +427,34 @@ def test_chunked_handles_async_copies_match_single_handle():
     assert np.max(np.abs(b.optimizer.abar - b_ref.optimizer.abar)) < 1e-7 * np.max(np.abs(b_ref.optimizer.abar))
     for h in subs + [ref]:
         h.close()
+
+
+def test_ensemble_ves_along_path_cv():
+    """Ensemble VES with LegendreBasis2DPathCV (ves/basis.py:386-548) and a uniform target in the scaled path
+    coordinate: the path runs along the x axis of the 2D double well through both minima, so the converged bias
+    must flatten the 20 kT barrier -- the walkers, all started in one well, end up spread over the whole path, and
+    F(s) = -V(s) reproduces the analytic x projection (s is linear in x for this path)."""
+    pot = potentials.DoubleWellPotential2D()
+    kT = 8.3145e-3 * 300
+    n_img = 40
+    x_i, y_i = np.linspace(-2.2, 2.2, n_img), np.zeros(n_img)
+    model = basis.LegendreBasis2DPathCV(8, x_i, y_i, 100.0, weights=np.zeros(9))
+    b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(401), 1 / kT, "averaged_sgd",
+                              {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
+    init = np.array([[-1.47, 0.0, 0.0]])
+    sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=32768, seed=5, temp=300, init_coord=init)
+    sim.init_ves(b, startafter=100, learnevery=100)
+    quiet(sim, nsteps=60001, chkevery=0, trajevery=0, energyevery=0, chkfile=None, trajfile=None, energyfile=None)
+    assert b.n_updates == 600
+    pos = sim.get_state().positions
+    assert (pos[:, 0] > 0.5).mean() > 0.25 and (pos[:, 0] < -0.5).mean() > 0.25      # crossed the barrier, both wells populated
+    # F(s) against the analytic projection on x(s): s = (i + 1) / N at image i  ->  x = x_0 + (N s - 1) dx
+    F = b.fes() / kT
+    sp = np.asarray(b.target.x)
+    xs = x_i[0] + (n_img * (sp + 1) / 2 - 1) * (x_i[1] - x_i[0])
+    xa, F_ref = fes.projection_x(pot, 300, [-2.25, 2.25], [-2, 2])
+    sel = (xs > -1.9) & (xs < 1.9)
+    F_ref_s = np.interp(xs[sel], xa, F_ref)
+    d = (F[sel] - F[sel].min()) - (F_ref_s - F_ref_s.min())
+    keep = F_ref_s - F_ref_s.min() < 15
+    assert np.sqrt(np.mean(d[keep] ** 2)) < 1.0, np.sqrt(np.mean(d[keep] ** 2))
