@@ -286,6 +286,44 @@ def test_full_size_sharding_invariance():
         h.close()
 
 
+def test_int64_indexing_beyond_2_31_walkers():
+    """Maximum-size case: 2^31 + 4096 walkers (34 GB of FP32 state on the 180 GB B200).  Placement, the packed step
+    kernel, the one-pass moments and the histogram index with 64 bits: every walker is counted, and the last 4096
+    walkers equal a 4096-walker handle with the same global ids bit for bit."""
+    free, _ = torch.cuda.mem_get_info()
+    n = 2 ** 31 + 4096
+    if free < 90e9:
+        pytest.skip("needs ~75 GB of free device memory")
+    kT = 8.3145e-3 * 300
+    w = np.array([0.3, -1.2, 0.8, 0.1, -0.4, 0.2])
+
+    def make(count, offset):
+        e = _lib.Ensemble(count, dims=2, seed=99, precision="fp32")
+        e.set_integrator(1.0, 8.31446261815324e-3 * 300, 20.0, 0.01)
+        e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+        e.set_walker_offset(offset)
+        e.set_bias_legendre1d(0, 5, -2.5, 2.5, w)
+        assert e.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1.0 / kT) == 0
+        e.init_velocities()
+        e.step(6)
+        return e
+
+    big = make(n, 0)
+    sw, sf, sff = big.moments(cov=True)
+    assert float(sw.cpu()[0]) == float(n) and float(sff.cpu()[0, 0]) == float(n)
+    counts = big.histogram((-10.0, 10.0), 64, axis=0)
+    assert float(counts.sum().cpu()) == float(n)
+    x, v = big.get_state()
+    tail = make(4096, n - 4096)
+    xt, vt = tail.get_state()
+    assert torch.equal(x[:, n - 4096:], xt) and torch.equal(v[:, n - 4096:], vt)
+    assert bool(torch.isfinite(x[:, -1]).all()) and float(x[0, n - 1]) != 0.0
+    del x, v
+    big.close()
+    tail.close()
+    torch.cuda.empty_cache()
+
+
 def test_general_kernel_3d_middle_record():
     """dims = 3 (z simulated, 1000 z^2), both schemes, trajectory recording (frame t before step t)."""
     rng = np.random.default_rng(3)
