@@ -386,6 +386,8 @@ class Ensemble:
             sw = torch.zeros(1, dtype=torch.float64, device=dev)
             sf = torch.zeros(K, dtype=torch.float64, device=dev)
             sff = torch.zeros((K, K), dtype=torch.float64, device=dev) if cov else None
+        if pos is not None and n == 0:
+            return sw, sf, sff           # an empty row set sums to zero (a NULL pointer would mean "the handle's walkers")
         self._ck(self.lib.pyves_moments(self.h, _ptr(pos), n, ncols, _ptr(row_weights), _ptr(sw), _ptr(sf), _ptr(sff),
                                         int(host), self.stream))
         return sw, sf, sff
@@ -406,6 +408,8 @@ class Ensemble:
             pos = np.ascontiguousarray(pos, dtype=self.np_dtype)
         if host and row_weights is not None:
             row_weights = np.ascontiguousarray(row_weights, dtype=self.np_dtype)
+        if pos is not None and n == 0:
+            return counts                # nothing to add (a NULL pointer would mean "the handle's walkers")
         self._ck(self.lib.pyves_histogram(self.h, _ptr(pos), n, ncols, ndim, axis, rp, nb.ctypes.data_as(_ip),
                                           _ptr(row_weights), _ptr(counts), int(host), self.stream))
         return counts

@@ -286,6 +286,40 @@ def test_full_size_sharding_invariance():
         h.close()
 
 
+def test_empty_and_ragged_inputs():
+    """Empty row sets (eval_bias, moments, histogram), zero-length launches and ensembles that do not fill a
+    thread block / a pair of walkers / a tile: n = 1, 2, 31, 129, 257 against the oracle."""
+    rng = np.random.default_rng(5)
+    k = langevin.constants()
+    specs = [rng_spec("leg1d", rng, degree=5), rng_spec("leg2d", rng, deg_x=15, deg_y=15), rng_spec("leg2d", rng, deg_x=4, deg_y=6)]
+    for spec in specs:
+        f = biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec)
+        for n in (1, 2, 31, 129, 257):
+            x0 = np.stack([rng.uniform(-1.6, -1.2, n), rng.uniform(-0.3, 0.3, n)], 1)
+            v0 = rng.standard_normal((n, 2)) * k["sigma_v"]
+            xr, vr = langevin.run_philox(x0, v0, f, k, 3, 0, 0, 9)
+            e = biasspec.make_ensemble(n, 2, 3, "fp64", potentials.DOUBLE_WELL_2D, None, spec)
+            e.set_state(torch.tensor(x0.T.copy(), dtype=torch.float64, device=DEV), torch.tensor(v0.T.copy(), dtype=torch.float64, device=DEV))
+            e.step(0)                                   # zero-length launch: nothing happens
+            e.step(9)
+            x, v = e.get_state(host=True)
+            assert rel_err(x.T, xr) < 1e-9 and rel_err(v.T, vr) < 1e-9, (spec["kind"], n)
+            sw, sf, sff = e.moments(cov=True)
+            fr = biasspec.oracle_basis(spec, x.T)
+            assert float(sw.cpu()[0]) == n and np.max(np.abs(sf.cpu().numpy() - fr.sum(0))) < 1e-9 * max(1, n)
+            assert np.max(np.abs(sff.cpu().numpy() - fr.T @ fr)) < 1e-9 * max(1, n)
+            e.close()
+        # empty caller arrays
+        e = biasspec.make_ensemble(4, 2, 3, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+        empty = torch.empty((0, 2), dtype=torch.float32, device=DEV)
+        E, F = e.eval_bias(empty)
+        assert E.shape == (0,) and F.shape == (0, 2)
+        sw, sf, sff = e.moments(pos=empty, cov=True)
+        assert float(sw.cpu()[0]) == 0 and not sf.cpu().numpy().any() and not sff.cpu().numpy().any()
+        assert float(e.histogram((-1.0, 1.0), 8, axis=0, pos=empty).sum().cpu()) == 0
+        e.close()
+
+
 def test_int64_indexing_beyond_2_31_walkers():
     """Maximum-size case: 2^31 + 4096 walkers (34 GB of FP32 state on the 180 GB B200).  Placement, the packed step
     kernel, the one-pass moments and the histogram index with 64 bits: every walker is counted, and the last 4096
