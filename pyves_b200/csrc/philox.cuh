@@ -36,13 +36,8 @@ PV_DEV uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, c
   for (int r = 0; r < 10; ++r) {
     const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
     const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-#ifdef PV_PHILOX_BUMP_KEYS
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (K.k0[0] + (uint32_t)r * kPhiloxW0);
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (K.k1[0] + (uint32_t)r * kPhiloxW1);
-#else
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
     const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
-#endif
     c1 = (uint32_t)p1;
     c3 = (uint32_t)p0;
     c0 = n0;
