@@ -458,3 +458,16 @@ def test_ensemble_ves_along_path_cv():
     d = (F[sel] - F[sel].min()) - (F_ref_s - F_ref_s.min())
     keep = F_ref_s - F_ref_s.min() < 15
     assert np.sqrt(np.mean(d[keep] ** 2)) < 1.0, np.sqrt(np.mean(d[keep] ** 2))
+
+
+def test_example_script_ensemble_ves():
+    """examples/double_well_2D_ensemble_ves.py (configs[1] through the `ves.*` names, device-resident updates):
+    converged 2D surface within 0.1 kT of the analytic one at test size."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "double_well_2D_ensemble_ves.py")
+    spec = importlib.util.spec_from_file_location("example_ensemble_ves", path)
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+        rmse = mod.main(200000, 60000, quiet=True)
+    assert rmse < 0.1, rmse
