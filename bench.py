@@ -391,6 +391,43 @@ def cpu_iteration(cport, k, spec, opt, pos, vel, step0, stride, seed):
     spec["weights"] = opt.step(ft - sf / pos.shape[1]).reshape(spec["weights"].shape)
 
 
+def torchforce_style_rate(args, steps=300):
+    """What the reference executes per MD step for ONE particle: a TorchScript bias module
+    evaluated forward + backward on the CPU, as openmm-torch's TorchForce does (ves/bias.py:52-58), plus the
+    OpenMM-form Langevin update in numpy; one thread.  The module is this package's TorchScript export (the file a
+    reference run would load from model_loc); OpenMM's own per-step overhead is not included (OpenMM is absent)."""
+    import torch
+    from pyves_b200.basis import LegendreBasis1D, LegendreBasis2D
+    old_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    out = {}
+    kT, g, dt = KB * TEMP, 20.0, 0.01
+    a = np.exp(-g * dt)
+    b, c = (1 - a) / g, np.sqrt(kT * (1 - a * a))
+    rng = np.random.default_rng(0)
+    mods = {"legendre1d_d5": LegendreBasis1D(5, -2.5, 2.5, 'x', weights=rng.standard_normal(6)),
+            "legendre2d_%dx%d" % (args.basis, args.basis): LegendreBasis2D(args.basis - 1, args.basis - 1, *MINMAX,
+                                                                            weights=rng.standard_normal((args.basis, args.basis)) * 0.1)}
+    for name, mod in mods.items():
+        ts = mod.export_torchscript()
+        x = np.array([[-1.4, 0.1, 0.0]])
+        v = np.zeros((1, 3))
+        for it in range(steps + 20):
+            if it == 20:
+                t0 = time.perf_counter()
+            pos = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+            E = ts(pos).sum()
+            E.backward()
+            F = -pos.grad.numpy()
+            F[0, 0] -= 10 * (4 * x[0, 0] ** 3 - 8 * x[0, 0] + 0.7)
+            F[0, 1] -= 10 * x[0, 1]
+            v = a * v + b * F + c * rng.standard_normal((1, 3))
+            x = x + dt * v
+        out[name] = steps / (time.perf_counter() - t0)
+    torch.set_num_threads(old_threads)
+    return out
+
+
 def cpu_baseline(args, seconds=12.0):
     from oracle import ves
     cport, k, spec = cpu_model(args, args.seed)
@@ -407,7 +444,11 @@ def cpu_baseline(args, seconds=12.0):
     return {"value": n * args.stride / dt, "unit": "walker-steps/s", "cores": cport.num_threads(), "kind": "port",
             "sample": "%d walkers x %d steps + moments + update, FP64, gcc -O3 OpenMP C port of the same path "
                       "(oracle/c/pyves_oracle.c); the reference itself (Python + OpenMM + TorchForce) cannot run here: "
-                      "OpenMM absent" % (n, args.stride)}
+                      "OpenMM absent" % (n, args.stride),
+            "torchforce_style_single_walker": dict(torchforce_style_rate(args), unit="walker-steps/s", cores=1,
+                                                   note="TorchScript bias forward + backward per step for one particle on the "
+                                                        "CPU + numpy Langevin update: the per-step work of the reference's "
+                                                        "TorchForce path without OpenMM's own overhead")}
 
 
 def run_reference(args):
