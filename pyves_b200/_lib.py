@@ -130,6 +130,26 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _Range:
+    """NVTX range around a library call when PYVES_NVTX=1 (ncu --nvtx / nsys filter on pyves.step, pyves.moments,
+    pyves.update); a no-op otherwise."""
+    enabled = os.environ.get("PYVES_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Range.enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class Ensemble:
     """One ensemble of walkers on one GPU (one ``pyves_t`` handle)."""
 
@@ -323,7 +343,8 @@ class Ensemble:
     def step(self, nsteps, noise=None):
         if noise is not None:
             self._check(noise, (nsteps, self.dims, self.n))
-        self._ck(self.lib.pyves_step(self.h, nsteps, _ptr(noise), self.stream))
+        with _Range("pyves.step"):
+            self._ck(self.lib.pyves_step(self.h, nsteps, _ptr(noise), self.stream))
 
     def step_record(self, nsteps, every=1, n_rec=1, noise=None):
         import torch
@@ -388,8 +409,9 @@ class Ensemble:
             sff = torch.zeros((K, K), dtype=torch.float64, device=dev) if cov else None
         if pos is not None and n == 0:
             return sw, sf, sff           # an empty row set sums to zero (a NULL pointer would mean "the handle's walkers")
-        self._ck(self.lib.pyves_moments(self.h, _ptr(pos), n, ncols, _ptr(row_weights), _ptr(sw), _ptr(sf), _ptr(sff),
-                                        int(host), self.stream))
+        with _Range("pyves.moments"):
+            self._ck(self.lib.pyves_moments(self.h, _ptr(pos), n, ncols, _ptr(row_weights), _ptr(sw), _ptr(sf), _ptr(sff),
+                                            int(host), self.stream))
         return sw, sf, sff
 
     def histogram(self, ranges, nbins, axis=0, pos=None, row_weights=None, counts=None, host=False):

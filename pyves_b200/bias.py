@@ -481,6 +481,10 @@ class DeviceUpdater:
 
     def update(self, sum_w, sum_wf, sum_wff=None):
         """One update from ensemble sums on the device (already reduced over all GPUs).  Enqueue only."""
+        with _lib._Range("pyves.update"):
+            self._update(sum_w, sum_wf, sum_wff)
+
+    def _update(self, sum_w, sum_wf, sum_wff):
         mean = sum_wf / sum_w
         d = self.f_target - mean
         if self.second_order:
