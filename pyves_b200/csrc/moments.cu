@@ -445,7 +445,7 @@ size_t moments_scratch_doubles(int64_t K, bool cov) {
   int g = kMaxBlocks / npt;
   if (g < 1) g = 1;
   size_t total = first + (size_t)g * npt * kPairTile * kPairTile;
-  if (K > 128 && K <= 4096) {   // room for the tensor-core path's FP32 partial tiles
+  if (K > 64 && K <= 4096) {   // room for the tensor-core path's FP32 partial tiles
     const size_t tc = first + (cov_tc_scratch_floats(kMaxSmForScratch) + 1) / 2;
     if (tc > total) total = tc;
   }

@@ -44,7 +44,7 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
                                  double* sum_wff, double* scratch, cudaStream_t st, int* launches);
 
 // tcgen05 / TF32 covariance (cov_tc.cu): used for FP32 handles, unit row weights, 2D Legendre bases with
-// 128 < K <= 256; everything else runs moments2_kernel on the CUDA cores.
+// 64 < K <= 4096; everything else runs moments_small_kernel / moments2_kernel on the CUDA cores.
 bool cov_tc_supported(const RowSource<float>& S, const BasisParams<float>& B);
 size_t cov_tc_scratch_floats(int n_sm);
 cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B, double* sum_wff, float* scratch, int n_sm,

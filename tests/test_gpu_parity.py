@@ -567,9 +567,10 @@ def test_equilibrium_sampling_double_well_fes():
     e.close()
 
 
-@pytest.mark.parametrize("deg,sizes", [(15, (31, 10007, 300000)), (19, (10007,)), (31, (77, 5003))], ids=["K256", "K400", "K1024"])
+@pytest.mark.parametrize("deg,sizes", [(9, (10007,)), (15, (31, 10007, 300000)), (19, (10007,)), (31, (77, 5003))],
+                         ids=["K100", "K256", "K400", "K1024"])
 def test_covariance_tensor_core_path(deg, sizes):
-    """K > 128 covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM), tiled into
+    """K > 64 covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM), tiled into
     256 x 256 output tiles (K = 400: padded tiles, K = 1024: 10 upper-triangular tiles): agrees with the FP64
     oracle to TF32 rounding (2^-11 per factor, averaging out over rows) and with the CUDA-core kernel;
     symmetric exactly; row 0 reproduces the first moments (f_0 = 1)."""

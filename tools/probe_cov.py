@@ -28,7 +28,7 @@ def t_ms(fn, reps=5):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
     out = []
-    for k in (12, 16, 20, 32):
+    for k in (6, 8, 10, 12, 16, 20, 32):
         e = _lib.Ensemble(n, dims=2, seed=1, precision="fp32")
         e.set_integrator(1.0, 2.494, 20.0, 0.01)
         e.set_potential(_lib.POT_DOUBLE_WELL_2D)
