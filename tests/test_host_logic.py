@@ -172,6 +172,44 @@ def test_host_side_validation_messages():
     assert sim.biased and sim.static and sim.startafter is None
 
 
+def test_ensemble_bias_host_logic_without_gpu():
+    """VESBias_Ensemble pieces that need no device: sample_domain validation and its hand-over through the bias
+    descriptor, DeviceUpdater.supports, and the path-CV target averages (node sums of Legendre polynomials)."""
+    from pyves_b200 import basis, bias, target
+    kT = 8.3145e-3 * 300
+    sgd = {"mu": 0.5, "averaging": "ewma", "decay": 0.8}
+    m2 = basis.LegendreBasis2D(3, 3, -1, 1, -1, 1)
+    with pytest.raises(ValueError, match="sample_domain"):
+        bias.VESBias_Ensemble(m2, target.Target_Uniform_2D(8, 8), 1 / kT, "averaged_sgd", sgd, sample_domain="plane")
+    for dom, flag in (("box", True), ("all", False)):
+        b = bias.VESBias_Ensemble(m2, target.Target_Uniform_2D(8, 8), 1 / kT, "averaged_sgd", sgd, sample_domain=dom)
+        d = b.force
+        assert d.kind == "legendre2d" and d.moment_inside is flag
+        assert bias.DeviceUpdater.supports(b)
+    assert bias.StaticBias_SingleParticle(m2, None).force.moment_inside is None      # static biases leave the domain alone
+    nn = basis.NNBasis1D(-4, 4, hidden_layer_sizes=[8, 8])
+    assert not bias.DeviceUpdater.supports(bias.VESBias_Ensemble(nn, target.Target_Uniform_HardSwitch_x(50), 1 / kT, "Adam", {"lr": 1e-3}))
+    assert not bias.DeviceUpdater.supports(bias.VESBias_Ensemble(m2, target.Target_Uniform_2D(8, 8), 1 / kT, "averaged_sgd", sgd,
+                                                                 gradient_average='running'))
+    # path CV: uniform target on [-1, 1] -> <P_k>_p = delta_k0 (trapezoid rule on 2001 nodes); well-tempered refresh
+    x_i, y_i = np.linspace(-2, 2, 30), np.zeros(30)
+    mp = basis.LegendreBasis2DPathCV(6, x_i, y_i, 100.0, weights=np.array([0.0, 1.0, -0.5, 0.0, 0.2, 0.0, 0.0]))
+    bp = bias.VESBias_Ensemble(mp, target.Target_Uniform_HardSwitch_x(2001), 1 / kT, "averaged_sgd", sgd, target_update_every=0)
+    ft = bp.target_average()
+    assert abs(ft[0] - 1) < 1e-12 and np.max(np.abs(ft[1:])) < 1e-5
+    assert not bias.DeviceUpdater.supports(bp)
+    bw = bias.VESBias_Ensemble(mp, target.Target_WellTempered_x(401, 4.0), 1 / kT, "averaged_sgd", sgd, target_update_every=1)
+    s = np.asarray(bw.target.x)
+    V = np.polynomial.legendre.legval(s, mp.weights.detach().numpy())
+    bw.refresh_target()
+    p_ref = np.exp(-(1 / kT / 4.0) * ((-V - np.log(0.5) * kT) - (-V - np.log(0.5) * kT).min()))
+    wq = np.ones_like(s); wq[0] = wq[-1] = 0.5
+    p_ref /= np.sum(p_ref * wq) * (s[1] - s[0])
+    assert np.max(np.abs(bw.target.p - p_ref)) < 1e-12
+    F = bw.fes()
+    assert F.min() == 0 and F.shape == s.shape
+
+
 def test_torchscript_exports_are_scriptable_and_match_oracle(tmp_path, golden):
     """model_loc files (ves/bias.py:52-53) load with plain torch.jit and reproduce the golden values."""
     import torch
