@@ -424,6 +424,24 @@ def torchforce_style_rate(args, steps=300):
             v = a * v + b * F + c * rng.standard_normal((1, 3))
             x = x + dt * v
         out[name] = steps / (time.perf_counter() - t0)
+    # best-effort vectorised CPU (figure 2): the same TorchScript module on a batch of 10^5
+    # particles, all cores, autograd for the forces, vectorised numpy integrator
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    nb, nst = 100000, 6
+    ts = mods["legendre2d_%dx%d" % (args.basis, args.basis)].export_torchscript()
+    x = np.concatenate([rng.uniform(-1.6, -1.2, (nb, 1)), rng.uniform(-0.3, 0.3, (nb, 1)), np.zeros((nb, 1))], 1)
+    v = np.zeros((nb, 3))
+    for it in range(nst + 2):
+        if it == 2:
+            t0 = time.perf_counter()
+        pos = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        ts(pos).sum().backward()
+        F = -pos.grad.numpy()
+        F[:, 0] -= 10 * (4 * x[:, 0] ** 3 - 8 * x[:, 0] + 0.7)
+        F[:, 1] -= 10 * x[:, 1]
+        v = a * v + b * F + c * rng.standard_normal((nb, 3))
+        x = x + dt * v
+    out["legendre2d_%dx%d_batched_1e5_all_cores" % (args.basis, args.basis)] = nb * nst / (time.perf_counter() - t0)
     torch.set_num_threads(old_threads)
     return out
 
@@ -445,10 +463,10 @@ def cpu_baseline(args, seconds=12.0):
             "sample": "%d walkers x %d steps + moments + update, FP64, gcc -O3 OpenMP C port of the same path "
                       "(oracle/c/pyves_oracle.c); the reference itself (Python + OpenMM + TorchForce) cannot run here: "
                       "OpenMM absent" % (n, args.stride),
-            "torchforce_style_single_walker": dict(torchforce_style_rate(args), unit="walker-steps/s", cores=1,
-                                                   note="TorchScript bias forward + backward per step for one particle on the "
-                                                        "CPU + numpy Langevin update: the per-step work of the reference's "
-                                                        "TorchForce path without OpenMM's own overhead")}
+            "torchforce_style": dict(torchforce_style_rate(args), unit="walker-steps/s",
+                                     note="TorchScript bias forward + backward per step on the CPU + numpy Langevin update: the "
+                                          "per-step work of the reference's TorchForce path without OpenMM's own overhead; one "
+                                          "particle on one thread (the reference's regime) and a 10^5-particle batch on all cores")}
 
 
 def run_reference(args):
