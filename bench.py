@@ -172,10 +172,13 @@ def run_ours(args):
         if timed:
             b.record()
             step_events.append((a, b))
-        sw, sf, _ = reduce_moments(*ens.moments())               # one NCCL allreduce of 1 + K doubles
         if upd is not None:
-            upd.update(sw, sf)                                   # optimiser + target + coefficient hand-over, all enqueued
+            bufs = upd.moment_buffers(False)
+            ens.moments(out=bufs)                                # 1 + K doubles into the updater's flat buffer
+            upd.reduce_flat()                                    # one NCCL all-reduce, in place
+            upd.update(*bufs)                                    # optimiser kernel + target + coefficient hand-over, all enqueued
         else:
+            sw, sf, _ = reduce_moments(*ens.moments())           # one NCCL allreduce of 1 + K doubles
             bias.update_from_moments(sw, sf)                     # host optimiser on K coefficients
             bias.force.apply(ens)                                # re-upload the coefficients
 

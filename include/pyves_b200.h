@@ -169,6 +169,17 @@ int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const dou
  * the general step kernel) refresh a host copy first (one synchronous 8 (degree + 1)-byte read). */
 int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double min, double max, const double* w_dev, void* stream);
 
+/* One averaged-SGD update of the coefficients entirely on `device` (all pointers device, FP64): gradient
+ * f_target - sum_wf / sum_w, Hessian term beta Cov (alpha - abar) when sum_wff != NULL, optional diagonal
+ * preconditioner `scale`, then the EWMA (averaging 0) or running (averaging 1, n_after = updates done incl. this
+ * one) average.  The optimiser step that ves/bias.py:236-245 delegates to torch.optim on the host after a
+ * Python loop over the trajectory; here it is one kernel between pyves_moments and
+ * pyves_set_bias_legendre*_device.  Outputs must not alias the inputs. */
+int pyves_averaged_sgd_step(int device, int K, const double* sum_w, const double* sum_wf, const double* sum_wff,
+                            const double* f_target, const double* alpha, const double* abar, const double* scale,
+                            double mu, double beta, int averaging, double decay, int64_t n_after, double* alpha_out,
+                            double* abar_out, void* stream);
+
 /* Domain of the ensemble averages of pyves_moments for the Legendre / path-CV bases.  0 (default): every
  * row counts, rows outside the basis interval enter with their clamped coordinate, exactly what
  * LegendreBasis1D.forward does to them (ves/basis.py:143).  1: rows outside the interval get weight 0, i.e.

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
     "pyves_set_moment_domain": (_i, [_vp, _i]),
+    "pyves_averaged_sgd_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _i64, _vp, _vp, _vp]),
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
     "pyves_set_bias_legendre1d_device": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
@@ -99,6 +100,17 @@ def _raise(code, handle):
     if code == ENOMEM:
         raise MemoryError(msg)
     raise RuntimeError(msg)
+
+
+def averaged_sgd_step(device, sum_w, sum_wf, sum_wff, f_target, alpha, abar, scale, mu, beta, averaging, decay, n_after,
+                      alpha_out, abar_out):
+    """pyves_averaged_sgd_step on CUDA float64 tensors (enqueued on the current stream of ``device``)."""
+    lib = load()
+    rc = lib.pyves_averaged_sgd_step(device, alpha.numel(), _ptr(sum_w), _ptr(sum_wf), _ptr(sum_wff), _ptr(f_target), _ptr(alpha), _ptr(abar),
+                                     _ptr(scale), float(mu), float(beta), 0 if averaging == 'ewma' else 1, float(decay), int(n_after),
+                                     _ptr(alpha_out), _ptr(abar_out), _stream(device))
+    if rc:
+        raise (ValueError if rc == -1 else RuntimeError)(lib.pyves_last_error(None).decode())
 
 
 def launch_count():
@@ -383,9 +395,17 @@ class Ensemble:
         self._ck(self.lib.pyves_energies(self.h, _ptr(PE), _ptr(KE), int(host), self.stream))
         return PE, KE
 
-    def moments(self, pos=None, row_weights=None, cov=False, host=False):
-        """(sum_w, sum_wf [K], sum_wff [K, K] or None) of the walkers (pos None) or of rows pos [n, ncols]."""
+    def moments(self, pos=None, row_weights=None, cov=False, host=False, out=None):
+        """(sum_w, sum_wf [K], sum_wff [K, K] or None) of the walkers (pos None) or of rows pos [n, ncols].
+        ``out`` = (sum_w, sum_wf, sum_wff or None): caller-owned CUDA float64 tensors that are overwritten (no
+        allocation, e.g. views of one flat buffer that is then all-reduced in place)."""
         import torch
+        if out is not None:
+            sw, sf, sff = out
+            n, ncols = (0, 0) if pos is None else pos.shape
+            with _Range("pyves.moments"):
+                self._ck(self.lib.pyves_moments(self.h, _ptr(pos), n, ncols, _ptr(row_weights), _ptr(sw), _ptr(sf), _ptr(sff), 0, self.stream))
+            return sw, sf, sff
         K = self.basis_size
         n, ncols = (0, 0) if pos is None else pos.shape
         if pos is not None and isinstance(pos, np.ndarray):

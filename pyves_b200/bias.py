@@ -453,6 +453,8 @@ class DeviceUpdater:
             tw[0] = tw[-1] = 0.5                               # trapezoid rule of Target_x.quadrature_weights
             self.trap = torch.tensor(tw, **f64)
         self.handles = [ens]                 # every handle that receives the coefficients (add_handle)
+        self._spare = (torch.empty_like(self.alpha), torch.empty_like(self.abar))
+        self._flat = None
         self._upload(self.ev)
         self.f_target = self._target_average()
         ens.set_moment_domain(bias.sample_domain == 'box')
@@ -485,22 +487,14 @@ class DeviceUpdater:
             self._update(sum_w, sum_wf, sum_wff)
 
     def _update(self, sum_w, sum_wf, sum_wff):
-        mean = sum_wf / sum_w
-        d = self.f_target - mean
-        if self.second_order:
-            if sum_wff is None:
-                raise ValueError("the second-order step needs the second moments (ens.moments(cov=True))")
-            hess = self.bias.beta * (sum_wff / sum_w - torch.outer(mean, mean))      # optim.gradient_hessian
-            d = d + hess @ (self.alpha - self.abar)
-        if self.scale is not None:
-            d = d * self.scale
-        self.alpha = self.alpha - self.mu * d
+        if self.second_order and sum_wff is None:
+            raise ValueError("the second-order step needs the second moments (ens.moments(cov=True))")
         self.n += 1
-        if self.averaging == 'ewma':
-            self.abar = self.decay * self.abar + (1.0 - self.decay) * self.alpha
-        else:
-            self.abar = self.abar + (self.alpha - self.abar) / (self.n + 1)
-        self.abar = self.abar.contiguous()
+        a_out, b_out = self._spare                                    # ping-pong: the kernel must not update in place
+        _lib.averaged_sgd_step(self.ens.device, sum_w, sum_wf, sum_wff if self.second_order else None, self.f_target, self.alpha,
+                               self.abar, self.scale, self.mu, self.bias.beta, self.averaging, self.decay, self.n, a_out, b_out)
+        self._spare = (self.alpha, self.abar)
+        self.alpha, self.abar = a_out, b_out
         self.n_updates += 1
         for hdl in self.handles:
             self._upload(hdl)
@@ -508,6 +502,22 @@ class DeviceUpdater:
         if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
             self.p = self._refreshed_density()
             self.f_target = self._target_average()
+
+    def moment_buffers(self, cov=None):
+        """Views (sum_w, sum_wf, sum_wff or None) of ONE persistent flat FP64 buffer for ``ens.moments(out=...)``:
+        no allocation per update, and ``reduce_flat`` all-reduces the flat buffer in place (one NCCL call)."""
+        cov = self.second_order if cov is None else cov
+        K = self.alpha.numel()
+        n = 1 + K + (K * K if cov else 0)
+        if getattr(self, "_flat", None) is None or self._flat.numel() != n:
+            self._flat = torch.zeros(n, dtype=torch.float64, device=self.dev)
+        f = self._flat
+        return f[:1], f[1:1 + K], (f[1 + K:].view(K, K) if cov else None)
+
+    def reduce_flat(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=group)
 
     def _refreshed_density(self):
         """Target_WellTempered_{x,2D}.update on the device: p' ~ exp(-(beta / gamma) F), F = -V - kT ln p."""

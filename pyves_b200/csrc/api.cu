@@ -670,6 +670,21 @@ int pyves_set_moment_domain(pyves_t* h, int inside_only) {
   return PYVES_OK;
 }
 
+int pyves_averaged_sgd_step(int device, int K, const double* sum_w, const double* sum_wf, const double* sum_wff, const double* f_target,
+                            const double* alpha, const double* abar, const double* scale, double mu, double beta, int averaging,
+                            double decay, int64_t n_after, double* alpha_out, double* abar_out, void* stream) {
+  pyves_ctx* h = nullptr;
+  if (K < 1 || !sum_w || !sum_wf || !f_target || !alpha || !abar || !alpha_out || !abar_out) return fail(h, PYVES_EINVAL, "averaged_sgd_step: NULL argument or K < 1");
+  if (alpha_out == alpha || abar_out == abar || alpha_out == abar || abar_out == alpha) return fail(h, PYVES_EINVAL, "averaged_sgd_step: outputs must not alias the inputs");
+  if (averaging != 0 && averaging != 1) return fail(h, PYVES_EINVAL, "averaged_sgd_step: averaging must be 0 (ewma) or 1 (running)");
+  DeviceGuard g(device);
+  cudaError_t e = launch_averaged_sgd_step(K, sum_w, sum_wf, sum_wff, f_target, alpha, abar, scale, mu, beta, averaging, decay,
+                                           (long long)n_after, alpha_out, abar_out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(h, PYVES_ECUDA, cudaGetErrorString(e));
+  g_launches++;
+  return PYVES_OK;
+}
+
 int pyves_set_tuning(pyves_t* h, int variant) {
   if (!h) return PYVES_EINVAL;
   if (variant == 98 || variant == 97) {   // 98: covariance on CUDA cores only; 97: tensor cores allowed again

@@ -285,6 +285,38 @@ cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm,
   return cudaGetLastError();
 }
 
+// one warp per coefficient k: the lanes split the Hessian row (fixed order, butterfly), lane 0 applies the update
+__global__ void __launch_bounds__(256) averaged_sgd_kernel(int K, const double* __restrict__ sum_w, const double* __restrict__ sum_wf,
+                                                           const double* __restrict__ sum_wff, const double* __restrict__ f_target,
+                                                           const double* __restrict__ alpha, const double* __restrict__ abar,
+                                                           const double* __restrict__ scale, double mu, double beta, int averaging, double decay,
+                                                           long long n_after, double* __restrict__ alpha_out, double* __restrict__ abar_out) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const double inv_w = 1.0 / sum_w[0];
+  const double mean_k = sum_wf[k] * inv_w;
+  double h = 0.0;
+  if (sum_wff != nullptr) {
+    for (int l = lane; l < K; l += 32) h += (sum_wff[(size_t)k * K + l] * inv_w - mean_k * (sum_wf[l] * inv_w)) * (alpha[l] - abar[l]);
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  }
+  if (lane != 0) return;
+  double d = f_target[k] - mean_k + beta * h;
+  if (scale != nullptr) d *= scale[k];
+  const double a = alpha[k] - mu * d;
+  alpha_out[k] = a;
+  abar_out[k] = averaging == 0 ? decay * abar[k] + (1.0 - decay) * a : abar[k] + (a - abar[k]) / (double)(n_after + 1);
+}
+
+cudaError_t launch_averaged_sgd_step(int K, const double* sum_w, const double* sum_wf, const double* sum_wff, const double* f_target,
+                                     const double* alpha, const double* abar, const double* scale, double mu, double beta, int averaging,
+                                     double decay, long long n_after, double* alpha_out, double* abar_out, cudaStream_t st) {
+  averaged_sgd_kernel<<<(K + 7) / 8, 256, 0, st>>>(K, sum_w, sum_wf, sum_wff, f_target, alpha, abar, scale, mu, beta, averaging, decay, n_after,
+                                                   alpha_out, abar_out);
+  return cudaGetLastError();
+}
+
 template <typename T>
 __global__ void convert_weights1d_kernel(const double* __restrict__ w64, int n, T* __restrict__ w_t, double* __restrict__ keep64) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

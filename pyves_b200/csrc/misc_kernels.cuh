@@ -18,6 +18,15 @@ cudaError_t launch_convert_weights2d(const double* w64, int kx, int ky, T* w_rm,
 template <typename T>
 cudaError_t launch_convert_weights1d(const double* w64, int n, T* w_t, double* keep64, cudaStream_t st);
 
+// One averaged-SGD update of the VES coefficients on the device (FP64), the host twin is pyves_b200/optim.py:
+//   mean = sum_wf / sum_w;  d = f_target - mean  (+ beta (sum_wff / sum_w - mean mean^T) (alpha - abar) when sum_wff)
+//   d *= scale (optional);  alpha' = alpha - mu d;  abar' = decay abar + (1 - decay) alpha'   (averaging 0, EWMA)
+//                                                   abar' = abar + (alpha' - abar) / (n + 1)  (averaging 1, running)
+// alpha_out / abar_out must not alias the inputs (the Hessian term reads every old entry).
+cudaError_t launch_averaged_sgd_step(int K, const double* sum_w, const double* sum_wf, const double* sum_wff, const double* f_target,
+                                     const double* alpha, const double* abar, const double* scale, double mu, double beta, int averaging,
+                                     double decay, long long n_after, double* alpha_out, double* abar_out, cudaStream_t st);
+
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>
 cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,

@@ -177,6 +177,14 @@ class SingleParticleSimulation:
                     self._updater = DeviceUpdater(self.bias, self.ens)    # optimiser state + coefficients stay on the GPU
                 else:
                     self.bias.force.apply(self.ens)  # defines the basis for the moment kernels; forces start now
+            if self._updater is not None and self._acc is None:
+                # lean path: moments into the updater's persistent flat buffer, ONE in-place all-reduce, one optimiser
+                # kernel, coefficient hand-over -- four library calls and one NCCL call per update, nothing else
+                bufs = self._updater.moment_buffers(self.bias.needs_covariance)
+                self.ens.moments(cov=self.bias.needs_covariance, out=bufs)
+                self._updater.reduce_flat(self.process_group)
+                self._updater.update(*bufs)
+                return
             self._sample_moments()
             sw, sf, sff = reduce_moments(*self._acc, group=self.process_group)   # one allreduce per update
             self._acc = None

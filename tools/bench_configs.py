@@ -94,8 +94,9 @@ def cfg3(iters):
 
     def it():
         e.step(STRIDE)
-        sw, sf, sff = e.moments(cov=True)
-        upd.update(sw, sf, sff)
+        bufs = upd.moment_buffers(True)
+        e.moments(cov=True, out=bufs)
+        upd.update(*bufs)
     t = timed(it, iters)
     parts = dict(steps_ms=timed(lambda: e.step(STRIDE), 3) * 1e3, moments_cov_ms=timed(lambda: e.moments(cov=True), 3) * 1e3)
     upd.close()
