@@ -45,16 +45,8 @@ template <> struct Pair<float> {
     asm("mov.b64 %0, {%1, %2};" : "=l"(p.v) : "f"(lo), "f"(hi));
     return p;
   }
-  PV_DEV float lo() const {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-  }
-  PV_DEV float hi() const {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-  }
+  PV_DEV float lo() const { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+  PV_DEV float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
   // a * w + c with the scalar w broadcast to both halves
   static PV_DEV Pair fma_bcast(Pair a, float w, Pair c) {
     Pair d, ww = make(w, w);
