@@ -393,7 +393,10 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
     case PYVES_BIAS_LEGENDRE_2D: {
       const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
       const Legendre2DSmemParams<T> BP = l2_params<T>(h);
-      if (pk == PYVES_POT_DOUBLE_WELL_2D) {
+      // FP64 16 x 16: the static functor feeds every DFMA with its own LDC.64 (196 per step, ADU bound); the
+      // shared-memory column sweep is 19 % faster there (1.83e10 vs 1.54e10 walker-steps/s), so doubles skip it
+      const bool static_ok = !(sizeof(T) == 8 && kx == 16 && ky == 16 && h->variant != 1);
+      if (pk == PYVES_POT_DOUBLE_WELL_2D && h->variant != 2 && static_ok) {   // variant 2: runtime-size functor for tuning runs
         if (h->l2_dev_mode && ((kx == 8 && ky == 8) || (kx == 16 && ky == 16)) && h->device < 64) {
           // coefficients were set from a device pointer: the kernels read them from the __constant__ array
           const uint64_t tag = (h->serial << 32) | (h->l2_version & 0xffffffffull);

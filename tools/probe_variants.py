@@ -77,9 +77,9 @@ def main():
         run("dw_none", prec, DW, (), lambda e: e.set_bias_none(), variants=(-1, 1), flops=32)
         run("cfg1_dw_leg1d5", prec, DW, (), lambda e: e.set_bias_legendre1d(0, 5, -2.5, 2.5, rng.standard_normal(6)), variants=(-1, 1), flops=70)
         run("cfg3_slip_leg1d12", prec, SLIP, slip, lambda e: e.set_bias_legendre1d(0, 12, -3, 6, rng.standard_normal(13) * 0.1), variants=(-1, 1), flops=133, box=(-8, 10, -6, 8))
-        run("dw_leg2d8", prec, DW, (), lambda e: e.set_bias_legendre2d(7, 7, (-2.5, 2.5, -2, 2), rng.standard_normal(64) * 0.1), variants=(-1, 1), flops=4 * 64 + 32 + 84 + 32)
+        run("dw_leg2d8", prec, DW, (), lambda e: e.set_bias_legendre2d(7, 7, (-2.5, 2.5, -2, 2), rng.standard_normal(64) * 0.1), variants=(-1, 1, 2), flops=4 * 64 + 32 + 84 + 32)
         run("cfg2_dw_leg2d16", prec, DW, (), lambda e: e.set_bias_legendre2d(15, 15, (-2.5, 2.5, -2, 2), rng.standard_normal(256) * 0.1),
-            variants=(-1, 1), flops=1300)
+            variants=(-1, 1, 2), flops=1300)
         run("cfg5_dw_leg2d32", prec, DW, (), lambda e: e.set_bias_legendre2d(31, 31, (-2.5, 2.5, -2, 2), rng.standard_normal(1024) * 0.05), flops=4628)
         run("cfg5_dw_leg2d64", prec, DW, (), lambda e: e.set_bias_legendre2d(63, 63, (-2.5, 2.5, -2, 2), rng.standard_normal(4096) * 0.02), flops=17428)
         run("cfg4_sb_mlp48x3", prec, SB, sb, lambda e: e.set_bias_mlp(0, -4, 4, [48, 48, 48], 0, rng.standard_normal(4849) * 0.2), flops=9635, box=(-4, 4, -4, 4))
