@@ -405,7 +405,7 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
             g_const_owner[h->device].store(tag);
           }
           if (kx == 8) return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8, true>, 2, 1>(h, A, l2_static_tc_params<T, 8, 8>(h), st);
-          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, true>, 1, 1>(h, A, l2_static_tc_params<T, 16, 16>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, true, kHybrid16>, 1, 1>(h, A, l2_static_tc_params<T, 16, 16>(h), st);
         }
         // variant 1 selects the row-major functor (kept for tuning runs); default = column sweep
         if (kx == 8 && ky == 8 && !h->l2_dev_mode) {
@@ -414,7 +414,7 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
         }
         if (kx == 16 && ky == 16 && !h->l2_dev_mode) {
           if (h->variant == 1) return run_fast<T, DW, BiasLegendre2DStatic<T, 16, 16>, 1, 1>(h, A, l2_static_params<T, 16, 16>(h), st);
-          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
+          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, false, kHybrid16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
         }
         if (kx > 16 && kx <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 1, 5>, 1, 2>(h, A, BP, st);
         if (kx > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 2, 5>, 1, 2>(h, A, BP, st);

@@ -248,15 +248,28 @@ template <typename T, int KX, int KY> struct Legendre2DStaticTCParams {
   T cx, ihx, cy, ihy;
 };
 
-template <typename T, int KX, int KY, bool CONSTSYM = false> struct BiasLegendre2DStaticT {
+// J0 < KY makes the sweep HYBRID: columns j < J0 take their weights from the constant bank, columns j >= J0 from a
+// shared-memory copy read with volatile LDS.128 broadcasts right before use.  ptxas feeds only ~64 of the 256
+// weights of the 16 x 16 kernel through cheap uniform loads and fetches the rest with LDC.64 into vector registers
+// (ADU path, one per ~8.7 cycles per scheduler); moving those columns to the LSU path is worth 5 %:
+// 16 x 16, 10^6 walkers x 500 steps: 11.83 ms all constant bank, 11.21 ms with J0 = 4 (profiles/r01_variants.md).
+template <typename T, int KX, int KY, bool CONSTSYM = false, int J0 = KY> struct BiasLegendre2DStaticT {
   using Params = typename std::conditional<CONSTSYM, Legendre2DStaticTCParams<T, KX, KY>, Legendre2DStaticTParams<T, KX, KY>>::type;
   static_assert(!CONSTSYM || KX * KY <= kConstWeights, "constant weight array too small");
+  static_assert(J0 >= 2 && J0 <= KY, "columns 0 and 1 always come from the constant bank");
+  static constexpr int V = 16 / sizeof(T);
   template <bool C = CONSTSYM> static PV_DEV typename std::enable_if<C, T>::type weight(const Params&, int idx) { return const_weights<T>()[idx]; }
   template <bool C = CONSTSYM> static PV_DEV typename std::enable_if<!C, T>::type weight(const Params& P, int idx) { return P.wt[idx]; }
   static_assert(KX >= 2 && KY >= 2, "static sizes start at 2 x 2");
-  static size_t smem_bytes(const Params&) { return 0; }
-  static PV_DEV void stage(const Params&, void*) {}
-  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void*, T x, T y, T& e, T& gx, T& gy) {
+  static size_t smem_bytes(const Params&) { return J0 < KY ? sizeof(T) * KX * KY : 0; }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    if (J0 < KY) {
+      T* d = reinterpret_cast<T*>(smem);
+      for (int i = threadIdx.x; i < KX * KY; i += blockDim.x) d[i] = weight(P, i);
+    }
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    const T* ws = reinterpret_cast<const T*>(smem);
     bool inx, iny;
     const T sx = scale_clamp(x, P.cx, P.ihx, inx);
     const T sy = scale_clamp(y, P.cy, P.ihy, iny);
@@ -274,8 +287,18 @@ template <typename T, int KX, int KY, bool CONSTSYM = false> struct BiasLegendre
       const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
       pm = p; p = pn; dpm = dp; dp = dpn;
       const Pair<T> Q = Pair<T>::make(p, dp);
+      if (j < J0) {
 #pragma unroll
-      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, weight(P, j * KX + i), AB[i]);
+        for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, weight(P, j * KX + i), AB[i]);
+      } else {
+#pragma unroll
+        for (int iv = 0; iv < KX / V; ++iv) {
+          T w[V];
+          lds_vec(ws + j * KX + iv * V, w);
+#pragma unroll
+          for (int q = 0; q < V; ++q) Pair<T>::acc_bcast(AB[iv * V + q], Q, w[q]);
+        }
+      }
     }
     // row sweep: (dV/dsx, dV/dsy) = sum_i (P'_i(x'), P_i(x')) * (A_i, B_i), two chains
     Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));

@@ -11,6 +11,8 @@
 namespace pv {
 
 constexpr int kStepThreads = 128;
+// leading columns of the static 16 x 16 sweep that keep their weights in the constant bank (bias.cuh, hybrid sweep)
+constexpr int kHybrid16 = 4;
 
 template <typename T> struct IntegratorParams {
   T a;              // exp(-gamma dt)

@@ -36,9 +36,9 @@ PV_PAIR(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5>, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStatic<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8>, 2, 1)
-PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA false PV_COMMA kHybrid16>, 1, 1)
 PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 8 PV_COMMA 8 PV_COMMA true>, 2, 1)
-PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA true>, 1, 1)
+PV_FAST(PotDoubleWell2D<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA true PV_COMMA kHybrid16>, 1, 1)
 // every kernel that reads the __constant__ weights lives in THIS translation unit (the array is per unit)
 PV_PAIR(PotDoubleWell2D<T>, BiasLegendre1D<T PV_COMMA 5 PV_COMMA true>, 1)
 PV_PAIR(PotSlipBond2D<T>, BiasLegendre1D<T PV_COMMA 12 PV_COMMA true>, 1)

@@ -170,4 +170,67 @@ template <typename T, int KXP, int UNR> struct BiasLegendre2DSmemT {
   }
 };
 
+// Experiment: hybrid column sweep -- the first J0 columns take their weights from the constant bank (static),
+// the others from shared memory (volatile LDS.128 right before use), to trade LDC / ADU traffic for LSU traffic.
+template <int KX, int KY> struct Legendre2DStaticTHParams {
+  float cx, ihx, cy, ihy;
+  float wt[KY * KX];        // constant-bank copy
+  const float* wdev;        // device copy of the same transposed weights (staged into shared memory)
+};
+template <int KX, int KY, int J0, bool TAIL = false> struct BiasLegendre2DStaticTH {
+  using T = float;
+  using Params = Legendre2DStaticTHParams<KX, KY>;
+  static size_t smem_bytes(const Params&) { return sizeof(T) * KX * KY; }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    T* d = reinterpret_cast<T*>(smem);
+    for (int i = threadIdx.x; i < KX * KY; i += blockDim.x) d[i] = P.wdev[i];
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    const T* ws = reinterpret_cast<const T*>(smem);
+    Pair<T> AB[KX];
+    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+    {
+      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
+#pragma unroll
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
+    }
+#pragma unroll
+    for (int j = 2; j < KY; ++j) {
+      const T pn = leg_a<T>(j - 1) * sy * p - leg_b<T>(j - 1) * pm;
+      const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
+      pm = p; p = pn; dpm = dp; dp = dpn;
+      const Pair<T> Q = Pair<T>::make(p, dp);
+      if (TAIL ? (j >= KY - J0 + 2) : (j < J0)) {
+#pragma unroll
+        for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
+      } else {
+#pragma unroll
+        for (int iv = 0; iv < KX / 4; ++iv) {
+          T w[4];
+          lds_vec(ws + j * KX + iv * 4, w);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) Pair<T>::acc_bcast(AB[iv * 4 + q], Q, w[q]);
+        }
+      }
+    }
+    Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));
+    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
+#pragma unroll
+    for (int i = 1; i < KX; ++i) {
+      if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G1);
+      else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G0);
+    }
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
+  }
+};
+
 }  // namespace pv

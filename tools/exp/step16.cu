@@ -99,6 +99,10 @@ int main(int argc, char** argv) {
     if (o == "T2") run<BiasLegendre2DStaticT<float, 16, 16>, WPT_T, MINB_T>("T gch2", Tt, n, steps, p0, v0, out, 2);
     return 0;
   }
+  static Legendre2DStaticTHParams<16, 16> TH{};
+  TH.cx = 0; TH.ihx = 1 / 2.5f; TH.cy = 0; TH.ihy = 1 / 2.0f;
+  for (int k = 0; k < 256; ++k) TH.wt[k] = Tt.wt[k];
+  { float* wd; cudaMalloc(&wd, 1024); cudaMemcpy(wd, Tt.wt, 1024, cudaMemcpyHostToDevice); TH.wdev = wd; }
   // numerics check on a short run
   const int64_t nc = 4096;
   std::vector<float> pc(2 * nc), vc(2 * nc);
@@ -112,7 +116,17 @@ int main(int argc, char** argv) {
   run<BiasLegendre2DRolledT<float, 16, 16, UNR_T, SRC_T>, WPT_T, MINB_T>("rolled", R, n, steps, p0, v0, out, 3);
   return 0;
 #endif
-  run<BiasLegendre2DStatic<float, 16, 16, 4, false>, 1, 1>("base rows4 nosplit", S, n, steps, p0, v0, ref, 3);
-  run<BiasLegendre2DStaticT<float, 16, 16>, WPT_T, MINB_T>("T gch2", Tt, n, steps, p0, v0, out, 3);
+  { std::vector<float> tmp; run<BiasLegendre2DStatic<float, 16, 16, 4, false>, 1, 1>("base rows4 nosplit", S, n, steps, p0, v0, tmp, 3); }
+  { std::vector<float> tmp; run<BiasLegendre2DStaticT<float, 16, 16>, WPT_T, MINB_T>("T gch2", Tt, n, steps, p0, v0, tmp, 3); }
+  run<BiasLegendre2DStaticTH<16, 16, 6>, 1, 1>("check TH6", TH, nc, 40, pc, vc, out, 1);
+  printf("max |dx| after 40 steps, TH vs base: %.3e\n", maxdiff(ref, out));
+  run<BiasLegendre2DStaticTH<16, 16, 4>, 1, 1>("TH J0=4", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 6>, 1, 1>("TH J0=6", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 10>, 1, 1>("TH J0=10", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 5>, 1, 1>("TH J0=5", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 8>, 1, 1>("TH J0=8", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 4, true>, 1, 1>("TH tail 4 (2 cols)", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 6, true>, 1, 1>("TH tail 6 (4 cols)", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 8, true>, 1, 1>("TH tail 8 (6 cols)", TH, n, steps, p0, v0, out, 3);
   return 0;
 }
