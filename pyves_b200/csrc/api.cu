@@ -419,6 +419,9 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
         if (kx > 16 && kx <= 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 1, 5>, 1, 2>(h, A, BP, st);
         if (kx > 32) return run_fast<T, DW, BiasLegendre2DSmem<T, 32, 2, 5>, 1, 2>(h, A, BP, st);
       }
+      // any other potential with a 16 x 16 basis: the same static hybrid sweep behind the runtime potential switch
+      if (kx == 16 && ky == 16 && !h->l2_dev_mode && static_ok && h->variant != 2 && pk != PYVES_POT_DOUBLE_WELL_2D)
+        return run_fast<T, GP, BiasLegendre2DStaticT<T, 16, 16, false, kHybrid16>, 1, 1>(h, A, l2_static_t_params<T, 16, 16>(h), st);
       if (kx <= 16) return run_fast<T, GP, BiasLegendre2DSmem<T, 16, 1, 7>, 1, 3>(h, A, BP, st);
       if (kx <= 32) return run_fast<T, GP, BiasLegendre2DSmem<T, 32, 1, 5>, 1, 2>(h, A, BP, st);
       return run_fast<T, GP, BiasLegendre2DSmem<T, 32, 2, 5>, 1, 2>(h, A, BP, st);

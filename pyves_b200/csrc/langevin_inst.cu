@@ -65,6 +65,7 @@ PV_FAST(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 2, 1)
 PV_PAIR(PotGeneric<T>, BiasNone<T>, 1)
 PV_PAIR(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 16 PV_COMMA 1 PV_COMMA 7>, 1, 3)
+PV_FAST(PotGeneric<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA false PV_COMMA kHybrid16>, 1, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasOther<T>, 1, 1)

@@ -171,6 +171,9 @@ TRAJ_CASES = [
     ("dw_leg2d64", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=63, deg_y=63, scale=0.5), (-1.6, -1.2, -0.3, 0.3), [-1]),
     ("dw_leg2d_5x11", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=10), (-1.6, -1.2, -0.3, 0.3), [-1]),
     ("slip_none", potentials.SLIP_BOND_2D, None, lambda r: dict(kind="none"), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("slip_leg2d16", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15, minmax=(-6.0, 6.0, -6.0, 6.0), scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1, 2]),
+    ("mb_leg2d_40x24", potentials.MULLER_BROWN, None, lambda r: rng_spec("leg2d", r, deg_x=39, deg_y=23, minmax=(-1.5, 1.0, 0.0, 2.0), scale=0.3), (-0.6, -0.5, 1.4, 1.5), [-1]),
+    ("sb_leg2d_20x36", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("leg2d", r, deg_x=19, deg_y=35, minmax=(-4.0, 4.0, -4.0, 4.0), scale=0.5), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("slip_leg1d12", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg1d", r, degree=12, min=-3.0, max=6.0, scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1]),
     ("slip_forced_leg1d7y", potentials.SLIP_BOND_2D, (1.5, -0.5, 0.8, 4.0, 3.0, 0.2, 2.5), lambda r: rng_spec("leg1d", r, degree=7, axis='y', min=-4.0, max=6.0, scale=1.0), (-3.0, -2.5, -3.0, -2.5), [-1]),
     ("sb_none", potentials.SZABO_BEREZHKOVSKII, None, lambda r: dict(kind="none"), (2.0, 2.4, 2.0, 2.4), [-1]),
