@@ -123,6 +123,9 @@ int main(int argc, char** argv) {
   run<BiasLegendre2DStaticTH<16, 16, 4>, 1, 1>("TH J0=4", TH, n, steps, p0, v0, out, 3);
   run<BiasLegendre2DStaticTH<16, 16, 6>, 1, 1>("TH J0=6", TH, n, steps, p0, v0, out, 3);
   run<BiasLegendre2DStaticTH<16, 16, 10>, 1, 1>("TH J0=10", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 4>, 2, 1>("TH J0=4 WPT2", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 8>, 2, 1>("TH J0=8 WPT2", TH, n, steps, p0, v0, out, 3);
+  run<BiasLegendre2DStaticTH<16, 16, 16>, 2, 1>("TH J0=16 WPT2", TH, n, steps, p0, v0, out, 3);
   run<BiasLegendre2DStaticTH<16, 16, 5>, 1, 1>("TH J0=5", TH, n, steps, p0, v0, out, 3);
   run<BiasLegendre2DStaticTH<16, 16, 8>, 1, 1>("TH J0=8", TH, n, steps, p0, v0, out, 3);
   run<BiasLegendre2DStaticTH<16, 16, 4, true>, 1, 1>("TH tail 4 (2 cols)", TH, n, steps, p0, v0, out, 3);
