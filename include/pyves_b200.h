@@ -169,6 +169,15 @@ int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const dou
  * the general step kernel) refresh a host copy first (one synchronous 8 (degree + 1)-byte read). */
 int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double min, double max, const double* w_dev, void* stream);
 
+/* h takes the SAME device-resident Legendre coefficients as `leader` (same device and precision; the leader's
+ * bias was set by pyves_set_bias_legendre{1d,2d}_device): two device-to-device copies of the leader's converted
+ * weights in stream order, and the same content tag, so that handles which evaluate one bias on shards of one
+ * ensemble (each on its own stream) share the __constant__ weights instead of re-copying and serialising on
+ * them.  Independent handles need no such call: launches that read the __constant__ array and copies into it are
+ * ordered across streams with events.  Replaces, like the two calls above, the TorchForce reload of
+ * ves/langevin_dynamics.py:153-159 for every replica that shares one bias. */
+int pyves_set_bias_like(pyves_t* h, const pyves_t* leader, void* stream);
+
 /* One averaged-SGD update of the coefficients entirely on `device` (all pointers device, FP64): gradient
  * f_target - sum_wf / sum_w, Hessian term beta Cov (alpha - abar) when sum_wff != NULL, optional diagonal
  * preconditioner `scale`, then the EWMA (averaging 0) or running (averaging 1, n_after = updates done incl. this

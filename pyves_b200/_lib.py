@@ -60,6 +60,7 @@ SIGNATURES = {
     "pyves_averaged_sgd_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _i64, _vp, _vp, _vp]),
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
     "pyves_set_bias_legendre1d_device": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
+    "pyves_set_bias_like": (_i, [_vp, _vp, _vp]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -284,6 +285,10 @@ class Ensemble:
             raise ValueError("w_dev lives on another device")
         m, mp = _darr(minmax)
         self._ck(self.lib.pyves_set_bias_legendre2d_device(self.h, deg_x, deg_y, mp, ctypes.c_void_p(w_dev.data_ptr()), self.stream))
+
+    def set_bias_like(self, leader):
+        """Share the device-resident Legendre coefficients of ``leader`` (same device and precision)."""
+        self._ck(self.lib.pyves_set_bias_like(self.h, leader.h, self.stream))
 
     def set_bias_mlp(self, axis, lo, hi, sizes, act, theta):
         a, p = _darr(theta)

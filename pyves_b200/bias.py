@@ -470,6 +470,9 @@ class DeviceUpdater:
 
     def _upload(self, handle):
         m = self.bias.model
+        if handle is not self.ens and handle is not self.ev and handle.precision == self.ens.precision:
+            handle.set_bias_like(self.ens)          # shards of one ensemble share the converted weights (and their tag)
+            return
         if self.two_d:
             handle.set_bias_legendre2d_device(m.degree_x, m.degree_y, (m.min_x, m.max_x, m.min_y, m.max_y), self.abar)
         else:

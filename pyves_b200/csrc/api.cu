@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -15,9 +16,9 @@
 using namespace pv;
 
 static std::atomic<int64_t> g_launches{0};
-// which handle's weights the __constant__ array currently holds, per device (serial << 32 | version)
-std::atomic<uint64_t> g_const_owner[64];
-std::atomic<uint64_t> g_handle_serial{1};
+// content tag of device-resident coefficients: a fresh value per pyves_set_bias_legendre{1d,2d}_device call,
+// copied by pyves_set_bias_like (0 = none)
+std::atomic<uint64_t> g_const_tag{1};
 static thread_local std::string g_err;
 
 struct pyves_ctx {
@@ -49,12 +50,11 @@ struct pyves_ctx {
   bool l2_dev_mode = false;      // weights live on the device only: the host copy l2_w is stale
   void* l2_wt_dev = nullptr;     // transposed element-type copy wt[ky][kx] (source of the __constant__ upload)
   size_t l2_dev_count = 0;       // elements allocated in l2_w_dev / l2_wt_dev
-  uint64_t l2_version = 0;       // bumped by every device update
   bool l1_dev_mode = false;      // pyves_set_bias_legendre1d_device: l1_w (host) may be stale
   bool l1_host_stale = false;
   void* l1_wt_dev = nullptr;     // element-type copy, kMaxK1 entries
   double* l1_w64_dev = nullptr;  // FP64 copy (host refresh for the consumers that take weights by value)
-  uint64_t serial = 0;           // unique per handle (owner tag of the __constant__ weights)
+  uint64_t const_tag = 0;        // identifies the content of l1_wt_dev / l2_wt_dev for the __constant__ array's owner check
   std::map<void**, size_t> alloc_count;   // element counts of the buffers managed by upload()
   // MLP
   int mlp_axis = 0, mlp_act = 0;
@@ -293,6 +293,67 @@ int64_t basis_size(const pyves_ctx* h) {
   }
 }
 
+// ------------------------------------------------------------------- the __constant__ weight array
+// One array per device and process, shared by every handle in device mode.  `owner` is the content tag of the
+// coefficients it holds.  Launches and re-uploads may come from different streams, so the slot keeps
+// an event per reading stream and one for the last upload: an upload waits for every kernel that still reads the
+// old content (other streams only; the own stream is ordered anyway), a launch on another stream than the
+// upload's waits for the upload.  The mutex covers bind + launch + record, so handles driven from different host
+// threads cannot interleave between the upload and the launch that depends on it.
+constexpr int kMaxConstDevices = 64;
+struct ConstSlot {
+  std::mutex mu;
+  uint64_t owner = 0;
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t up_event = nullptr;
+  struct Reader {
+    cudaStream_t st;
+    cudaEvent_t ev;
+    bool pending;
+  };
+  std::vector<Reader> readers;
+};
+ConstSlot g_const[kMaxConstDevices];
+
+template <typename T, class Launch>
+int with_const_weights(pyves_ctx* h, const T* src, int count, cudaStream_t st, Launch&& launch) {
+  ConstSlot& S = g_const[h->device];
+  std::lock_guard<std::mutex> lock(S.mu);
+  const uint64_t tag = h->const_tag;
+  if (S.owner != tag) {
+    for (auto& r : S.readers) {
+      if (r.pending && r.st != st) CU(cudaStreamWaitEvent(st, r.ev, 0));
+      r.pending = false;
+    }
+    if (S.readers.size() > 64) {               // streams come and go: forget the idle ones
+      for (auto& r : S.readers) cudaEventDestroy(r.ev);
+      S.readers.clear();
+    }
+    S.owner = 0;
+    CU(upload_static_weights<T>(src, count, st));
+    if (!S.up_event) CU(cudaEventCreateWithFlags(&S.up_event, cudaEventDisableTiming));
+    CU(cudaEventRecord(S.up_event, st));
+    S.up_stream = st;
+    S.owner = tag;
+  } else if (S.up_stream != st) {
+    CU(cudaStreamWaitEvent(st, S.up_event, 0));
+  }
+  const int rc = launch();
+  if (rc) return rc;
+  ConstSlot::Reader* me = nullptr;
+  for (auto& r : S.readers)
+    if (r.st == st) me = &r;
+  if (!me) {
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    S.readers.push_back({st, ev, false});
+    me = &S.readers.back();
+  }
+  CU(cudaEventRecord(me->ev, st));
+  me->pending = true;
+  return PYVES_OK;
+}
+
 // ---------------------------------------------------------------------------------------- stepping
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 int run_fast(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP, cudaStream_t st) {
@@ -373,16 +434,13 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       return run_pair<T, GP, BiasNone<T>>(h, A, BP, st);
     }
     case PYVES_BIAS_LEGENDRE_1D: {
-      if (h->l1_dev_mode && h->variant != 1 && h->device < 64) {   // weights in the __constant__ array
-        const uint64_t tag = (h->serial << 32) | (h->l2_version & 0xffffffffull);
-        if (g_const_owner[h->device].load() != tag) {
-          CU(upload_static_weights<T>(static_cast<const T*>(h->l1_wt_dev), h->l1_degree + 1, st));
-          g_const_owner[h->device].store(tag);
-        }
+      if (h->l1_dev_mode && h->variant != 1 && h->device < kMaxConstDevices) {   // weights in the __constant__ array
         const Legendre1DParams<T> CP = l1_params<T>(h);            // centre / scale / axis / degree; weights unused
-        if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair_c<T, DW, BiasLegendre1D<T, 5, true>>(h, A, CP, st);
-        if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair_c<T, SL, BiasLegendre1D<T, 12, true>>(h, A, CP, st);
-        return run_pair_c<T, GP, BiasLegendre1D<T, 0, true>>(h, A, CP, st);
+        return with_const_weights<T>(h, static_cast<const T*>(h->l1_wt_dev), h->l1_degree + 1, st, [&]() {
+          if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair_c<T, DW, BiasLegendre1D<T, 5, true>>(h, A, CP, st);
+          if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair_c<T, SL, BiasLegendre1D<T, 12, true>>(h, A, CP, st);
+          return run_pair_c<T, GP, BiasLegendre1D<T, 0, true>>(h, A, CP, st);
+        });
       }
       { const int rc = refresh_l1_host(h); if (rc) return rc; }
       const Legendre1DParams<T> BP = l1_params<T>(h);
@@ -397,15 +455,12 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       // shared-memory column sweep is 19 % faster there (1.83e10 vs 1.54e10 walker-steps/s), so doubles skip it
       const bool static_ok = !(sizeof(T) == 8 && kx == 16 && ky == 16 && h->variant != 1);
       if (pk == PYVES_POT_DOUBLE_WELL_2D && h->variant != 2 && static_ok) {   // variant 2: runtime-size functor for tuning runs
-        if (h->l2_dev_mode && ((kx == 8 && ky == 8) || (kx == 16 && ky == 16)) && h->device < 64) {
+        if (h->l2_dev_mode && ((kx == 8 && ky == 8) || (kx == 16 && ky == 16)) && h->device < kMaxConstDevices) {
           // coefficients were set from a device pointer: the kernels read them from the __constant__ array
-          const uint64_t tag = (h->serial << 32) | (h->l2_version & 0xffffffffull);
-          if (g_const_owner[h->device].load() != tag) {
-            CU(upload_static_weights<T>(static_cast<const T*>(h->l2_wt_dev), kx * ky, st));
-            g_const_owner[h->device].store(tag);
-          }
-          if (kx == 8) return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8, true>, 2, 1>(h, A, l2_static_tc_params<T, 8, 8>(h), st);
-          return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, true, kHybrid16>, 1, 1>(h, A, l2_static_tc_params<T, 16, 16>(h), st);
+          return with_const_weights<T>(h, static_cast<const T*>(h->l2_wt_dev), kx * ky, st, [&]() {
+            if (kx == 8) return run_fast<T, DW, BiasLegendre2DStaticT<T, 8, 8, true>, 2, 1>(h, A, l2_static_tc_params<T, 8, 8>(h), st);
+            return run_fast<T, DW, BiasLegendre2DStaticT<T, 16, 16, true, kHybrid16>, 1, 1>(h, A, l2_static_tc_params<T, 16, 16>(h), st);
+          });
         }
         // variant 1 selects the row-major functor (kept for tuning runs); default = column sweep
         if (kx == 8 && ky == 8 && !h->l2_dev_mode) {
@@ -523,9 +578,6 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
   return PYVES_OK;
 }
 
-// Which handle's weights the __constant__ array of this process currently holds, per device
-// (handle serial << 32 | version); a launch in device mode re-copies its 1 KB when it is not the owner.
-
 template <typename T> static int set_l2_device(pyves_ctx* h, const double* w_dev, int kx, int ky, cudaStream_t st) {
   const size_t K = (size_t)kx * ky;
   if (h->l2_dev_count != K || !h->l2_w_dev || !h->l2_wt_dev) {
@@ -566,7 +618,6 @@ int pyves_create(pyves_t** out, int device, int64_t n_walkers, int dims, uint64_
   h = new (std::nothrow) pyves_ctx();
   if (!h) return fail(nullptr, PYVES_ENOMEM, "out of host memory");
   h->device = device;
-  h->serial = g_handle_serial.fetch_add(1);
   h->n = n_walkers;
   h->dims = dims;
   h->seed = seed;
@@ -752,7 +803,7 @@ int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double lo
   h->l1_hi = hi;
   h->l1_dev_mode = true;
   h->l1_host_stale = true;
-  h->l2_version++;               // shared version counter of the __constant__ owner tag
+  h->const_tag = g_const_tag.fetch_add(1);
   h->bias_kind = PYVES_BIAS_LEGENDRE_1D;
   return PYVES_OK;
 }
@@ -793,9 +844,56 @@ int pyves_set_bias_legendre2d_device(pyves_t* h, int deg_x, int deg_y, const dou
                                       : set_l2_device<float>(h, w_dev, deg_x + 1, deg_y + 1, st);
   if (rc) return rc;
   h->l2_dev_mode = true;
-  h->l2_version++;
+  h->const_tag = g_const_tag.fetch_add(1);
   h->l2_w.clear();               // no host copy in this mode
   h->bias_kind = PYVES_BIAS_LEGENDRE_2D;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_like(pyves_t* h, const pyves_t* leader, void* stream) {
+  if (!h || !leader) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (h == leader) return PYVES_OK;
+  if (h->device != leader->device || h->prec != leader->prec) return fail(h, PYVES_EINVAL, "set_bias_like: handles must share device and precision");
+  const bool l1 = leader->bias_kind == PYVES_BIAS_LEGENDRE_1D && leader->l1_dev_mode;
+  const bool l2 = leader->bias_kind == PYVES_BIAS_LEGENDRE_2D && leader->l2_dev_mode;
+  if (!l1 && !l2) return fail(h, PYVES_ESTATE, "set_bias_like: the leader's bias was not set by pyves_set_bias_legendre{1d,2d}_device");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (l1) {
+    if (!h->l1_wt_dev) {
+      CU(cudaMalloc(&h->l1_wt_dev, kMaxK1 * sizeof(double)));
+      CU(cudaMalloc(reinterpret_cast<void**>(&h->l1_w64_dev), kMaxK1 * sizeof(double)));
+    }
+    CU(cudaMemcpyAsync(h->l1_wt_dev, leader->l1_wt_dev, kMaxK1 * h->esz, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->l1_w64_dev, leader->l1_w64_dev, kMaxK1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    h->l1_axis = leader->l1_axis;
+    h->l1_degree = leader->l1_degree;
+    h->l1_lo = leader->l1_lo;
+    h->l1_hi = leader->l1_hi;
+    h->l1_dev_mode = true;
+    h->l1_host_stale = true;
+  } else {
+    const size_t K = (size_t)(leader->l2_dx + 1) * (leader->l2_dy + 1);
+    if (h->l2_dev_count != K || !h->l2_w_dev || !h->l2_wt_dev) {
+      if (h->l2_w_dev) cudaFree(h->l2_w_dev);
+      if (h->l2_wt_dev) cudaFree(h->l2_wt_dev);
+      h->l2_w_dev = h->l2_wt_dev = nullptr;
+      h->l2_dev_count = 0;
+      h->alloc_count.erase(&h->l2_w_dev);
+      CU(cudaMalloc(&h->l2_w_dev, K * h->esz));
+      CU(cudaMalloc(&h->l2_wt_dev, K * h->esz));
+      h->l2_dev_count = K;
+    }
+    CU(cudaMemcpyAsync(h->l2_w_dev, leader->l2_w_dev, K * h->esz, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->l2_wt_dev, leader->l2_wt_dev, K * h->esz, cudaMemcpyDeviceToDevice, st));
+    h->l2_dx = leader->l2_dx;
+    h->l2_dy = leader->l2_dy;
+    std::memcpy(h->l2_mm, leader->l2_mm, sizeof(h->l2_mm));
+    h->l2_dev_mode = true;
+    h->l2_w.clear();
+  }
+  h->const_tag = leader->const_tag;   // same content: a launch of either handle finds the __constant__ array up to date
+  h->bias_kind = leader->bias_kind;
   return PYVES_OK;
 }
 

@@ -597,3 +597,86 @@ def test_covariance_tensor_core_path(deg, sizes):
         e.set_tuning(97)
         assert np.max(np.abs(sff_cc.cpu().numpy() - sff_r) / scale) < 1e-5
         e.close()
+
+
+@pytest.mark.gpu
+def test_device_coefficients_on_concurrent_streams():
+    """Handles whose coefficients were set from device memory (pyves_set_bias_legendre{1d,2d}_device) share ONE
+    __constant__ weight array per device.  Independent handles with DIFFERENT coefficients, launched alternately on
+    different streams so that their kernels overlap in time, must each see their own weights (the re-copy waits
+    for the other stream's readers); a follower made with pyves_set_bias_like shares the leader's weights.  Every
+    run equals, bit for bit, the same handle fed from the host."""
+    import torch
+    kT = 8.31446261815324e-3 * 300
+    rng = np.random.default_rng(3)
+    n, stride, rounds = 300_000, 150, 3
+
+    def make(offset, count=n):
+        e = _lib.Ensemble(count, dims=2, seed=5, precision="fp32")
+        e.set_integrator(1.0, kT, 20.0, 0.01)
+        e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+        e.set_walker_offset(offset)
+        assert e.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1 / kT) == 0
+        e.init_velocities()
+        return e
+
+    for kind in ("2d", "1d"):
+        if kind == "2d":
+            ws = [rng.normal(size=(16, 16)) * 0.5 / (1 + np.add.outer(np.arange(16), np.arange(16))) for _ in range(2)]
+            set_host = lambda e, w: e.set_bias_legendre2d(15, 15, (-2.5, 2.5, -2.0, 2.0), w)
+            set_dev = lambda e, w: e.set_bias_legendre2d_device(15, 15, (-2.5, 2.5, -2.0, 2.0), w)
+        else:
+            ws = [rng.normal(size=6) * 2.0 for _ in range(2)]
+            set_host = lambda e, w: e.set_bias_legendre1d(0, 5, -2.5, 2.5, w)
+            set_dev = lambda e, w: e.set_bias_legendre1d_device(0, 5, -2.5, 2.5, w)
+        # reference: host-fed handles, one after the other
+        want = []
+        for k in range(2):
+            e = make(k * n)
+            set_host(e, ws[k])
+            for _ in range(rounds):
+                e.step(stride)
+            want.append(e.get_state(host=True))
+            e.close()
+        # two independent device-fed handles on their own streams, launches interleaved
+        hs = [make(k * n) for k in range(2)]
+        wd = [torch.tensor(w, dtype=torch.float64, device="cuda").contiguous() for w in ws]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        torch.cuda.synchronize()
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                set_dev(hs[k], wd[k])
+        for _ in range(rounds):
+            for k in range(2):
+                with torch.cuda.stream(streams[k]):
+                    hs[k].step(stride)
+        torch.cuda.synchronize()
+        for k in range(2):
+            x, v = hs[k].get_state(host=True)
+            assert np.array_equal(x, want[k][0]) and np.array_equal(v, want[k][1]), (kind, k)
+        # a follower of handle 0 on a third stream, interleaved with handle 1: same walkers as handle 0 had
+        f = make(0)
+        s3 = torch.cuda.Stream()
+        with torch.cuda.stream(s3):
+            f.set_bias_like(hs[0])
+        for _ in range(rounds):
+            with torch.cuda.stream(streams[1]):
+                hs[1].step(stride)
+            with torch.cuda.stream(s3):
+                f.step(stride)
+        torch.cuda.synchronize()
+        x, v = f.get_state(host=True)
+        assert np.array_equal(x, want[0][0]) and np.array_equal(v, want[0][1]), kind
+        for e in hs + [f]:
+            e.close()
+    # mismatched handles are refused
+    a = _lib.Ensemble(8, dims=2, seed=1, precision="fp32")
+    b = _lib.Ensemble(8, dims=2, seed=1, precision="fp64")
+    a.set_bias_legendre1d(0, 5, -2.5, 2.5, np.zeros(6))
+    with pytest.raises(Exception):
+        b.set_bias_like(a)           # precision differs
+    c = _lib.Ensemble(8, dims=2, seed=1, precision="fp32")
+    with pytest.raises(Exception):
+        c.set_bias_like(a)           # the leader's coefficients are host-fed
+    for e in (a, b, c):
+        e.close()
