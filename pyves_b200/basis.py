@@ -127,7 +127,7 @@ class LegendreBasis1D(_KernelModule):
     @classmethod
     def legendre_polynomial_expansion(cls, x, degree: int, weights: torch.Tensor) -> torch.Tensor:
         """sum_n w_n P_n(x) for x already in [-1, 1] (``ves/basis.py:86-121``, Bonnet recursion on the GPU)."""
-        m = cls(degree, -1.0, 1.0, weights=np.zeros(degree + 1))
+        m = LegendreBasis1D(degree, -1.0, 1.0, weights=np.zeros(degree + 1))
         out = _KernelBias.apply(m, m._prepare(x.reshape(-1, 1)), weights.to(torch.float64))
         return out.reshape(x.shape)
 
@@ -291,6 +291,10 @@ class LegendreBasis2DPathCV(_KernelModule):
             w = torch.rand(degree + 1, dtype=torch.float64)
         self.weights = nn.Parameter(w)
         self.phi = phi
+
+    # the reference class carries its own copies of the two Legendre helpers (``ves/basis.py:442-507``)
+    legendre_polynomial_expansion = LegendreBasis1D.__dict__['legendre_polynomial_expansion']
+    legendre_polynomial = LegendreBasis1D.__dict__['legendre_polynomial']
 
     def _kernel_params(self):
         return (self.weights,)

@@ -42,7 +42,11 @@ def test_reference_unit_tests_legendre_polynomials():
         bench = sum(weights[i] * basis.LegendreBasis1D.legendre_polynomial(x, i).cpu() for i in range(6))
         out = basis.LegendreBasis1D.legendre_polynomial_expansion(x, 5, weights).detach().cpu()
         assert np.allclose(bench.numpy(), out.numpy())
-        for degree in range(1, 5):                                    # test_basis.py:48-68
+        # the path-CV class carries the same two helpers upstream (ves/basis.py:442-507)
+        out2 = basis.LegendreBasis2DPathCV.legendre_polynomial_expansion(x, 5, weights).detach().cpu()
+        assert np.array_equal(out2.numpy(), out.numpy())
+        assert np.allclose(basis.LegendreBasis2DPathCV.legendre_polynomial(x, 3).cpu().numpy(), scipy_legendre(3)(x.cpu().numpy()))
+        for degree in range(1, 5):                                   # test_basis.py:48-68
             xg = torch.linspace(-1, 1, 1000, dtype=torch.float64, device=device, requires_grad=True)
             l = basis.LegendreBasis1D.legendre_polynomial(xg, degree)
             g = torch.autograd.grad(l, xg, grad_outputs=torch.ones_like(l))[0].cpu().numpy()
