@@ -233,4 +233,130 @@ template <int KX, int KY, int J0, bool TAIL = false> struct BiasLegendre2DStatic
   }
 };
 
+// Experiment: like StaticTH, but the shared-memory copy holds every weight TWICE (w, w), so the FFMA2s of the
+// shared-memory columns take a plain 64-bit register operand instead of a broadcast scalar (2 KB, two weights
+// per LDS.128).
+template <int KX, int KY, int J0> struct BiasLegendre2DStaticTHD {
+  using T = float;
+  using Params = Legendre2DStaticTHParams<KX, KY>;
+  static size_t smem_bytes(const Params&) { return sizeof(T) * KX * KY * 2; }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    T* d = reinterpret_cast<T*>(smem);
+    for (int i = threadIdx.x; i < KX * KY; i += blockDim.x) {
+      const T v = P.wdev[i];
+      d[2 * i] = v;
+      d[2 * i + 1] = v;
+    }
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    const T* ws = reinterpret_cast<const T*>(smem);
+    Pair<T> AB[KX];
+    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+    {
+      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
+#pragma unroll
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
+    }
+#pragma unroll
+    for (int j = 2; j < KY; ++j) {
+      const T pn = leg_a<T>(j - 1) * sy * p - leg_b<T>(j - 1) * pm;
+      const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
+      pm = p; p = pn; dpm = dp; dp = dpn;
+      const Pair<T> Q = Pair<T>::make(p, dp);
+      if (j < J0) {
+#pragma unroll
+        for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
+      } else {
+#pragma unroll
+        for (int iv = 0; iv < KX / 2; ++iv) {
+          unsigned long long w0, w1;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"((unsigned)__cvta_generic_to_shared(ws + 2 * (j * KX + iv * 2))));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AB[iv * 2].v) : "l"(Q.v), "l"(w0));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AB[iv * 2 + 1].v) : "l"(Q.v), "l"(w1));
+        }
+      }
+    }
+    Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));
+    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
+#pragma unroll
+    for (int i = 1; i < KX; ++i) {
+      if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G1);
+      else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G0);
+    }
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
+  }
+};
+
+// THD with an explicit software pipeline: loads and FFMA2s of the shared-memory columns are all `asm volatile`
+// (program order kept), the loads run DEPTH slots ahead of their use.
+template <int KX, int KY, int J0, int DEPTH> struct BiasLegendre2DStaticTHP {
+  using T = float;
+  using Params = Legendre2DStaticTHParams<KX, KY>;
+  static size_t smem_bytes(const Params&) { return sizeof(T) * KX * KY * 2; }
+  static PV_DEV void stage(const Params& P, void* smem) { BiasLegendre2DStaticTHD<KX, KY, J0>::stage(P, smem); }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    bool inx, iny;
+    const T sx = scale_clamp(x, P.cx, P.ihx, inx);
+    const T sy = scale_clamp(y, P.cy, P.ihy, iny);
+    const unsigned ws = (unsigned)__cvta_generic_to_shared(smem);
+    Pair<T> AB[KX];
+    T pm = T(1), p = sy, dpm = T(0), dp = T(1);
+    constexpr int HX = KX / 2, NL = (KY - J0) * HX;
+    unsigned long long buf[DEPTH][2];
+#pragma unroll
+    for (int l = 0; l < DEPTH; ++l)
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(buf[l][0]), "=l"(buf[l][1]) : "r"(ws + 8u * (unsigned)((J0 + l / HX) * KX + (l % HX) * 2)));
+    {
+      const Pair<T> Q1 = Pair<T>::make(sy, T(1));
+#pragma unroll
+      for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q1, P.wt[1 * KX + i], Pair<T>::make(P.wt[i], T(0)));
+    }
+#pragma unroll
+    for (int j = 2; j < KY; ++j) {
+      const T pn = leg_a<T>(j - 1) * sy * p - leg_b<T>(j - 1) * pm;
+      const T dpn = Math<T>::fma(leg_c<T>(j - 1), p, dpm);
+      pm = p; p = pn; dpm = dp; dp = dpn;
+      const Pair<T> Q = Pair<T>::make(p, dp);
+      if (j < J0) {
+#pragma unroll
+        for (int i = 0; i < KX; ++i) AB[i] = Pair<T>::fma_bcast(Q, P.wt[j * KX + i], AB[i]);
+      } else {
+#pragma unroll
+        for (int iv = 0; iv < HX; ++iv) {
+          const int l = (j - J0) * HX + iv;
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AB[iv * 2].v) : "l"(Q.v), "l"(buf[l % DEPTH][0]));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AB[iv * 2 + 1].v) : "l"(Q.v), "l"(buf[l % DEPTH][1]));
+          if (l + DEPTH < NL) {
+            const int ln = l + DEPTH;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(buf[l % DEPTH][0]), "=l"(buf[l % DEPTH][1]) : "r"(ws + 8u * (unsigned)((J0 + ln / HX) * KX + (ln % HX) * 2)));
+          }
+        }
+      }
+    }
+    Pair<T> G0 = Pair<T>::make(T(0), AB[0].hi()), G1 = Pair<T>::make(T(0), T(0));
+    T pxm = T(1), px = sx, dpxm = T(0), dpx = T(1);
+#pragma unroll
+    for (int i = 1; i < KX; ++i) {
+      if (i >= 2) {
+        const T pn = leg_a<T>(i - 1) * sx * px - leg_b<T>(i - 1) * pxm;
+        const T dpn = Math<T>::fma(leg_c<T>(i - 1), px, dpxm);
+        pxm = px; px = pn; dpxm = dpx; dpx = dpn;
+      }
+      if (i & 1) G1 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G1);
+      else G0 = Pair<T>::fma(Pair<T>::make(dpx, px), AB[i], G0);
+    }
+    gx += inx ? (G0.lo() + G1.lo()) * P.ihx : T(0);
+    gy += iny ? (G0.hi() + G1.hi()) * P.ihy : T(0);
+  }
+};
+
 }  // namespace pv

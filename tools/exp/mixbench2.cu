@@ -27,9 +27,14 @@ __device__ __forceinline__ void f2b(unsigned long long& acc, unsigned long long 
   asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(q), "l"(ww));
 }
 template <int SRC, int NQ> __global__ void __launch_bounds__(128) k(float* out, const W P, float a, int iters) {
-  __shared__ __align__(16) float sw[256];
-  for (int i = threadIdx.x; i < 256; i += 128) sw[i] = P.w[i];
+  __shared__ __align__(16) float sw[SRC == 2 ? 512 : 256];
+  if (SRC == 2) { for (int i = threadIdx.x; i < 256; i += 128) { sw[2 * i] = P.w[i]; sw[2 * i + 1] = P.w[i]; } }
+  else { for (int i = threadIdx.x; i < 256; i += 128) sw[i] = P.w[i]; }
   __syncthreads();
+  // SRC 3 / 4: loop-invariant weights in registers, as pairs (w, w) / as scalars broadcast by the FFMA2
+  unsigned long long WP[16];
+  float WS[16];
+  for (int i = 0; i < 16; ++i) { WS[i] = P.w[i] * a; asm("mov.b64 %0, {%1, %2};" : "=l"(WP[i]) : "f"(WS[i]), "f"(WS[i] + a)); }
   unsigned long long AB[16], Q[NQ];
   for (int i = 0; i < 16; ++i) AB[i] = i;
   for (int j = 0; j < NQ; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(Q[j]) : "f"(a + j), "f"(a * j));
@@ -39,6 +44,20 @@ template <int SRC, int NQ> __global__ void __launch_bounds__(128) k(float* out, 
       if (SRC == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) f2b(AB[i], Q[j % NQ], P.w[j * 16 + i]);
+      } else if (SRC == 3) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f2p(AB[i], Q[j % NQ], WP[i]);
+      } else if (SRC == 4) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f2b(AB[i], Q[j % NQ], WS[i]);
+      } else if (SRC == 2) {
+#pragma unroll
+        for (int iv = 0; iv < 8; ++iv) {
+          unsigned long long w0, w1;
+          const unsigned ad = (unsigned)__cvta_generic_to_shared(&sw[2 * (j * 16 + iv * 2)]);
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(ad));
+          f2p(AB[iv * 2 + 0], Q[j % NQ], w0); f2p(AB[iv * 2 + 1], Q[j % NQ], w1);
+        }
       } else {
 #pragma unroll
         for (int iv = 0; iv < 4; ++iv) {
@@ -93,6 +112,13 @@ template <int NQ> void runp(const char* name, int bps) {
   cudaFree(out);
 }
 int main() {
+  run<3, 16>("regs pair, 16 Q", 2);
+  run<4, 16>("regs bcast, 16 Q", 2);
+  run<3, 1>("regs pair, 1 Q", 2);
+  run<4, 1>("regs bcast, 1 Q", 2);
+  run<2, 16>("LDS.128 dup, 16 Q", 2);
+  run<2, 16>("LDS.128 dup, 16 Q", 4);
+  run<2, 1>("LDS.128 dup, 1 Q", 2);
   runp<16>("pair weights const, 16 Q", 2);
   runp<16>("pair weights const, 16 Q", 4);
   run<0, 16>("const-bank, 16 Q", 2);

@@ -90,6 +90,27 @@ int main(int argc, char** argv) {
   for (int k = 0; k < 256; ++k) R.wt[k] = Tt.wt[k];
   const char* only = argc > 3 ? argv[3] : nullptr;
   std::vector<float> ref, out;
+  if (only && std::string(only) == "thd") {   // duplicated shared-memory weights vs broadcast scalars
+    static Legendre2DStaticTHParams<16, 16> TH{};
+    TH.cx = 0; TH.ihx = 1 / 2.5f; TH.cy = 0; TH.ihy = 1 / 2.0f;
+    for (int k = 0; k < 256; ++k) TH.wt[k] = Tt.wt[k];
+    { float* wd; cudaMalloc(&wd, 1024); cudaMemcpy(wd, Tt.wt, 1024, cudaMemcpyHostToDevice); TH.wdev = wd; }
+    const int64_t nc = 4096;
+    std::vector<float> pc(2 * nc), vc(2 * nc), o2;
+    for (int64_t i = 0; i < nc; ++i) { pc[i] = p0[i]; pc[nc + i] = p0[n + i]; vc[i] = v0[i]; vc[nc + i] = v0[n + i]; }
+    run<BiasLegendre2DStaticTH<16, 16, 4>, 1, 1>("check TH4", TH, nc, 40, pc, vc, ref, 1);
+    run<BiasLegendre2DStaticTHD<16, 16, 4>, 1, 1>("check THD4", TH, nc, 40, pc, vc, o2, 1);
+    printf("max |dx| after 40 steps, THD vs TH: %.3e\n", maxdiff(ref, o2));
+    run<BiasLegendre2DStaticTH<16, 16, 4>, 1, 1>("TH J0=4", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTHD<16, 16, 4>, 1, 1>("THD J0=4", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTHP<16, 16, 4, 4>, 1, 1>("check THP4", TH, nc, 40, pc, vc, o2, 1);
+    printf("max |dx| after 40 steps, THP vs TH: %.3e\n", maxdiff(ref, o2));
+    run<BiasLegendre2DStaticTHP<16, 16, 4, 4>, 1, 1>("THP J0=4 D4", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTHP<16, 16, 4, 8>, 1, 1>("THP J0=4 D8", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTHP<16, 16, 2, 6>, 1, 1>("THP J0=2 D6", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTHP<16, 16, 6, 6>, 1, 1>("THP J0=6 D6", TH, n, steps, p0, v0, out, 3);
+    return 0;
+  }
   if (only) {
     std::string o(only);
 #ifdef ROLLED
