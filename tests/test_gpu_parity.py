@@ -667,7 +667,32 @@ def test_device_coefficients_on_concurrent_streams():
         torch.cuda.synchronize()
         x, v = f.get_state(host=True)
         assert np.array_equal(x, want[0][0]) and np.array_equal(v, want[0][1]), kind
-        for e in hs + [f]:
+        # the same two handles driven from two host threads (ctypes releases the GIL during the calls)
+        import threading
+        gs = [make(k * n) for k in range(2)]
+        errs = []
+
+        def drive(k):
+            try:
+                torch.cuda.set_device(0)
+                with torch.cuda.stream(streams[k]):
+                    set_dev(gs[k], wd[k])
+                    for _ in range(rounds):
+                        gs[k].step(stride)
+            except Exception as exc:       # noqa: BLE001
+                errs.append(exc)
+
+        ths = [threading.Thread(target=drive, args=(k,)) for k in range(2)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        assert not errs, errs
+        for k in range(2):
+            x, v = gs[k].get_state(host=True)
+            assert np.array_equal(x, want[k][0]) and np.array_equal(v, want[k][1]), (kind, "threads", k)
+        for e in hs + gs + [f]:
             e.close()
     # mismatched handles are refused
     a = _lib.Ensemble(8, dims=2, seed=1, precision="fp32")
