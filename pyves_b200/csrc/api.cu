@@ -1104,10 +1104,22 @@ int pyves_step_record(pyves_t* h, int64_t nsteps, int64_t every, int64_t n_rec, 
   if (nsteps == 0) return PYVES_OK;
   DeviceGuard g(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int rc = h->prec == PYVES_F64 ? do_step<double>(h, nsteps, injected_noise, traj_out, every, n_rec, st)
-                                      : do_step<float>(h, nsteps, injected_noise, traj_out, every, n_rec, st);
-  if (rc == PYVES_OK) h->step += nsteps;
-  return rc;
+  // Philox launches are cut at multiples of 2^33 steps: PhiloxSeq (philox.cuh) keeps the upper word of the call
+  // index fixed within a launch
+  int64_t left = nsteps;
+  while (left > 0) {
+    int64_t chunk = left;
+    if (!injected_noise && !traj_out) {
+      const int64_t boundary = ((h->step >> 33) + 1) << 33;
+      if (boundary - h->step < chunk) chunk = boundary - h->step;
+    }
+    const int rc = h->prec == PYVES_F64 ? do_step<double>(h, chunk, injected_noise, traj_out, every, n_rec, st)
+                                        : do_step<float>(h, chunk, injected_noise, traj_out, every, n_rec, st);
+    if (rc != PYVES_OK) return rc;
+    h->step += chunk;
+    left -= chunk;
+  }
+  return PYVES_OK;
 }
 
 int pyves_step(pyves_t* h, int64_t nsteps, const void* injected_noise, void* stream) {

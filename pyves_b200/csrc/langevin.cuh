@@ -76,6 +76,13 @@ langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotPar
     x[k] = Math<T>::fma(I.dt, vx[k], x[k]);
     y[k] = Math<T>::fma(I.dt, vy[k], y[k]);
   };
+  // the heavy one-walker kernels sit at the register limit: they keep the plain call (Philox is < 5 % there)
+  constexpr bool kSeq = WPT >= 2;
+  PhiloxSeq SQ[WPT];
+  if (!INJECT && kSeq) {
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) SQ[k].init(A.gid0 + (uint64_t)w[k], (uint64_t)(A.step0 >> 1), kStreamDyn2, K);
+  }
   // noise of steps 2c and 2c+1 for walker k
   auto draw = [&](int k, int64_t t_even, T (&z)[4]) {
     if (INJECT) {
@@ -85,7 +92,8 @@ langevin2d_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const PotPar
         z[q] = (ts >= 0 && ts < A.nsteps) ? A.noise[(ts * 2 + (q & 1)) * A.n + w[k]] : T(0);
       }
     } else {
-      const uint4 r = philox_call(A.gid0 + (uint64_t)w[k], (uint64_t)(t_even >> 1), kStreamDyn2, K);
+      // call t_even / 2; the calls of a launch are consecutive, which the light kernels exploit (PhiloxSeq)
+      const uint4 r = kSeq ? SQ[k].next(K) : philox_call(A.gid0 + (uint64_t)w[k], (uint64_t)(t_even >> 1), kStreamDyn2, K);
       box_muller(r.x, r.y, z[0], z[1]);
       box_muller(r.z, r.w, z[2], z[3]);
     }
@@ -203,6 +211,11 @@ langevin2d_pair_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const P
     X = Q::fma_bcast(VX, I.dt, X);
     Y = Q::fma_bcast(VY, I.dt, Y);
   };
+  PhiloxSeq SA, SB;
+  if (!INJECT) {
+    SA.init(A.gid0 + (uint64_t)w[0], (uint64_t)(A.step0 >> 1), kStreamDyn2, K);
+    SB.init(A.gid0 + (uint64_t)w[1], (uint64_t)(A.step0 >> 1), kStreamDyn2, K);
+  }
   // noise of steps 2c and 2c+1 for both walkers: Z[0], Z[1] = (zx, zy) of the even step, Z[2], Z[3] of the odd one
   auto draw = [&](int64_t t_even, Q (&Z)[4]) {
     if (INJECT) {
@@ -213,8 +226,8 @@ langevin2d_pair_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const P
         Z[q] = Q::make(ok ? A.noise[(ts * 2 + (q & 1)) * A.n + w[0]] : T(0), ok ? A.noise[(ts * 2 + (q & 1)) * A.n + w[1]] : T(0));
       }
     } else {
-      const uint4 ra = philox_call(A.gid0 + (uint64_t)w[0], (uint64_t)(t_even >> 1), kStreamDyn2, K);
-      const uint4 rb = philox_call(A.gid0 + (uint64_t)w[1], (uint64_t)(t_even >> 1), kStreamDyn2, K);
+      const uint4 ra = SA.next(K);     // call t_even / 2: the calls of a launch are consecutive
+      const uint4 rb = SB.next(K);
       box_muller_pair<T>(ra.x, ra.y, rb.x, rb.y, Z[0], Z[1]);
       box_muller_pair<T>(ra.z, ra.w, rb.z, rb.w, Z[2], Z[3]);
     }

@@ -51,6 +51,55 @@ PV_DEV uint4 philox_call(uint64_t gid, uint64_t call, uint32_t stream, const Rng
                        ((uint32_t)(call >> 32) & 0xFFFFFFu) | (stream << 24), K);
 }
 
+// Consecutive calls of one walker (the dynamics stream: call index = step / 2).  Same output as philox_call,
+// with the work that does not change from call to call taken out of the loop: in round 1, M0 * gid_lo is
+// constant and M1 * call_lo grows by M1 per call (a 64-bit add); its other output word, and so M1 * c2 of
+// round 2, are constant as well.  17 wide multiplies per call instead of 20 (they hold the FMA pipe for
+// 4 cycles each and bound the light kernels).  Valid while the upper 32 bits of the call index do not
+// change: the host cuts launches at multiples of 2^33 steps (api.cu).
+struct PhiloxSeq {
+  uint32_t c1;        // gid_hi
+  uint32_t lo0;       // low word of M0 * gid_lo  (c3 of round 2)
+  uint32_t p1b_lo, p1b_hi;   // M1 * c2 of round 2
+  uint64_t p1;        // M1 * call_lo of the next call
+  PV_DEV void init(uint64_t gid, uint64_t call, uint32_t stream, const RngKeys& K) {
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * (uint32_t)gid;
+    const uint32_t c3 = ((uint32_t)(call >> 32) & 0xFFFFFFu) | (stream << 24);
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[0];
+    const uint64_t p1b = (uint64_t)kPhiloxM1 * n2;
+    c1 = (uint32_t)(gid >> 32);
+    lo0 = (uint32_t)p0;
+    p1b_lo = (uint32_t)p1b;
+    p1b_hi = (uint32_t)(p1b >> 32);
+    p1 = (uint64_t)kPhiloxM1 * (uint32_t)call;
+  }
+  PV_DEV uint4 next(const RngKeys& K) {
+    // round 1
+    uint32_t c0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[0];
+    uint32_t d1 = (uint32_t)p1;
+    p1 += kPhiloxM1;
+    // round 2: only M0 * c0 is new
+    const uint64_t q0 = (uint64_t)kPhiloxM0 * c0;
+    uint32_t n0 = p1b_hi ^ d1 ^ K.k0[1];
+    uint32_t c2 = (uint32_t)(q0 >> 32) ^ lo0 ^ K.k1[1];
+    d1 = p1b_lo;
+    uint32_t c3 = (uint32_t)q0;
+    c0 = n0;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+      const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+      const uint64_t pp = (uint64_t)kPhiloxM1 * c2;
+      n0 = (uint32_t)(pp >> 32) ^ d1 ^ K.k0[r];
+      const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
+      d1 = (uint32_t)pp;
+      c3 = (uint32_t)p0;
+      c0 = n0;
+      c2 = n2;
+    }
+    return make_uint4(c0, d1, c2, c3);
+  }
+};
+
 // (r + 0.5) 2^-32 in (0, 1]
 PV_DEV float uniform01(uint32_t r, float) { return fmaf(__uint2float_rn(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 PV_DEV double uniform01(uint32_t r, double) { return ((double)r + 0.5) * 2.3283064365386963e-10; }
