@@ -705,3 +705,49 @@ def test_device_coefficients_on_concurrent_streams():
         c.set_bias_like(a)           # the leader's coefficients are host-fed
     for e in (a, b, c):
         e.close()
+
+
+@pytest.mark.gpu
+def test_philox_sequence_across_call_index_word():
+    """The light kernels advance Philox incrementally within a launch (PhiloxSeq), valid while the upper word of
+    the call index (step / 2) is fixed; the library cuts launches at multiples of 2^33 steps.  One launch across
+    that boundary equals single-step launches (each of which starts from its own counter), bit for bit, and the
+    oracle's noise for those steps."""
+    kT = 8.31446261815324e-3 * 300
+    n, before, after = 1000, 7, 8
+    start = (1 << 33) - before
+    w = np.linspace(-1.0, 1.0, 6)
+    runs = []
+    for mode in ("one_launch", "single_steps"):
+        e = _lib.Ensemble(n, dims=2, seed=99, precision="fp32")
+        e.set_integrator(1.0, kT, 20.0, 0.01)
+        e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+        e.set_bias_legendre1d(0, 5, -2.5, 2.5, w)
+        assert e.init_positions_mc((-2.5, 2.5, -2.0, 2.0), 1 / kT) == 0
+        e.init_velocities()
+        e.step_counter = start
+        if mode == "one_launch":
+            e.step(before + after)
+        else:
+            for _ in range(before + after):
+                e.step(1)
+        assert e.step_counter == start + before + after
+        runs.append(e.get_state(host=True))
+        e.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    # and against the oracle's Philox stream for the same steps (FP64 handle; the call index crosses 2^32)
+    rng = np.random.default_rng(2)
+    spec = dict(kind="leg1d", axis='x', degree=5, min=-2.5, max=2.5, weights=w)
+    k = langevin.constants()
+    m = 64
+    x0 = np.stack([rng.uniform(-1.6, 1.5, m), rng.uniform(-0.3, 0.3, m)], 1)
+    v0 = rng.standard_normal((m, 2)) * k["sigma_v"]
+    xr, vr = langevin.run_philox(x0, v0, biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec), k, 99, 3, start, before + after)
+    e = biasspec.make_ensemble(m, 2, 99, "fp64", potentials.DOUBLE_WELL_2D, None, spec)
+    e.set_walker_offset(3)
+    e.set_state(torch.tensor(x0.T.copy(), dtype=torch.float64, device=DEV), torch.tensor(v0.T.copy(), dtype=torch.float64, device=DEV))
+    e.step_counter = start
+    e.step(before + after)
+    xg, vg = e.get_state(host=True)
+    e.close()
+    assert rel_err(xg.T, xr) < 1e-9 and rel_err(vg.T, vr) < 1e-9
