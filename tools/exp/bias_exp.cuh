@@ -177,7 +177,7 @@ template <int KX, int KY> struct Legendre2DStaticTHParams {
   float wt[KY * KX];        // constant-bank copy
   const float* wdev;        // device copy of the same transposed weights (staged into shared memory)
 };
-template <int KX, int KY, int J0, bool TAIL = false> struct BiasLegendre2DStaticTH {
+template <int KX, int KY, int J0, bool TAIL = false, bool NV = false> struct BiasLegendre2DStaticTH {
   using T = float;
   using Params = Legendre2DStaticTHParams<KX, KY>;
   static size_t smem_bytes(const Params&) { return sizeof(T) * KX * KY; }
@@ -210,7 +210,12 @@ template <int KX, int KY, int J0, bool TAIL = false> struct BiasLegendre2DStatic
 #pragma unroll
         for (int iv = 0; iv < KX / 4; ++iv) {
           T w[4];
-          lds_vec(ws + j * KX + iv * 4, w);
+          if (NV) {   // plain loads: the compiler may keep the weights in registers across the time loop
+            const float4 v = *reinterpret_cast<const float4*>(ws + j * KX + iv * 4);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+          } else {
+            lds_vec(ws + j * KX + iv * 4, w);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) Pair<T>::acc_bcast(AB[iv * 4 + q], Q, w[q]);
         }

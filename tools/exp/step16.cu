@@ -102,6 +102,12 @@ int main(int argc, char** argv) {
     run<BiasLegendre2DStaticTHD<16, 16, 4>, 1, 1>("check THD4", TH, nc, 40, pc, vc, o2, 1);
     printf("max |dx| after 40 steps, THD vs TH: %.3e\n", maxdiff(ref, o2));
     run<BiasLegendre2DStaticTH<16, 16, 4>, 1, 1>("TH J0=4", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTH<16, 16, 4, false, true>, 1, 1>("check TH4 nonvolatile", TH, nc, 40, pc, vc, o2, 1);
+    printf("max |dx| after 40 steps, TH nonvolatile vs TH: %.3e\n", maxdiff(ref, o2));
+    run<BiasLegendre2DStaticTH<16, 16, 4, false, true>, 1, 1>("TH J0=4 nonvolatile", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTH<16, 16, 5, false, true>, 1, 1>("TH J0=5 nonvolatile", TH, n, steps, p0, v0, out, 3);
+    run<BiasLegendre2DStaticTH<16, 16, 6, false, true>, 1, 1>("TH J0=6 nonvolatile", TH, n, steps, p0, v0, out, 3);
+    if (argc > 4) return 0;
     run<BiasLegendre2DStaticTHD<16, 16, 4>, 1, 1>("THD J0=4", TH, n, steps, p0, v0, out, 3);
     run<BiasLegendre2DStaticTHP<16, 16, 4, 4>, 1, 1>("check THP4", TH, nc, 40, pc, vc, o2, 1);
     printf("max |dx| after 40 steps, THP vs TH: %.3e\n", maxdiff(ref, o2));
