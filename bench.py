@@ -321,6 +321,17 @@ def run_ours(args):
                     "traffic": 16.04e6 * args.walkers / 1e6 if args.basis == 16 else None,
                     "traffic_note": "dram__bytes_read + dram__bytes_write per launch, ncu --set full capture "
                                     "profiles/r01b_ncu_step_kernel.md (16 B of state per walker; the 16 MB written back stay in L2)"}
+            # the HBM view of the same kernel, against the driver-measured copy bandwidth: why "hbm" is not the bound
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
+                    hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json"
+            except (OSError, KeyError, ValueError):
+                pass
+            alg_bytes = 32.0 * args.walkers                       # state read + written once per launch, 16 B each way per walker
+            hbm_gbs = alg_bytes / (kern_ms * 1e-3) * 1e-9
+            roof["hbm"] = {"algorithmic_bytes_per_launch": alg_bytes, "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}
         out = {"metric": "walker-steps/s (2D double well, Legendre bias)", "value": value, "unit": "walker-steps/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
