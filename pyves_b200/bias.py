@@ -463,7 +463,10 @@ class DeviceUpdater:
             self._refreshed_density()       # result discarded: loads the kernels of the refresh path (CUDA loads lazily)
 
     def add_handle(self, ens):
-        """Another ensemble handle on the same device (a shard processed on its own stream) that shares the bias."""
+        """Another ensemble handle on the same device (a shard processed on its own stream) that shares the bias.
+        ``update`` hands the new coefficients to every handle on the stream it is called on; a shard stepped on
+        another stream must wait for that stream first (``shard_stream.wait_stream(update_stream)``, as bench.py's
+        chunked end-to-end loop does)."""
         ens.set_moment_domain(self.bias.sample_domain == 'box')
         self._upload(ens)
         self.handles.append(ens)
