@@ -310,3 +310,20 @@ def test_two_rank_moment_reduction_gloo(tmp_path):
     ref = optim.AveragedSGD(np.zeros(16), 0.5, second_order=True, averaging='running').step(g, h)
     r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(r0, r1) and np.allclose(r0, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_histogram_fes_semantics():
+    """ves/visualization.py:475-478: empty bins take the smallest non-zero count, beta F = -log counts, shifted to
+    min 0; rmse_kt compares min-shifted profiles where the reference is below the clip."""
+    from pyves_b200 import fes
+    c = np.array([0.0, 4.0, 16.0, 0.0, 2.0])
+    bF = fes.counts_to_fes(c)
+    assert np.allclose(bF, -np.log([2.0, 4.0, 16.0, 2.0, 2.0]) + np.log(16.0))
+    assert bF.min() == 0.0 and c[0] == 0.0                     # the input is not modified
+    with pytest.raises(ValueError):
+        fes.counts_to_fes(np.zeros(4))
+    ref = np.array([0.0, 1.0, 5.0, 30.0])
+    est = ref + 7.0                                             # a constant offset is not an error
+    est[3] = 0.0                                                # ... and bins above the clip are ignored
+    assert fes.rmse_kt(est, ref, clip=20.0) < 1e-12
+    assert abs(fes.rmse_kt(ref + np.array([0.0, 0.3, 0.0, 0.0]), ref, clip=20.0) - 0.3 / np.sqrt(3)) < 1e-12
