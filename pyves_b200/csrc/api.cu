@@ -373,10 +373,12 @@ int run_pair(pyves_ctx* h, const StepArgs<T>& A, const typename Bias::Params& BP
 // Device-mode 1D weights reach the pair kernels through the __constant__ array; every other consumer takes the
 // weights by value from the host copy, which is refreshed here (synchronous, rare: eval_bias / energies /
 // general kernel on a handle whose coefficients were set from the device).
-int refresh_l1_host(pyves_ctx* h) {
+int refresh_l1_host(pyves_ctx* h, cudaStream_t st) {
   if (!h->l1_dev_mode || !h->l1_host_stale) return PYVES_OK;
   double tmp[kMaxK1];
-  CU(cudaMemcpy(tmp, h->l1_w64_dev, (size_t)(h->l1_degree + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  // on the caller's stream: the conversion that filled l1_w64_dev was enqueued there (or on a stream it waits for)
+  CU(cudaMemcpyAsync(tmp, h->l1_w64_dev, (size_t)(h->l1_degree + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   std::memset(h->l1_w, 0, sizeof(h->l1_w));
   for (int i = 0; i <= h->l1_degree; ++i) h->l1_w[i] = tmp[i];
   h->l1_host_stale = false;
@@ -395,7 +397,7 @@ template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaSt
     for (int w : h->mlp_sizes)
       if (w > kGenH) return fail(h, PYVES_EUNSUPPORTED, "MLP hidden width > 128 is not supported");
   }
-  { const int rc = refresh_l1_host(h); if (rc) return rc; }
+  { const int rc = refresh_l1_host(h, st); if (rc) return rc; }
   if (h->dims == 2) {
     CU((launch_langevin_general<T, 2>(A, integrator_params<T>(h), pot_params<T>(h), any_params<T>(h), make_keys(h->seed), st)));
   } else {
@@ -442,7 +444,7 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
           return run_pair_c<T, GP, BiasLegendre1D<T, 0, true>>(h, A, CP, st);
         });
       }
-      { const int rc = refresh_l1_host(h); if (rc) return rc; }
+      { const int rc = refresh_l1_host(h, st); if (rc) return rc; }
       const Legendre1DParams<T> BP = l1_params<T>(h);
       if (pk == PYVES_POT_DOUBLE_WELL_2D && h->l1_degree == 5) return run_pair<T, DW, BiasLegendre1D<T, 5>>(h, A, BP, st);
       if (pk == PYVES_POT_SLIP_BOND_2D && h->l1_degree == 12) return run_pair<T, SL, BiasLegendre1D<T, 12>>(h, A, BP, st);
@@ -1147,7 +1149,7 @@ int pyves_eval_bias(pyves_t* h, const void* pos, int64_t n, int ncols, void* E, 
     dF = F ? base + pb : nullptr;
     dE = E ? base + 2 * pb : nullptr;
   }
-  { const int rc = refresh_l1_host(h); if (rc) return rc; }
+  { const int rc = refresh_l1_host(h, st); if (rc) return rc; }
   if (h->prec == PYVES_F64) {
     CU(launch_eval_bias<double>(static_cast<const double*>(dpos), n, ncols, static_cast<double*>(dE), static_cast<double*>(dF), any_params<double>(h), st));
   } else {
@@ -1175,7 +1177,7 @@ int pyves_energies(pyves_t* h, void* PE, void* KE, int on_host, void* stream) {
     dPE = PE ? h->stage : nullptr;
     dKE = KE ? static_cast<char*>(h->stage) + eb : nullptr;
   }
-  { const int rc = refresh_l1_host(h); if (rc) return rc; }
+  { const int rc = refresh_l1_host(h, st); if (rc) return rc; }
   if (h->prec == PYVES_F64) {
     CU(launch_energies<double>(static_cast<const double*>(h->pos), static_cast<const double*>(h->vel), h->n, h->dims, static_cast<double*>(dPE), static_cast<double*>(dKE), h->mass, h->dt, pot_params<double>(h), any_params<double>(h), st));
   } else {
