@@ -13,7 +13,15 @@ reduction + the coefficient update + the bias re-upload.  ``value`` is measured 
 resident in HBM; ``e2e`` drives the same iteration through the C ABI with HOST buffers (state uploaded
 from pinned memory and read back every iteration).  ``--impl reference`` times the CPU
 implementation of the same path (the oracle's OpenMP C port: the reference itself is Python + OpenMM,
-and OpenMM is absent from this image) on the host cores.
+and OpenMM is absent from this image) on the host cores, on the same workload: in-box averages, well-tempered refresh
+every 10 updates, preconditioned averaged SGD.
+
+Besides the headline the JSON line carries ``configs``: short legs of the other BASELINE.json configurations run in
+the same process (cfg1 static LegendreBasis1D(5), cfg3 slip bond + second-order update at 10^7 walkers in total
+= strong scaling over the ranks, cfg4 NN bias with the device-resident Adam loop, cfg5 K x K bases for K = 8 / 32 /
+64 and a 64 x 64 strong-scaling point), each with ``value``, ``kernel``, ``kernel_ms`` and ``roofline.frac``; and
+``comm_ms``, the time of the one all-reduce per update (CUDA events, max over ranks).  ``--scaling strong`` makes
+the HEADLINE itself a strong-scaling run (``--walkers-total`` walkers sharded over the ranks).
 """
 import argparse
 import json
@@ -56,7 +64,16 @@ def parse_args():
                          "host<->device copies of one chunk overlap the step kernel of another (1 = one handle, serial copies)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configurations")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --walkers per GPU (default); strong: --walkers-total sharded over the ranks")
+    ap.add_argument("--walkers-total", type=int, default=10000000, help="ensemble size of --scaling strong")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: wall-clock budget (s) of the whole run")
+    a = ap.parse_args()
+    if a.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", 1))
+        a.walkers = a.walkers_total // world
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -132,6 +149,14 @@ def make_ensemble(args, rank, device):
     return ens
 
 
+def peak_all(_lib, local, rank, world, dev):
+    """FP32 FMA peak of rank 0's GPU for the legs' roofline (measured once, before the timed region; see run_ours)."""
+    return _PEAK.get("tflops")
+
+
+_PEAK = {}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -154,7 +179,7 @@ def run_ours(args):
     K = args.basis * args.basis
     n_total = args.walkers * world
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    step_events = []
+    step_events, comm_events = [], []
 
     def barrier():
         if world > 1:
@@ -175,7 +200,14 @@ def run_ours(args):
         if upd is not None:
             bufs = upd.moment_buffers(False)
             ens.moments(out=bufs)                                # 1 + K doubles into the updater's flat buffer
-            upd.reduce_flat()                                    # one NCCL all-reduce, in place
+            if timed and world > 1:
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                upd.reduce_flat()                                # one NCCL all-reduce, in place
+                c1.record()
+                comm_events.append((c0, c1))
+            else:
+                upd.reduce_flat()
             upd.update(*bufs)                                    # optimiser kernel + target + coefficient hand-over, all enqueued
         else:
             sw, sf, _ = reduce_moments(*ens.moments())           # one NCCL allreduce of 1 + K doubles
@@ -183,6 +215,7 @@ def run_ours(args):
             bias.force.apply(ens)                                # re-upload the coefficients
 
     peak = _lib.fp32_fma_peak(local) if rank == 0 else None     # before the timed region
+    _PEAK["tflops"] = peak
     for _ in range(args.warmup):
         iteration(False)
     torch.cuda.synchronize()
@@ -205,6 +238,12 @@ def run_ours(args):
     elapsed = float(elapsed)
     value = n_total * args.stride * args.steps / elapsed
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
+    # the one collective per update: CUDA events around the all-reduce on the launching stream (includes the wait for the
+    # slowest rank's moments, i.e. the skew), mean per iteration, MAX over ranks
+    comm = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in comm_events])) if comm_events else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(comm, op=dist.ReduceOp.MAX)
+    comm_ms = float(comm)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     # every iteration: walker state from pinned host memory -> GPU, the VES iteration, then the result (the 1 + K
@@ -233,16 +272,18 @@ def run_ours(args):
                 subs.append(e)
                 hp.append(torch.from_numpy(np.ascontiguousarray(hpos[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
                 hv.append(torch.from_numpy(np.ascontiguousarray(hvel[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
+            # per-chunk moment buffers allocated ONCE on the main stream and written through out=: no tensor allocated on a
+            # side stream is consumed on the main stream (the caching allocator could hand such a block out again too early)
+            mom = [(torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(K, dtype=torch.float64, device=dev), None) for _ in range(nch)]
 
         def e2e_chunked():
             main = torch.cuda.current_stream(dev)
-            mom = []
             for c in range(nch):
                 streams[c].wait_stream(main)                     # the coefficient hand-over was enqueued on the main stream
                 with torch.cuda.stream(streams[c]):
                     subs[c].set_state(hp[c], hv[c], async_copy=True)          # H2D of this chunk's inputs
                     subs[c].step(args.stride)
-                    mom.append(subs[c].moments())
+                    subs[c].moments(out=mom[c])
                     subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)    # D2H of this chunk's walkers
             for c in range(nch):
                 main.wait_stream(streams[c])
@@ -296,6 +337,13 @@ def run_ours(args):
         upd.close()
         bias.force.apply(ens)
 
+    # ---- the other BASELINE.json configurations, short legs (all ranks take part)
+    legs = None
+    if not args.no_configs:
+        legs = config_legs(args, rank, world, local, dev, peak_all(_lib, local, rank, world, dev))
+        if rank == 0 and world == 1:
+            legs["cfg0_single_walker"] = single_walker_rate(local, args.seed)
+
     # ---- accuracy: continue the optimisation (untimed) and compare the FES with the analytic surface
     fes_out = None
     if args.fes_updates > 0:
@@ -318,9 +366,7 @@ def run_ours(args):
                     "peak_source": "FFMA micro-benchmark run in this process (pyves_fp32_fma_peak); nominal 74.4",
                     "flops_per_walker_step": flops, "kernel_ms": kern_ms,
                     "kernel_share_of_step": kern_ms * args.steps / (elapsed * 1e3),
-                    "traffic": 16.04e6 * args.walkers / 1e6 if args.basis == 16 else None,
-                    "traffic_note": "dram__bytes_read + dram__bytes_write per launch, ncu --set full capture "
-                                    "profiles/r01b_ncu_step_kernel.md (16 B of state per walker; the 16 MB written back stay in L2)"}
+                    **ncu_traffic(args)}
             # the HBM view of the same kernel, against the driver-measured copy bandwidth: why "hbm" is not the bound
             hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
             try:
@@ -334,14 +380,16 @@ def run_ours(args):
                            "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}
         out = {"metric": "walker-steps/s (2D double well, Legendre bias)", "value": value, "unit": "walker-steps/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "configs[1]: 2D double well, %dx%d tensor Legendre bias, well-tempered target "
-                                      "(gamma 10, 100x100), averaged SGD update every %d steps, %d walkers per GPU"
-                                      % (args.basis, args.basis, args.stride, args.walkers),
+               "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_string(args),
                           "walkers_total": n_total, "md_steps_per_bench_step": args.stride, "parallelism": "walkers sharded, dp%d" % world,
                           "l2": "flushed between steps (256 MiB memset); state 16 MB/GPU is read once per 500 MD steps",
                           "update": args.update},
-               "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "comm_ms": comm_ms,
+               "comm_note": "one all-reduce of %d doubles per update; CUDA events around it on the launching stream (includes the wait for "
+                            "the slowest rank), mean per iteration, max over ranks" % (K + 1)}
+        if legs:
+            out["configs"] = legs
         if e2e:
             out["e2e"] = e2e
         if fes_out:
@@ -351,6 +399,170 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Legs of the other BASELINE.json configurations (same process, after the headline's timed region).  Every leg is a few
+# VES iterations of that configuration through the same C ABI; `value` is whole-job walker-steps/s of the full iteration
+# (MD steps + moments + all-reduce + update), `kernel_ms` the mean step-kernel launch (CUDA events), `roofline.frac` that
+# kernel's algorithmic flops against the FP32 FMA peak measured in this process.
+LEG_FLOPS = {"cfg1": 70, "cfg3": 133, "cfg4": 9635, 8: 404, 16: 1300, 32: 4628, 64: 17428}
+
+
+def _leg_ensemble(n, gid0, pot_kind, pot_params, box, local, seed, ntrials=2000):
+    from pyves_b200 import _lib
+    e = _lib.Ensemble(n, dims=2, seed=seed, precision="fp32", device=local)
+    e.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
+    e.set_potential(pot_kind, pot_params)
+    e.set_walker_offset(gid0)
+    assert e.init_positions_mc(box, 1.0 / (KB_PY * TEMP), ntrials=ntrials) == 0
+    e.init_velocities()
+    return e
+
+
+def _leg_time(torch, dist, world, dev, ens, stride, iters, warm, update):
+    """(seconds per iteration MAX over ranks, mean step-kernel ms) of `iters` iterations: ens.step(stride); update()."""
+    for _ in range(warm):
+        ens.step(stride)
+        update()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ens.step(stride)
+        b.record()
+        ev.append((a, b))
+        update()
+    t1.record()
+    torch.cuda.synchronize()
+    el = torch.tensor([t0.elapsed_time(t1) * 1e-3 / iters], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    return float(el), float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def config_legs(args, rank, world, local, dev, peak):
+    import torch
+    import torch.distributed as dist
+    from pyves_b200 import _lib, basis, bias, target
+    from pyves_b200.bias import DeviceUpdater
+    from pyves_b200.parallel import shard
+    beta = 1.0 / (KB_PY * TEMP)
+    out = {}
+
+    def row(name, workload, n_rank, n_total, stride, sec, kern_ms, kernel, flops, scaling, extra=None):
+        r = {"workload": workload, "walkers_total": int(n_total), "md_steps_per_iteration": stride, "scaling": scaling,
+             "value": n_total * stride / sec, "unit": "walker-steps/s", "ms_per_iteration": sec * 1e3, "kernel": kernel, "kernel_ms": kern_ms}
+        if peak and flops:
+            ach = n_rank * stride * flops / (kern_ms * 1e-3) * 1e-12
+            r["roofline"] = {"bound": "fp32-fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "flops_per_walker_step": flops}
+        if extra:
+            r.update(extra)
+        out[name] = r
+
+    def updater_leg(name, workload, make_bias, pot_kind, pot_params, box, n_rank, gid0, n_total, stride, iters, kernel, flops, scaling, cov=False):
+        b = make_bias()
+        e = _leg_ensemble(n_rank, gid0, pot_kind, pot_params, box, local, args.seed)
+        upd = DeviceUpdater(b, e)
+
+        def update():
+            bufs = upd.moment_buffers(cov)
+            e.moments(cov=cov, out=bufs)
+            upd.reduce_flat()
+            upd.update(*bufs)
+        sec, kms = _leg_time(torch, dist, world, dev, e, stride, iters, 1, update)
+        row(name, workload, n_rank, n_total, stride, sec, kms, kernel, flops, scaling, {"update": "device-resident (%s)" % b.optimizer_type})
+        upd.close()
+        e.close()
+
+    # cfg1 (configs[0] at ensemble size): static LegendreBasis1D(5) along x, no updates, 2^20 walkers per GPU
+    n1 = 1 << 20
+    e = _leg_ensemble(n1, rank * n1, _lib.POT_DOUBLE_WELL_2D, (), MINMAX, local, args.seed)
+    bias.StaticBias_SingleParticle(basis.LegendreBasis1D(5, -2.5, 2.5, 'x', weights=np.array([-11.8, 4.2, 13.1, -2.5, -9.0, 0.4])), None).force.apply(e)
+    sec, kms = _leg_time(torch, dist, world, dev, e, 1000, 3, 1, lambda: None)
+    row("cfg1", "configs[0] shape: 2D double well + static LegendreBasis1D(5, -2.5, 2.5, 'x'), 2^20 walkers per GPU", n1, n1 * world, 1000, sec, kms,
+        "langevin2d_pair_kernel<DoubleWell, Legendre1D<5>>", LEG_FLOPS["cfg1"], "weak")
+    e.close()
+
+    # cfg3 (configs[2]): slip bond, LegendreBasis1D(12, -3, 6), uniform target, second-order averaged SGD, 10^7 walkers in TOTAL
+    lo, hi = shard(10 ** 7, rank, world)
+    updater_leg("cfg3", "configs[2]: slip bond + LegendreBasis1D(12,-3,6,'x'), uniform target, 2nd-order averaged SGD (13x13 covariance), "
+                "10^7 walkers sharded over the ranks",
+                lambda: bias.VESBias_Ensemble(basis.LegendreBasis1D(12, -3, 6, 'x', weights=np.zeros(13)), target.Target_Uniform_HardSwitch_x(200), beta,
+                                              "averaged_sgd", {"mu": 0.5, "second_order": True, "averaging": "ewma", "decay": 0.8}, target_update_every=0),
+                _lib.POT_SLIP_BOND_2D, (0, 0, 1, 5, 4, 0, 2), (-8, 10, -6, 8), hi - lo, lo, 10 ** 7, args.stride, 3,
+                "langevin2d_pair_kernel<SlipBond, Legendre1D<12>>", LEG_FLOPS["cfg3"], "strong", cov=True)
+
+    # cfg4 (configs[3]): Szabo-Berezhkovskii, NNBasis1D [48, 48, 48], Adam 1e-3, running-average gradients, 10^6 walkers per GPU
+    def nn_bias():
+        torch.manual_seed(0)
+        return bias.VESBias_Ensemble(basis.NNBasis1D(min=-4, max=4, axis='x', hidden_layer_sizes=[48, 48, 48]), target.Target_Uniform_HardSwitch_x(200),
+                                     beta, "Adam", {"lr": 1e-3}, target_update_every=0, gradient_average='running')
+    updater_leg("cfg4", "configs[3]: Szabo-Berezhkovskii + NNBasis1D [48,48,48] (ReLU), Adam 1e-3, running-average gradients, uniform target, "
+                "10^6 walkers per GPU", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII, (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000,
+                1000000 * world, args.stride, 2, "langevin2d_kernel<SzaboBerezhkovskii, Mlp<48>>", LEG_FLOPS["cfg4"], "weak")
+
+    # cfg5 (configs[4]): K x K bases, uniform target; weak points at 10^6 walkers per GPU and a 64 x 64 strong point at 10^7 in total
+    def leg2d(K):
+        return lambda: bias.VESBias_Ensemble(basis.LegendreBasis2D(K - 1, K - 1, *MINMAX), target.Target_Uniform_2D(100, 100), beta, "averaged_sgd",
+                                             {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=0)
+    kern = {8: "langevin2d_kernel<DoubleWell, Legendre2DStaticT<8,8>>", 32: "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,1,5>>",
+            64: "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,2,5>>"}
+    for K, stride in ((8, 500), (32, 100), (64, 30)):
+        updater_leg("cfg5_%dx%d" % (K, K), "configs[4]: 2D double well + %dx%d Legendre, uniform target, 10^6 walkers per GPU" % (K, K), leg2d(K),
+                    _lib.POT_DOUBLE_WELL_2D, (), MINMAX, 1000000, rank * 1000000, 1000000 * world, stride, 2, kern[K], LEG_FLOPS[K], "weak")
+    updater_leg("cfg5_64x64_strong", "configs[4]: 2D double well + 64x64 Legendre, uniform target, 10^7 walkers sharded over the ranks", leg2d(64),
+                _lib.POT_DOUBLE_WELL_2D, (), MINMAX, hi - lo, lo, 10 ** 7, 20, 2, kern[64], LEG_FLOPS[64], "strong")
+    return out
+
+
+def single_walker_rate(local, seed):
+    """configs[0] as the reference runs it: ONE particle, static LegendreBasis1D(5) bias, 3 simulated dimensions, FP64, stepped
+    through the C ABI -- steps/s of 2 x 10^5 steps in launches of 10^4 (the reference's Python loop reaches ~10^3 steps/s)."""
+    import torch
+    from pyves_b200 import _lib
+    e = _lib.Ensemble(1, dims=3, seed=seed, precision="fp64", device=local)
+    e.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
+    e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+    e.set_bias_legendre1d(0, 5, -2.5, 2.5, np.array([-11.8, 4.2, 13.1, -2.5, -9.0, 0.4]))
+    e.set_state(np.array([[-1.4], [0.0], [0.0]]), np.zeros((3, 1)))
+    e.step(1000)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(20):
+        e.step(10000)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    e.close()
+    return {"value": 2e5 / dt, "unit": "steps/s", "note": "one walker, dims 3, FP64, general kernel, 20 launches of 10^4 steps (latency bound: "
+            "one thread does the work); the reference's per-step Python/TorchForce loop is the torchforce_style figure of cpu_baseline"}
+
+
+def workload_string(args):
+    return ("configs[1]: 2D double well, %dx%d tensor Legendre bias on [-2.5,2.5]x[-2,2], well-tempered target (gamma 10, 100x100, "
+            "refreshed every 10 updates), in-box ensemble averages, preconditioned averaged SGD (mu %g, EWMA 0.8) every %d steps, "
+            "%d walkers per GPU" % (args.basis, args.basis, args.mu, args.stride, args.walkers))
+
+
+def ncu_traffic(args):
+    """DRAM traffic of the headline kernel cannot be read without a profiler: it comes from the committed ncu --set full
+    capture named here (profiles/), scaled to this run's walker count, or is null."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        if t.get("basis") == args.basis:
+            return {"traffic": t["dram_bytes_per_walker"] * args.walkers,
+                    "traffic_note": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full "
+                                    "capture %s (%s), %g B per walker, scaled to %d walkers" % (t["source"], t["when"], t["dram_bytes_per_walker"], args.walkers)}
+    except (OSError, KeyError, ValueError):
+        pass
+    return {"traffic": None, "traffic_note": "not measured in this run (needs ncu); algorithmic traffic is 32 B per walker per launch"}
 
 
 def fes_rmse(bias, args):
@@ -377,13 +589,47 @@ def fes_rmse(bias, args):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_model(args, seed):
-    from oracle import cport, langevin
-    cport.use_all_threads()
-    k = langevin.constants()
-    spec = dict(kind="leg2d", deg_x=args.basis - 1, deg_y=args.basis - 1, minmax=MINMAX,
-                weights=np.zeros((args.basis, args.basis)))
-    return cport, k, spec
+class CpuVes:
+    """The headline workload on the host cores with the oracle's C port (gcc -O3, OpenMP) + numpy: the same VES iteration
+    as the GPU arm -- `stride` Langevin steps of every walker, in-box first moments, preconditioned averaged-SGD update
+    (mu, EWMA 0.8, scale (2i+1)(2j+1)), well-tempered target (gamma 10, 100 x 100 grid) refreshed every 10 updates."""
+
+    def __init__(self, args, n):
+        from oracle import cport, langevin, legendre, ves
+        self.cport, self.ves, self.legendre = cport, ves, legendre
+        cport.use_all_threads()
+        self.args, self.n = args, n
+        self.k = langevin.constants()
+        K = args.basis
+        self.spec = dict(kind="leg2d", deg_x=K - 1, deg_y=K - 1, minmax=MINMAX, weights=np.zeros((K, K)))
+        self.opt = ves.AveragedSGD(np.zeros(K * K), mu=args.mu, decay=0.8)
+        self.scale = np.outer(2 * np.arange(K) + 1, 2 * np.arange(K) + 1).ravel().astype(np.float64)
+        self.beta = 1.0 / (KB_PY * TEMP)
+        m = 100
+        c = -1 + (2 * np.arange(m) + 1) / m
+        gx, gy = np.meshgrid(c, c, indexing="ij")
+        lv = np.polynomial.legendre.legvander
+        self.basis_grid = (lv(gx.ravel(), K - 1)[:, :, None] * lv(gy.ravel(), K - 1)[:, None, :]).reshape(m * m, K * K)   # f_k at the target nodes
+        self.p = np.full(m * m, 0.25)
+        self.f_target = ves.target_average(self.basis_grid, self.p)
+        self.n_updates = 0
+        self.pos, self.vel = cpu_state(n, self.k, args.seed)
+        self.step0 = 0
+
+    def iteration(self):
+        from oracle import potentials
+        a = self.args
+        m = self.cport.Model(potentials.DOUBLE_WELL_2D, (), self.spec, self.k, seed=a.seed, gid0=0)
+        m.run(self.pos, self.vel, self.step0, a.stride)
+        self.step0 += a.stride
+        sw, sf = self.cport.moments_par(m, self.pos, inside_only=True)
+        abar = self.opt.step((self.f_target - sf / sw) * self.scale)
+        self.spec["weights"] = abar.reshape(self.spec["weights"].shape)
+        self.n_updates += 1
+        if self.n_updates % 10 == 0:
+            q = self.ves.well_tempered_target(self.basis_grid @ abar, self.p, self.beta, 10.0)
+            self.p = q / (q.sum() * 4.0 / q.size)
+            self.f_target = self.ves.target_average(self.basis_grid, self.p)
 
 
 def cpu_state(n, k, seed):
@@ -394,15 +640,15 @@ def cpu_state(n, k, seed):
     return np.ascontiguousarray(pos.T), np.ascontiguousarray(vel.T)
 
 
-def cpu_iteration(cport, k, spec, opt, pos, vel, step0, stride, seed):
-    """One VES iteration of the CPU port: stride steps, first moments, averaged-SGD update."""
-    from oracle import potentials
-    m = cport.Model(potentials.DOUBLE_WELL_2D, (), spec, k, seed=seed, gid0=0)
-    m.run(pos, vel, step0, stride)
-    sf = m.moments(pos)
-    ft = np.zeros_like(sf)
-    ft[0] = 1.0                                                   # uniform target average of P_i P_j
-    spec["weights"] = opt.step(ft - sf / pos.shape[1]).reshape(spec["weights"].shape)
+def cpu_rate_probe(args):
+    """walker-steps/s of the port on a 4096-walker probe (sizes the bounded samples)."""
+    probe = CpuVes(args, 4096)
+    stride, args.stride = args.stride, 50
+    t = time.perf_counter()
+    probe.iteration()
+    dt = time.perf_counter() - t
+    args.stride = stride
+    return 4096 * 50 / dt
 
 
 def torchforce_style_rate(args, steps=300):
@@ -461,22 +707,16 @@ def torchforce_style_rate(args, steps=300):
 
 
 def cpu_baseline(args, seconds=12.0):
-    from oracle import ves
-    cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.8)
-    pos, vel = cpu_state(2048, k, args.seed)
-    t = time.perf_counter()
-    cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
-    rate = 2048 * 50 / (time.perf_counter() - t)
+    rate = cpu_rate_probe(args)
     n = int(max(2048, min(args.walkers, rate * seconds / args.stride)))
-    pos, vel = cpu_state(n, k, args.seed)
+    cpu = CpuVes(args, n)
     t = time.perf_counter()
-    cpu_iteration(cport, k, spec, opt, pos, vel, 0, args.stride, args.seed)
+    cpu.iteration()
     dt = time.perf_counter() - t
-    return {"value": n * args.stride / dt, "unit": "walker-steps/s", "cores": cport.num_threads(), "kind": "port",
-            "sample": "%d walkers x %d steps + moments + update, FP64, gcc -O3 OpenMP C port of the same path "
-                      "(oracle/c/pyves_oracle.c); the reference itself (Python + OpenMM + TorchForce) cannot run here: "
-                      "OpenMM absent" % (n, args.stride),
+    return {"value": n * args.stride / dt, "unit": "walker-steps/s", "cores": cpu.cport.num_threads(), "kind": "port",
+            "sample": "%d of the %d walkers x %d steps + in-box moments + preconditioned averaged-SGD update, FP64, gcc -O3 OpenMP C port of the "
+                      "same path (oracle/c/pyves_oracle.c); the reference itself (Python + OpenMM + TorchForce) cannot run here: "
+                      "OpenMM absent" % (n, args.walkers, args.stride),
             "torchforce_style": dict(torchforce_style_rate(args), unit="walker-steps/s",
                                      note="TorchScript bias forward + backward per step on the CPU + numpy Langevin update: the "
                                           "per-step work of the reference's TorchForce path without OpenMM's own overhead; one "
@@ -484,40 +724,35 @@ def cpu_baseline(args, seconds=12.0):
 
 
 def run_reference(args):
+    """--impl reference: the CPU implementation of the headline workload (see CpuVes) on all host threads.  The FULL
+    ensemble is run when the whole --steps/--warmup run fits --ref-budget seconds (same_config true), else a bounded sample
+    of the walkers (every other element of the workload unchanged)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from oracle import ves
-    cport, k, spec = cpu_model(args, args.seed)
-    opt = ves.AveragedSGD(np.zeros(args.basis * args.basis), mu=args.mu, decay=0.8)
-    pos, vel = cpu_state(2048, k, args.seed)
-    t = time.perf_counter()
-    cpu_iteration(cport, k, spec, opt, pos, vel, 0, 50, args.seed)
-    rate = 2048 * 50 / (time.perf_counter() - t)
-    per_step_s = max(0.5, min(4.0, 90.0 / max(1, args.steps + args.warmup)))
-    n = int(max(2048, min(args.walkers, rate * per_step_s / args.stride)))
-    pos, vel = cpu_state(n, k, args.seed)
-    step0 = 0
+    rate = cpu_rate_probe(args)
+    iters = max(1, args.steps + args.warmup)
+    n_fit = int(rate * args.ref_budget * 0.9 / (iters * args.stride))
+    n = int(max(2048, min(args.walkers, n_fit)))
+    full = n == args.walkers
+    cpu = CpuVes(args, n)
     for _ in range(args.warmup):
-        cpu_iteration(cport, k, spec, opt, pos, vel, step0, args.stride, args.seed)
-        step0 += args.stride
+        cpu.iteration()
     t = time.perf_counter()
     for _ in range(args.steps):
-        cpu_iteration(cport, k, spec, opt, pos, vel, step0, args.stride, args.seed)
-        step0 += args.stride
+        cpu.iteration()
     dt = time.perf_counter() - t
     value = n * args.stride * args.steps / dt
-    sample = ("%d walkers x %d MD steps per bench step (bounded sample of the %d-walker workload), FP64, all host threads"
-              % (n, args.stride, args.walkers))
+    sample = ("%s: %d walkers x %d MD steps per bench step, FP64, %d host threads"
+              % ("the full ensemble" if full else "bounded sample of the %d-walker workload" % args.walkers, n, args.stride, cpu.cport.num_threads()))
     out = {"impl": "reference", "metric": "walker-steps/s (2D double well, Legendre bias)", "value": value,
            "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "configs[1]: 2D double well, %dx%d tensor Legendre bias, averaged SGD update every %d steps"
-                                  % (args.basis, args.basis, args.stride), "sample": sample},
-           "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cport.num_threads(), "kind": "port",
-                            "sample": sample + "; OpenMP C port of the path (oracle/c/pyves_oracle.c) -- the reference's own "
-                                               "OpenMM + TorchForce stack is not installable here (no network)"},
+           "config": {"workload": workload_string(args), "sample": sample, "same_config": bool(full), "walkers_run": n},
+           "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cpu.cport.num_threads(), "kind": "port",
+                            "sample": sample + "; OpenMP C port of the path (oracle/c/pyves_oracle.c) + numpy target refresh -- the "
+                                               "reference's own OpenMM + TorchForce stack is not installable here (no network)"},
            "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

@@ -26,7 +26,7 @@ extern "C" {
 
 typedef struct pyves_ctx pyves_t;
 
-#define PYVES_ABI_VERSION 1
+#define PYVES_ABI_VERSION 2
 
 /* error codes */
 #define PYVES_OK 0
@@ -97,13 +97,17 @@ int pyves_get_step_counter(const pyves_t* h, int64_t* step);
 int pyves_set_bias_none(pyves_t* h);
 /* axis 0 = x, 1 = y; w[degree+1] */
 int pyves_set_bias_legendre1d(pyves_t* h, int axis, int degree, double lo, double hi, const double* w);
-/* minmax = {xlo, xhi, ylo, yhi}; w row-major [deg_x+1][deg_y+1] */
-int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* minmax, const double* w);
+/* The three setters below keep their parameters in device buffers: the host arrays are copied with
+ * cudaMemcpyAsync on `stream` (pageable source: staged before the call returns, so the caller may reuse it at
+ * once), i.e. ordered after the launches already enqueued on that stream; launches of this handle on OTHER
+ * streams must wait for `stream` themselves.
+ * minmax = {xlo, xhi, ylo, yhi}; w row-major [deg_x+1][deg_y+1] */
+int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* minmax, const double* w, void* stream);
 /* theta in torch parameters() order: W0[h0,1] b0[h0] W1[h1,h0] b1[h1] ... Wout[1,hL] bout[1] */
 int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act,
-                       const double* theta);
+                       const double* theta, void* stream);
 int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, const double* y_i, double lam,
-                          const double* w, double phi);
+                          const double* w, double phi, void* stream);
 int pyves_set_bias_harmonic(pyves_t* h, int axis, double k, double s0);
 /* number of basis functions (Legendre) or parameters (MLP) of the current bias */
 int pyves_basis_size(const pyves_t* h, int64_t* K);
@@ -189,7 +193,32 @@ int pyves_averaged_sgd_step(int device, int K, const double* sum_w, const double
                             double mu, double beta, int averaging, double decay, int64_t n_after, double* alpha_out,
                             double* abar_out, void* stream);
 
-/* Domain of the ensemble averages of pyves_moments for the Legendre / path-CV bases.  0 (default): every
+/* pyves_set_bias_mlp with the parameters read from DEVICE memory (FP64, torch parameters() order) in stream order:
+ * conversion to the element type, the fold of the activation-free pair Linear(1, h0) -> Linear(h0, h1)
+ * (ves/basis.py:197-202) and the transposed repack of the third layer run as one kernel, so a device-resident
+ * optimiser hands new NN parameters to the step kernels without the TorchScript save / TorchForce reload of
+ * ves/bias.py:249-253 + ves/langevin_dynamics.py:153-159 and without any host copy.  n_hidden >= 2. */
+int pyves_set_bias_mlp_device(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act,
+                              const double* theta_dev, void* stream);
+
+/* optimiser kinds of pyves_optimizer_step: the three the reference accepts (ves/bias.py:193-200) */
+#define PYVES_OPT_SGD 0
+#define PYVES_OPT_RMSPROP 1
+#define PYVES_OPT_ADAM 2
+
+/* One torch.optim step of P device-resident parameters `theta` (FP64, in place) on the gradient of the VES
+ * functional g = f_target - sum_wf / sum_w, i.e. optimizer.step() of ves/bias.py:236-245 without leaving the GPU.
+ * grad_average: 0 none, 1 running mean over updates, 2 exponentially weighted mean with grad_decay; grad_state [P]
+ * holds the mean and n_average counts the updates averaged so far including this one.  hyper (host, 4 doubles):
+ * {lr, momentum, -, -} for SGD; {lr, alpha, -, eps} for RMSprop (state1 = square_avg); {lr, beta1, beta2, eps} for
+ * Adam (state1 = exp_avg, state2 = exp_avg_sq, bias corrections from `step`, which counts from 1).  Weight decay,
+ * Nesterov, centred RMSprop and AMSGrad are not implemented.  sum_w <= 0 leaves everything unchanged. */
+int pyves_optimizer_step(int device, int kind, int64_t P, const double* sum_w, const double* sum_wf, const double* f_target,
+                         int grad_average, double grad_decay, int64_t n_average, double* grad_state, double* theta,
+                         double* state1, double* state2, const double* hyper, int64_t step, void* stream);
+
+/* Domain of the ensemble averages of pyves_moments (Legendre / path-CV bases; for the NN basis the interval is
+ * [min, max] of NNBasis1D, scaled coordinate in [0, 1]).  0 (default): every
  * row counts, rows outside the basis interval enter with their clamped coordinate, exactly what
  * LegendreBasis1D.forward does to them (ves/basis.py:143).  1: rows outside the interval get weight 0, i.e.
  * <f>_V conditional on the box -- the estimator of the VES functional restricted to the support of the

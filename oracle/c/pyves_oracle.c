@@ -226,6 +226,52 @@ int oracle_moments(const oracle_cfg* C, const double* pos, int64_t n, double* su
   return 0;
 }
 
+/* sum_w and first moments sum_w f_k with OpenMP (thread-private partials combined in thread order); inside_only: walkers
+ * whose scaled coordinate leaves the basis interval get weight 0 (the estimator pyves_set_moment_domain(h, 1) selects) */
+int oracle_moments_par(const oracle_cfg* C, const double* pos, int64_t n, int inside_only, double* sum_w, double* sum_f) {
+  const int kx = C->deg_x + 1, ky = C->bias_kind == BIAS_LEGENDRE_2D ? C->deg_y + 1 : 1;
+  const int K = kx * ky;
+  int nt = 1;
+#ifdef _OPENMP
+  nt = omp_get_max_threads();
+#endif
+  double* part = (double*)calloc((size_t)nt * (K + 1), sizeof(double));
+  if (!part) return -1;
+#pragma omp parallel num_threads(nt)
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    double* acc = part + (size_t)tid * (K + 1);
+#pragma omp for schedule(static)
+    for (int64_t w = 0; w < n; ++w) {
+      double Px[MAXK], dP[MAXK], Py[MAXK];
+      int inx = 1, iny = 1;
+      if (C->bias_kind == BIAS_LEGENDRE_2D) {
+        legendre(clamp_scale(pos[w], C->lo_x, C->hi_x, &inx), C->deg_x, Px, dP);
+        legendre(clamp_scale(pos[n + w], C->lo_y, C->hi_y, &iny), C->deg_y, Py, dP);
+        if (inside_only && !(inx && iny)) continue;
+        for (int i = 0; i < kx; ++i)
+          for (int j = 0; j < ky; ++j) acc[i * ky + j] += Px[i] * Py[j];
+      } else {
+        legendre(clamp_scale(pos[(C->axis ? n : 0) + w], C->lo_x, C->hi_x, &inx), C->deg_x, Px, dP);
+        if (inside_only && !inx) continue;
+        for (int i = 0; i < kx; ++i) acc[i] += Px[i];
+      }
+      acc[K] += 1.0;
+    }
+  }
+  memset(sum_f, 0, sizeof(double) * K);
+  *sum_w = 0.0;
+  for (int t = 0; t < nt; ++t) {
+    for (int k = 0; k < K; ++k) sum_f[k] += part[(size_t)t * (K + 1) + k];
+    *sum_w += part[(size_t)t * (K + 1) + K];
+  }
+  free(part);
+  return 0;
+}
+
 /* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use all host threads */
 void oracle_set_num_threads(int n) {
 #ifdef _OPENMP

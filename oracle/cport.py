@@ -45,6 +45,7 @@ def load():
         _lib.oracle_langevin2d.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_int64, ctypes.c_int64]
         _lib.oracle_moments.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        _lib.oracle_moments_par.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
 
 
@@ -95,6 +96,18 @@ class Model:
         out = np.zeros(K)
         load().oracle_moments(ctypes.byref(self.cfg), pos.ctypes.data, pos.shape[1], out.ctypes.data)
         return out
+
+
+def moments_par(model, pos, inside_only=False):
+    """(sum_w, sum_f [K]) of the Legendre basis over the walkers with all OpenMP threads; ``inside_only`` restricts the
+    averages to the walkers inside the basis box (the estimator of ``VESBias_Ensemble(sample_domain='box')``)."""
+    c = model.cfg
+    K = (c.deg_x + 1) * ((c.deg_y + 1) if c.bias_kind == 2 else 1)
+    out = np.zeros(K)
+    sw = np.zeros(1)
+    rc = load().oracle_moments_par(ctypes.byref(c), pos.ctypes.data, pos.shape[1], int(bool(inside_only)), sw.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return float(sw[0]), out
 
 
 def num_threads():

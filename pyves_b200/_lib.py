@@ -20,6 +20,10 @@ BIAS_NONE, BIAS_LEGENDRE_1D, BIAS_LEGENDRE_2D, BIAS_MLP_1D, BIAS_PATHCV, BIAS_HA
 ACT_RELU, ACT_TANH = 0, 1
 MAX_DEGREE = 63
 
+OPT_SGD, OPT_RMSPROP, OPT_ADAM = 0, 1, 2
+OPTIMIZERS = {"SGD": OPT_SGD, "RMSprop": OPT_RMSPROP, "Adam": OPT_ADAM}
+GRAD_AVERAGE = {None: 0, "running": 1, "ewma": 2}
+
 EINVAL, ECUDA, ESTATE, ENOMEM, EUNSUPPORTED = -1, -2, -3, -4, -5
 
 _c = ctypes
@@ -40,9 +44,9 @@ SIGNATURES = {
     "pyves_get_step_counter": (_i, [_vp, _c.POINTER(_i64)]),
     "pyves_set_bias_none": (_i, [_vp]),
     "pyves_set_bias_legendre1d": (_i, [_vp, _i, _i, _d, _d, _dp]),
-    "pyves_set_bias_legendre2d": (_i, [_vp, _i, _i, _dp, _dp]),
-    "pyves_set_bias_mlp": (_i, [_vp, _i, _d, _d, _i, _ip, _i, _dp]),
-    "pyves_set_bias_pathcv": (_i, [_vp, _i, _i, _dp, _dp, _d, _dp, _d]),
+    "pyves_set_bias_legendre2d": (_i, [_vp, _i, _i, _dp, _dp, _vp]),
+    "pyves_set_bias_mlp": (_i, [_vp, _i, _d, _d, _i, _ip, _i, _dp, _vp]),
+    "pyves_set_bias_pathcv": (_i, [_vp, _i, _i, _dp, _dp, _d, _dp, _d, _vp]),
     "pyves_set_bias_harmonic": (_i, [_vp, _i, _d, _d]),
     "pyves_basis_size": (_i, [_vp, _c.POINTER(_i64)]),
     "pyves_set_state": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -61,6 +65,8 @@ SIGNATURES = {
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
     "pyves_set_bias_legendre1d_device": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
     "pyves_set_bias_like": (_i, [_vp, _vp, _vp]),
+    "pyves_set_bias_mlp_device": (_i, [_vp, _i, _d, _d, _i, _ip, _i, _vp, _vp]),
+    "pyves_optimizer_step": (_i, [_i, _i, _i64, _vp, _vp, _vp, _i, _d, _i64, _vp, _vp, _vp, _vp, _dp, _i64, _vp]),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -110,6 +116,18 @@ def averaged_sgd_step(device, sum_w, sum_wf, sum_wff, f_target, alpha, abar, sca
     rc = lib.pyves_averaged_sgd_step(device, alpha.numel(), _ptr(sum_w), _ptr(sum_wf), _ptr(sum_wff), _ptr(f_target), _ptr(alpha), _ptr(abar),
                                      _ptr(scale), float(mu), float(beta), 0 if averaging == 'ewma' else 1, float(decay), int(n_after),
                                      _ptr(alpha_out), _ptr(abar_out), _stream(device))
+    if rc:
+        raise (ValueError if rc == -1 else RuntimeError)(lib.pyves_last_error(None).decode())
+
+
+def optimizer_step(device, kind, sum_w, sum_wf, f_target, grad_average, grad_decay, n_average, grad_state, theta, state1, state2, hyper, step):
+    """pyves_optimizer_step on CUDA float64 tensors (in place on ``theta`` and the state vectors; enqueued on the current
+    stream of ``device``).  ``kind``: 'SGD' | 'RMSprop' | 'Adam'; ``hyper``: (lr, a, b, eps) as in include/pyves_b200.h."""
+    lib = load()
+    hy = (_d * 4)(*[float(v) for v in hyper])
+    rc = lib.pyves_optimizer_step(device, OPTIMIZERS[kind], theta.numel(), _ptr(sum_w), _ptr(sum_wf), _ptr(f_target), GRAD_AVERAGE[grad_average],
+                                  float(grad_decay), int(n_average), _ptr(grad_state), _ptr(theta), _ptr(state1), _ptr(state2), hy, int(step),
+                                  _stream(device))
     if rc:
         raise (ValueError if rc == -1 else RuntimeError)(lib.pyves_last_error(None).decode())
 
@@ -260,7 +278,7 @@ class Ensemble:
         if a.size != (deg_x + 1) * (deg_y + 1):
             raise ValueError("weights must have (deg_x + 1) * (deg_y + 1) entries")
         m, mp = _darr(minmax)
-        self._ck(self.lib.pyves_set_bias_legendre2d(self.h, deg_x, deg_y, mp, p))
+        self._ck(self.lib.pyves_set_bias_legendre2d(self.h, deg_x, deg_y, mp, p, self.stream))
 
     def set_bias_legendre1d_device(self, axis, degree, lo, hi, w_dev):
         """1D coefficients from a CUDA float64 tensor [degree + 1], read in stream order."""
@@ -296,7 +314,22 @@ class Ensemble:
         dims = [1] + [int(v) for v in s] + [1]
         if len(s) and a.size != sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)):
             raise ValueError("parameter vector does not match the layer sizes")
-        self._ck(self.lib.pyves_set_bias_mlp(self.h, axis, lo, hi, len(s), s.ctypes.data_as(_ip), act, p))
+        self._ck(self.lib.pyves_set_bias_mlp(self.h, axis, lo, hi, len(s), s.ctypes.data_as(_ip), act, p, self.stream))
+
+    def set_bias_mlp_device(self, axis, lo, hi, sizes, act, theta_dev):
+        """NN parameters from a CUDA float64 tensor (torch ``parameters()`` order), read in stream order; the fold of the
+        first two layers and the repack for the step kernels run on the device."""
+        import torch
+        if not (torch.is_tensor(theta_dev) and theta_dev.is_cuda and theta_dev.dtype == torch.float64 and theta_dev.is_contiguous()):
+            raise ValueError("theta_dev must be a contiguous CUDA float64 tensor")
+        if theta_dev.device.index != self.device:
+            raise ValueError("theta_dev lives on another device")
+        s = np.ascontiguousarray(np.asarray(sizes, dtype=np.int32))
+        dims = [1] + [int(v) for v in s] + [1]
+        if theta_dev.numel() != sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)):
+            raise ValueError("parameter vector does not match the layer sizes")
+        self._ck(self.lib.pyves_set_bias_mlp_device(self.h, axis, lo, hi, len(s), s.ctypes.data_as(_ip), act, ctypes.c_void_p(theta_dev.data_ptr()),
+                                                    self.stream))
 
     def set_bias_pathcv(self, degree, x_i, y_i, lam, w, phi=0.0):
         xa, xp = _darr(x_i)
@@ -306,7 +339,7 @@ class Ensemble:
             raise ValueError("x_i and y_i must have the same length")
         if wa.size != degree + 1:
             raise ValueError("weights must have degree + 1 entries")
-        self._ck(self.lib.pyves_set_bias_pathcv(self.h, degree, xa.size, xp, yp, lam, wp, phi))
+        self._ck(self.lib.pyves_set_bias_pathcv(self.h, degree, xa.size, xp, yp, lam, wp, phi, self.stream))
 
     def set_bias_harmonic(self, axis, k, s0):
         self._ck(self.lib.pyves_set_bias_harmonic(self.h, axis, k, s0))

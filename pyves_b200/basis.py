@@ -75,7 +75,7 @@ class _KernelModule(nn.Module):
 
     def _evaluator(self, pos):
         host = not pos.is_cuda
-        dev = 0 if host else pos.device.index
+        dev = torch.cuda.current_device() if host else pos.device.index   # host rows: this process's GPU, not GPU 0
         prec = "fp32" if pos.dtype == torch.float32 else "fp64"
         cache = self.__dict__.setdefault("_evaluators", {})
         if (dev, prec) not in cache:

@@ -23,7 +23,9 @@ import torch.optim as optim
 
 from . import _lib
 from .basis import LegendreBasis1D, LegendreBasis2D, LegendreBasis2DPathCV, NNBasis1D, _KernelModule, _axis_id
-from .optim import AveragedSGD, RunningAverage, gradient_hessian
+import warnings
+
+from .optim import AveragedSGD, EmptyEnsembleAverage, RunningAverage, gradient_hessian
 
 
 class BiasDescriptor:
@@ -174,7 +176,7 @@ def _set_grads(model, flat):
 
 def _device_eval(model, pos_np):
     """Energies of rows ``pos_np`` [N, C] (float64) through the module's CUDA evaluator, no autograd."""
-    t = torch.as_tensor(np.ascontiguousarray(pos_np, dtype=np.float64), device="cuda")
+    t = torch.as_tensor(np.ascontiguousarray(pos_np, dtype=np.float64), device=torch.device("cuda", torch.cuda.current_device()))
     ens, _ = model._evaluator(t)
     model._upload(ens, model._kernel_params())
     return ens, t
@@ -361,7 +363,15 @@ class VESBias_Ensemble(NNBias):
         tonp = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
         sum_w = float(tonp(sum_w).ravel()[0])
         f_p = self.target_average()
-        grad, hess = gradient_hessian(sum_w, tonp(sum_wf), None if sum_wff is None else tonp(sum_wff), f_p, self.beta)
+        try:
+            grad, hess = gradient_hessian(sum_w, tonp(sum_wf), None if sum_wff is None else tonp(sum_wff), f_p, self.beta)
+        except EmptyEnsembleAverage as exc:
+            # same rule as the device kernel (averaged_sgd_kernel): an update without samples changes nothing
+            warnings.warn("VES update skipped: %s" % exc)
+            if self.optimizer_type == 'averaged_sgd':
+                self.optimizer.n += 1
+            self.n_updates += 1
+            return
         if self.grad_avg is not None:
             grad = self.grad_avg.update(grad)
         self.last_gradient = grad
@@ -392,6 +402,46 @@ class VESBias_Ensemble(NNBias):
             ens.set_moment_domain(False)       # the evaluator is shared with the module's other users
         self.update_from_moments(sw, sf, sff)
 
+    # ---- checkpoint of the whole update state (the reference archives only the TorchScript module,
+    # ves/bias.py:249-253, and pickles positions / velocities, ves/langevin_dynamics.py:197-204)
+    def state_dict(self):
+        """Everything a resumed run needs to continue the optimisation exactly: parameters, optimiser state (averaged-SGD
+        iterates and averages, or the ``torch.optim`` state), gradient running average, target density, update count."""
+        d = dict(optimizer_type=self.optimizer_type, n_updates=int(self.n_updates),
+                 model=[p.detach().cpu().numpy().copy() for p in self.model.parameters()],
+                 target_p=np.array(self.target.p, dtype=np.float64, copy=True),
+                 f_target=None if self._f_target is None else np.array(self._f_target, dtype=np.float64, copy=True),
+                 sgd_steps=int(getattr(self, "_sgd_steps", 0)))
+        if self.optimizer_type == 'averaged_sgd':
+            d["optimizer"] = self.optimizer.state_dict()
+        else:
+            d["optimizer"] = self.optimizer.state_dict()
+        if self.grad_avg is not None:
+            d["grad_avg"] = dict(decay=self.grad_avg.decay, n=int(self.grad_avg.n),
+                                 value=None if self.grad_avg.value is None else np.array(self.grad_avg.value, copy=True))
+        return d
+
+    def load_state_dict(self, d):
+        if d.get("optimizer_type") != self.optimizer_type:
+            raise ValueError("checkpoint was written by optimizer %r, this bias uses %r" % (d.get("optimizer_type"), self.optimizer_type))
+        params = list(self.model.parameters())
+        if len(params) != len(d["model"]) or any(tuple(p.shape) != tuple(a.shape) for p, a in zip(params, d["model"])):
+            raise ValueError("checkpointed parameters do not match the model")
+        with torch.no_grad():
+            for p, a in zip(params, d["model"]):
+                p.copy_(torch.from_numpy(np.asarray(a)))
+        self.optimizer.load_state_dict(d["optimizer"])
+        self.n_updates = int(d["n_updates"])
+        self._sgd_steps = int(d.get("sgd_steps", 0))
+        if len(d["target_p"]) != len(self.target.p):
+            raise ValueError("checkpointed target density does not match the target mesh")
+        self.target._p = np.array(d["target_p"], dtype=np.float64, copy=True)
+        self._f_target = None if d.get("f_target") is None else np.array(d["f_target"], dtype=np.float64, copy=True)
+        if self.grad_avg is not None and "grad_avg" in d:
+            self.grad_avg.n = int(d["grad_avg"]["n"])
+            v = d["grad_avg"]["value"]
+            self.grad_avg.value = None if v is None else np.array(v, dtype=np.float64, copy=True)
+
     def fes(self, nodes_scaled=None):
         """F(s) = -V(s) - (1/beta) ln p(s) at the target nodes, shifted to min 0 (kJ/mol)."""
         if isinstance(self.model, LegendreBasis2DPathCV):
@@ -403,48 +453,91 @@ class VESBias_Ensemble(NNBias):
         return F - F.min()
 
 
+def _torch_optimizer_plan(opt):
+    """(kind, hyper, why_not) of a ``torch.optim`` optimiser for ``pyves_optimizer_step``: the plain SGD / RMSprop / Adam
+    rules the reference constructs (``ves/bias.py:193-200``); ``why_not`` names the option the kernel does not implement."""
+    if len(opt.param_groups) != 1:
+        return None, None, "several parameter groups"
+    g = opt.param_groups[0]
+    if g.get("weight_decay", 0) or g.get("maximize", False):
+        return None, None, "weight_decay / maximize"
+    if isinstance(opt, optim.Adam):
+        if g.get("amsgrad", False) or type(opt) is not optim.Adam:
+            return None, None, "amsgrad / Adam subclass"
+        return "Adam", (g["lr"], g["betas"][0], g["betas"][1], g["eps"]), None
+    if isinstance(opt, optim.RMSprop):
+        if g.get("momentum", 0) or g.get("centered", False):
+            return None, None, "RMSprop momentum / centered"
+        return "RMSprop", (g["lr"], g["alpha"], 0.0, g["eps"]), None
+    if isinstance(opt, optim.SGD):
+        if g.get("nesterov", False) or g.get("dampening", 0):
+            return None, None, "SGD nesterov / dampening"
+        return "SGD", (g["lr"], g.get("momentum", 0.0), 0.0, 0.0), None
+    return None, None, "optimizer type"
+
+
 class DeviceUpdater:
-    """Device-resident update loop of a ``VESBias_Ensemble`` (``LegendreBasis1D`` / ``LegendreBasis2D`` model,
-    ``averaged_sgd`` first or second order): gradient, (Hessian-corrected, preconditioned) averaged-SGD step,
-    well-tempered target refresh and target averages are K-sized CUDA tensor operations enqueued on the current
-    stream, and the new coefficients reach the step kernels through ``pyves_set_bias_legendre{1d,2d}_device`` --
-    no device-to-host read, no host optimiser, no re-upload between two launches, so the GPU never waits for
-    Python.  Numerically it is the same update as ``VESBias_Ensemble.update_from_moments`` (FP64), which remains
-    the reference implementation; ``sync_to_host()`` copies coefficients, optimiser state and target back into
-    the bias object.
+    """Device-resident update loop of a ``VESBias_Ensemble``: the optimiser state, the target density, the target
+    averages and the bias parameters live in CUDA tensors, one update is a handful of launches enqueued on the
+    current stream, and the new parameters reach the step kernels through ``pyves_set_bias_*_device`` -- no
+    device-to-host read, no host optimiser, no re-upload between two launches, so the GPU never waits for Python.
+
+    * ``LegendreBasis1D`` / ``LegendreBasis2D`` with ``averaged_sgd`` (first or second order): gradient, Hessian term,
+      preconditioner and averaging are ONE kernel (``pyves_averaged_sgd_step``);
+    * ``NNBasis1D`` (two or more hidden layers) with ``SGD`` / ``RMSprop`` / ``Adam`` and the optional running /
+      exponentially weighted gradient average: ONE kernel (``pyves_optimizer_step``); the parameter-gradient target
+      average <dV/dtheta>_p is re-evaluated with the new parameters after every step (``pyves_moments`` on the
+      target nodes), the fold + repack of the layers for the step kernels is ``pyves_set_bias_mlp_device``.
+
+    Numerically it is the same update as ``VESBias_Ensemble.update_from_moments`` (FP64), which remains the reference
+    implementation; ``sync_to_host()`` copies parameters, optimiser state and target back into the bias object (and
+    its ``torch.optim`` optimiser), from which a new ``DeviceUpdater`` resumes.
 
     Replaces, for the ensemble, the per-update path ``bias.update`` -> TorchScript save -> ``TorchForce`` reload
     -> ``context.reinitialize`` of ``ves/langevin_dynamics.py:147-159`` + ``ves/bias.py:206-253``.
     """
 
     @staticmethod
+    def why_not(bias):
+        """None when ``bias`` can be updated on the device, else the reason."""
+        if not isinstance(bias, VESBias_Ensemble):
+            return "not a VESBias_Ensemble"
+        m = bias.model
+        if isinstance(m, (LegendreBasis1D, LegendreBasis2D)):
+            if bias.optimizer_type != 'averaged_sgd':
+                return "Legendre bases are updated on the device with averaged_sgd only"
+            if bias.grad_avg is not None:
+                return "averaged_sgd on the device has no gradient averaging"
+            return None
+        if isinstance(m, NNBasis1D):
+            if bias.optimizer_type == 'averaged_sgd':
+                return "averaged_sgd needs a linear basis"
+            if len(m.hidden_layer_sizes) < 2:
+                return "a single hidden layer is the linear case (host path)"
+            return _torch_optimizer_plan(bias.optimizer)[2]
+        return "basis %s is updated on the host" % type(m).__name__
+
+    @staticmethod
     def supports(bias):
-        return (isinstance(bias, VESBias_Ensemble) and isinstance(bias.model, (LegendreBasis1D, LegendreBasis2D))
-                and bias.optimizer_type == 'averaged_sgd' and bias.grad_avg is None)
+        return DeviceUpdater.why_not(bias) is None
 
     def __init__(self, bias, ens):
+        why = DeviceUpdater.why_not(bias)
+        if why is not None:
+            raise ValueError("DeviceUpdater: " + why)
         m = bias.model
-        if not isinstance(m, (LegendreBasis1D, LegendreBasis2D)):
-            raise ValueError("DeviceUpdater needs a LegendreBasis1D or LegendreBasis2D model")
-        if bias.optimizer_type != 'averaged_sgd' or bias.grad_avg is not None:
-            raise ValueError("DeviceUpdater implements the averaged_sgd update without gradient averaging")
         self.bias, self.ens = bias, ens
-        o = bias.optimizer
         self.dev = torch.device("cuda", ens.device)
+        self.nn = isinstance(m, NNBasis1D)
         self.two_d = isinstance(m, LegendreBasis2D)
         f64 = dict(dtype=torch.float64, device=self.dev)
-        self.alpha = torch.tensor(o.alpha, **f64)
-        self.abar = torch.tensor(o.abar, **f64)
-        self.scale = None if o.scale is None else torch.tensor(o.scale, **f64)
-        self.mu, self.decay, self.averaging, self.n = o.mu, o.decay, o.averaging, o.n
-        self.second_order = bool(o.second_order)
         self.n_updates = bias.n_updates
         # target: nodes in real coordinates, density, node averages of the basis functions (FP64 evaluator handle)
         self.ev = _lib.Ensemble(1, dims=2, precision="fp64", device=ens.device)
         self.tpos = torch.tensor(bias._target_positions(), **f64).contiguous()
         self.p = torch.tensor(np.asarray(bias.target.p, dtype=np.float64), **f64)
         self.refreshable = hasattr(bias.target, "bias_factor")
-        if self.two_d:
+        if getattr(bias.target, "ndim", 1) == 2:
             self.cell = 4.0 / float(len(bias.target.p))
         else:
             x = np.asarray(bias.target.x, dtype=np.float64)
@@ -452,15 +545,67 @@ class DeviceUpdater:
             tw = np.ones(len(x))
             tw[0] = tw[-1] = 0.5                               # trapezoid rule of Target_x.quadrature_weights
             self.trap = torch.tensor(tw, **f64)
-        self.handles = [ens]                 # every handle that receives the coefficients (add_handle)
-        self._spare = (torch.empty_like(self.alpha), torch.empty_like(self.abar))
+        self.handles = [ens]                 # every handle that receives the parameters (add_handle)
         self._flat = None
+        if self.nn:
+            self._init_nn(f64)
+        else:
+            o = bias.optimizer
+            self.alpha = torch.tensor(o.alpha, **f64)
+            self.abar = torch.tensor(o.abar, **f64)
+            self.scale = None if o.scale is None else torch.tensor(o.scale, **f64)
+            self.mu, self.decay, self.averaging, self.n = o.mu, o.decay, o.averaging, o.n
+            self.second_order = bool(o.second_order)
+            self._spare = (torch.empty_like(self.alpha), torch.empty_like(self.abar))
         self._upload(self.ev)
         self.f_target = self._target_average()
         ens.set_moment_domain(bias.sample_domain == 'box')
         self._upload(ens)
         if self.refreshable:
             self._refreshed_density()       # result discarded: loads the kernels of the refresh path (CUDA loads lazily)
+
+    # ---- NN state: flat parameter vector + torch.optim state + gradient average, all FP64 on the device
+    def _init_nn(self, f64):
+        b, m = self.bias, self.bias.model
+        self.second_order = False
+        params = list(m.parameters())
+        self.theta = torch.cat([p.detach().reshape(-1).to(torch.float64) for p in params]).to(self.dev).contiguous()
+        P = self.theta.numel()
+        self.kind, self.hyper, _ = _torch_optimizer_plan(b.optimizer)
+        self.s1 = torch.zeros(P, **f64)
+        self.s2 = torch.zeros(P, **f64)
+        self.t = 0                                           # optimiser steps done
+        st = b.optimizer.state
+        if len(st) > 0:                                      # resume from the host optimiser's state
+            key1 = {"Adam": "exp_avg", "RMSprop": "square_avg", "SGD": "momentum_buffer"}[self.kind]
+            cat = lambda key: torch.cat([(st[p][key] if st[p].get(key) is not None else torch.zeros_like(p)).detach().reshape(-1).to(torch.float64)
+                                         for p in params]).to(self.dev).contiguous()
+            self.s1 = cat(key1)
+            if self.kind == "Adam":
+                self.s2 = cat("exp_avg_sq")
+            step = st[params[0]].get("step", None)
+            self.t = int(step) if step is not None else int(getattr(b, "_sgd_steps", 0))
+        ga = b.grad_avg
+        self.gavg = None if ga is None else ("running" if ga.decay is None else "ewma")
+        self.gdecay = 0.0 if (ga is None or ga.decay is None) else float(ga.decay)
+        self.gn = 0 if ga is None else int(ga.n)
+        self.gstate = torch.zeros(P, **f64)
+        if ga is not None and ga.value is not None:
+            self.gstate.copy_(torch.as_tensor(ga.value, **f64))
+
+    @property
+    def K(self):
+        """Number of basis functions / parameters (length of ``sum_wf``)."""
+        return (self.theta if self.nn else self.alpha).numel()
+
+    @property
+    def lr(self):
+        return self.hyper[0]
+
+    @lr.setter
+    def lr(self, value):
+        """Learning-rate schedules are host arithmetic: the rate is a by-value argument of every step."""
+        self.hyper = (float(value),) + tuple(self.hyper[1:])
 
     def add_handle(self, ens):
         """Another ensemble handle on the same device (a shard processed on its own stream) that shares the bias.
@@ -473,6 +618,9 @@ class DeviceUpdater:
 
     def _upload(self, handle):
         m = self.bias.model
+        if self.nn:
+            handle.set_bias_mlp_device(_axis_id(m.axis), float(m.min), float(m.max), m.hidden_layer_sizes, m._act, self.theta)
+            return
         if handle is not self.ens and handle is not self.ev and handle.precision == self.ens.precision:
             handle.set_bias_like(self.ens)          # shards of one ensemble share the converted weights (and their tag)
             return
@@ -482,7 +630,8 @@ class DeviceUpdater:
             handle.set_bias_legendre1d_device(_axis_id(m.axis), m.degree, float(m.min), float(m.max), self.abar)
 
     def _target_average(self):
-        q = self.p if self.two_d else self.p * self.trap        # Target_2D / Target_x .quadrature_weights
+        """<dV/dparam>_p by quadrature over the target nodes (the evaluator handle must hold the current parameters)."""
+        q = self.p if getattr(self.bias.target, "ndim", 1) == 2 else self.p * self.trap   # Target_2D / Target_x .quadrature_weights
         q = (q / q.sum()).contiguous()
         sw, sf, _ = self.ev.moments(pos=self.tpos, row_weights=q)
         return sf / sw
@@ -490,7 +639,26 @@ class DeviceUpdater:
     def update(self, sum_w, sum_wf, sum_wff=None):
         """One update from ensemble sums on the device (already reduced over all GPUs).  Enqueue only."""
         with _lib._Range("pyves.update"):
-            self._update(sum_w, sum_wf, sum_wff)
+            if self.nn:
+                self._update_nn(sum_w, sum_wf)
+            else:
+                self._update(sum_w, sum_wf, sum_wff)
+
+    def _update_nn(self, sum_w, sum_wf):
+        self.t += 1
+        if self.gavg is not None:
+            self.gn += 1
+        _lib.optimizer_step(self.ens.device, self.kind, sum_w, sum_wf, self.f_target, self.gavg, self.gdecay, max(self.gn, 1),
+                            self.gstate if self.gavg is not None else None, self.theta, self.s1, self.s2 if self.kind == "Adam" else None,
+                            self.hyper, self.t)
+        self.n_updates += 1
+        for hdl in self.handles:
+            self._upload(hdl)
+        self._upload(self.ev)
+        b = self.bias
+        if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
+            self.p = self._refreshed_density()
+        self.f_target = self._target_average()              # <dV/dtheta>_p depends on theta: for the next update
 
     def _update(self, sum_w, sum_wf, sum_wff):
         if self.second_order and sum_wff is None:
@@ -513,7 +681,7 @@ class DeviceUpdater:
         """Views (sum_w, sum_wf, sum_wff or None) of ONE persistent flat FP64 buffer for ``ens.moments(out=...)``:
         no allocation per update, and ``reduce_flat`` all-reduces the flat buffer in place (one NCCL call)."""
         cov = self.second_order if cov is None else cov
-        K = self.alpha.numel()
+        K = self.K
         n = 1 + K + (K * K if cov else 0)
         if getattr(self, "_flat", None) is None or self._flat.numel() != n:
             self._flat = torch.zeros(n, dtype=torch.float64, device=self.dev)
@@ -532,22 +700,54 @@ class DeviceUpdater:
         V, _ = self.ev.eval_bias(self.tpos, want_force=False)
         F = -V - torch.log(torch.clamp(self.p, min=1e-300)) / b.beta
         q = torch.exp(-(b.beta / b.target.bias_factor) * (F - F.min()))
-        if self.two_d:
+        if getattr(b.target, "ndim", 1) == 2:
             return q / (q.sum() * self.cell)
         return q / (torch.sum(q * self.trap) * self.dx)
 
+    def bias_at_nodes(self):
+        """Bias energy at the target nodes with the current device parameters (CUDA float64 tensor [M])."""
+        self._upload(self.ev)
+        V, _ = self.ev.eval_bias(self.tpos, want_force=False)
+        return V
+
     def sync_to_host(self):
-        """Copy the device state back into the bias object (coefficients, optimiser, target)."""
+        """Copy the device state back into the bias object (parameters, optimiser, gradient average, target)."""
         b, o = self.bias, self.bias.optimizer
-        o.alpha = self.alpha.cpu().numpy().copy()
-        o.abar = self.abar.cpu().numpy().copy()
-        o.n = self.n
         b.n_updates = self.n_updates
-        with torch.no_grad():
-            off = 0
-            for prm in b.model.parameters():
-                prm.copy_(torch.from_numpy(o.abar[off:off + prm.numel()].reshape(tuple(prm.shape))))
-                off += prm.numel()
+        if self.nn:
+            theta = self.theta.cpu()
+            s1, s2, g = self.s1.cpu(), self.s2.cpu(), self.gstate.cpu()
+            with torch.no_grad():
+                off = 0
+                for prm in b.model.parameters():
+                    n = prm.numel()
+                    prm.copy_(theta[off:off + n].reshape(prm.shape))
+                    if self.t > 0:
+                        st = o.state[prm]
+                        if self.kind == "Adam":
+                            st["step"] = torch.tensor(float(self.t))
+                            st["exp_avg"] = s1[off:off + n].reshape(prm.shape).clone()
+                            st["exp_avg_sq"] = s2[off:off + n].reshape(prm.shape).clone()
+                        elif self.kind == "RMSprop":
+                            st["step"] = torch.tensor(float(self.t))
+                            st["square_avg"] = s1[off:off + n].reshape(prm.shape).clone()
+                        elif self.hyper[1] != 0.0:
+                            st["momentum_buffer"] = s1[off:off + n].reshape(prm.shape).clone()
+                    off += n
+            o.param_groups[0]["lr"] = self.hyper[0]
+            b._sgd_steps = self.t
+            if b.grad_avg is not None:
+                b.grad_avg.n = self.gn
+                b.grad_avg.value = g.numpy().copy() if self.gn > 0 else None
+        else:
+            o.alpha = self.alpha.cpu().numpy().copy()
+            o.abar = self.abar.cpu().numpy().copy()
+            o.n = self.n
+            with torch.no_grad():
+                off = 0
+                for prm in b.model.parameters():
+                    prm.copy_(torch.from_numpy(o.abar[off:off + prm.numel()].reshape(tuple(prm.shape))))
+                    off += prm.numel()
         if self.refreshable:
             b.target._p = self.p.cpu().numpy().copy()
         b._f_target = self.f_target.cpu().numpy().copy()

@@ -60,7 +60,7 @@ struct pyves_ctx {
   int mlp_axis = 0, mlp_act = 0;
   double mlp_lo = 0, mlp_hi = 1;
   std::vector<int> mlp_sizes;       // hidden widths
-  std::vector<double> mlp_theta;
+  size_t mlp_np = 0;                // number of parameters (torch parameters() order)
   void* mlp_theta_dev = nullptr;
   void* mlp_packed_dev = nullptr;
   int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
@@ -132,25 +132,35 @@ int ensure_stage(pyves_ctx* h, size_t bytes) {
   return PYVES_OK;
 }
 
-// upload a double host array as the handle's element type
-int upload(pyves_ctx* h, void** dev, const double* src, size_t count) {
-  // the buffer is reused when the size is unchanged (coefficient updates): cudaFree would synchronise the device
+// upload a double host array as the handle's element type, ordered on the caller's stream `st`: the copy comes
+// from pageable host memory, so cudaMemcpyAsync returns once the source has been staged (the temporary may die)
+// and the transfer itself is ordered after the work already enqueued on `st` -- a step / eval / moments kernel
+// still reading the previous parameters on that stream finishes first.  Launches on OTHER streams must be ordered
+// by the caller (wait for `st`).
+// device buffer of `count` elements of the handle's type behind *dev; reused when the size is unchanged
+// (coefficient updates): cudaFree would synchronise the device
+int ensure_buffer(pyves_ctx* h, void** dev, size_t count) {
   auto it = h->alloc_count.find(dev);
   const bool reuse = *dev != nullptr && it != h->alloc_count.end() && it->second == count && count > 0;
-  if (!reuse) {
-    if (*dev) cudaFree(*dev);
-    *dev = nullptr;
-    h->alloc_count.erase(dev);
-    if (count == 0) return PYVES_OK;
-    CU(cudaMalloc(dev, count * h->esz));
-    h->alloc_count[dev] = count;
-  }
+  if (reuse) return PYVES_OK;
+  if (*dev) cudaFree(*dev);
+  *dev = nullptr;
+  h->alloc_count.erase(dev);
+  if (count == 0) return PYVES_OK;
+  CU(cudaMalloc(dev, count * h->esz));
+  h->alloc_count[dev] = count;
+  return PYVES_OK;
+}
+
+int upload(pyves_ctx* h, void** dev, const double* src, size_t count, cudaStream_t st) {
+  { const int rc = ensure_buffer(h, dev, count); if (rc) return rc; }
+  if (count == 0) return PYVES_OK;
   if (h->prec == PYVES_F64) {
-    CU(cudaMemcpy(*dev, src, count * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(*dev, src, count * sizeof(double), cudaMemcpyHostToDevice, st));
   } else {
     std::vector<float> tmp(count);
     for (size_t i = 0; i < count; ++i) tmp[i] = (float)src[i];
-    CU(cudaMemcpy(*dev, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(*dev, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice, st));
   }
   return PYVES_OK;
 }
@@ -288,7 +298,7 @@ int64_t basis_size(const pyves_ctx* h) {
     case PYVES_BIAS_LEGENDRE_1D: return h->l1_degree + 1;
     case PYVES_BIAS_LEGENDRE_2D: return (int64_t)(h->l2_dx + 1) * (h->l2_dy + 1);
     case PYVES_BIAS_PATHCV: return h->pc_degree + 1;
-    case PYVES_BIAS_MLP_1D: return (int64_t)h->mlp_theta.size();
+    case PYVES_BIAS_MLP_1D: return (int64_t)h->mlp_np;
     default: return 0;
   }
 }
@@ -547,6 +557,7 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
     M.inv_range = (T)(1.0 / (h->mlp_hi - h->mlp_lo));
     M.theta = static_cast<const T*>(h->mlp_theta_dev);
     M.n_params = (int)K;
+    M.inside_only = h->mom_inside;
     CU(launch_moments_mlp<T>(S, M, sum_w, sum_wf, h->scratch, st, &launches));
   } else {
     BasisParams<T> B;
@@ -810,7 +821,7 @@ int pyves_set_bias_legendre1d_device(pyves_t* h, int axis, int degree, double lo
   return PYVES_OK;
 }
 
-int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm, const double* w) {
+int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm, const double* w, void* stream) {
   if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
   if (deg_x < 0 || deg_x > PYVES_MAX_DEGREE || deg_y < 0 || deg_y > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degrees must be in [0, 63]");
   if (!mm || !w || !(mm[1] > mm[0]) || !(mm[3] > mm[2])) return fail(h, PYVES_EINVAL, "need max > min per axis and weights");
@@ -820,7 +831,7 @@ int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm
   h->l2_dy = deg_y;
   std::memcpy(h->l2_mm, mm, sizeof(h->l2_mm));
   h->l2_w.assign(w, w + K);
-  const int rc = upload(h, &h->l2_w_dev, w, K);
+  const int rc = upload(h, &h->l2_w_dev, w, K, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   h->l2_dev_mode = false;
   h->l2_dev_count = 0;           // upload() reallocated l2_w_dev
@@ -899,7 +910,7 @@ int pyves_set_bias_like(pyves_t* h, const pyves_t* leader, void* stream) {
   return PYVES_OK;
 }
 
-int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act, const double* theta) {
+int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act, const double* theta, void* stream) {
   if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
   if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
   if (n_hidden < 1) return fail(h, PYVES_EINVAL, "NNBasis needs at least one hidden layer");
@@ -925,8 +936,9 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
   h->mlp_lo = lo;
   h->mlp_hi = hi;
   h->mlp_sizes.assign(sizes, sizes + n_hidden);
-  h->mlp_theta.assign(theta, theta + np);
-  int rc = upload(h, &h->mlp_theta_dev, theta, np);
+  h->mlp_np = np;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = upload(h, &h->mlp_theta_dev, theta, np, st);
   if (rc) return rc;
   // fold the activation-free pair Linear(1,h0) -> Linear(h0,h1)  (ves/basis.py:197-202)
   const int L = n_hidden;
@@ -963,13 +975,14 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
     }
     if (L == 2) {
       const int Wp = (h1 + 3) / 4 * 4;
-      packed.assign((size_t)3 * Wp, 0.0);
+      packed.assign((size_t)3 * Wp + 4, 0.0);
       const double* Wo = theta + woff[2];
       for (int j = 0; j < h1; ++j) {
         packed[j] = u[j];
         packed[Wp + j] = c[j];
         packed[2 * Wp + j] = Wo[j];
       }
+      packed[(size_t)3 * Wp] = theta[boff[2]];
       h->mlp_bout = theta[boff[2]];
       h->mlp_width = Wp;
       h->mlp_H = 0;
@@ -978,7 +991,7 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
       const int m = h1 > h2 ? h1 : h2;
       const int H = m <= 32 ? 32 : (m <= 48 ? 48 : (m <= 64 ? 64 : -1));
       if (H > 0) {
-        packed.assign((size_t)4 * H + (size_t)H * H, 0.0);
+        packed.assign((size_t)4 * H + (size_t)H * H + 4, 0.0);
         const double* W2 = theta + woff[2];
         const double* b2 = theta + boff[2];
         const double* Wo = theta + woff[3];
@@ -991,18 +1004,127 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
           packed[3 * H + j] = b2[j];
           for (int i = 0; i < h1; ++i) packed[4 * H + (size_t)i * H + j] = W2[j * h1 + i];   // transposed: W2T[i][j]
         }
+        packed[(size_t)4 * H + (size_t)H * H] = theta[boff[3]];
         h->mlp_bout = theta[boff[3]];
         h->mlp_H = H;
       }
     }
   }
-  rc = upload(h, &h->mlp_packed_dev, packed.data(), packed.size());
+  rc = upload(h, &h->mlp_packed_dev, packed.data(), packed.size(), st);
   if (rc) return rc;
   h->bias_kind = PYVES_BIAS_MLP_1D;
   return PYVES_OK;
 }
 
-int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, const double* y_i, double lam, const double* w, double phi) {
+int pyves_set_bias_mlp_device(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act, const double* theta_dev,
+                              void* stream) {
+  if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
+  if (!valid_axis(axis)) return fail(h, PYVES_EINVAL, "Invalid axis");
+  if (n_hidden < 1) return fail(h, PYVES_EINVAL, "NNBasis needs at least one hidden layer");
+  if (n_hidden < 2) return fail(h, PYVES_EUNSUPPORTED, "device-resident NN parameters need at least two hidden layers (a single one is the linear case: use pyves_set_bias_mlp)");
+  if (n_hidden > 8) return fail(h, PYVES_EUNSUPPORTED, "at most 8 hidden layers are supported");
+  if (act != PYVES_ACT_RELU && act != PYVES_ACT_TANH) return fail(h, PYVES_EUNSUPPORTED, "activation must be ReLU or Tanh");
+  if (!sizes || !theta_dev || hi == lo) return fail(h, PYVES_EINVAL, "need sizes, parameters and max != min");
+  for (int i = 0; i < n_hidden; ++i)
+    if (sizes[i] < 1) return fail(h, PYVES_EINVAL, "hidden layer sizes must be >= 1");
+  DeviceGuard g(h->device);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, theta_dev) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    return fail(h, PYVES_EINVAL, "theta_dev must be a device pointer (FP64, torch parameters() order)");
+  }
+  std::vector<int> dims(1, 1);
+  dims.insert(dims.end(), sizes, sizes + n_hidden);
+  dims.push_back(1);
+  size_t np = 0;
+  std::vector<size_t> woff, boff;
+  for (size_t l = 0; l + 1 < dims.size(); ++l) {
+    woff.push_back(np);
+    np += (size_t)dims[l] * dims[l + 1];
+    boff.push_back(np);
+    np += dims[l + 1];
+  }
+  MlpPackPlan Q;
+  std::memset(&Q, 0, sizeof(Q));
+  Q.np = (int)np;
+  Q.h0 = dims[1];
+  Q.h1 = dims[2];
+  Q.w0 = (int)woff[0]; Q.b0 = (int)boff[0]; Q.w1 = (int)woff[1]; Q.b1 = (int)boff[1];
+  int H = -1, width = 0;
+  if (n_hidden == 2) {
+    width = (dims[2] + 3) / 4 * 4;
+    H = 0;
+    Q.wo = (int)woff[2]; Q.bo = (int)boff[2];
+    Q.n_packed = 3 * width + 4;
+  } else if (n_hidden == 3) {
+    const int m = dims[2] > dims[3] ? dims[2] : dims[3];
+    H = m <= 32 ? 32 : (m <= 48 ? 48 : (m <= 64 ? 64 : -1));
+    if (H > 0) {
+      Q.h2 = dims[3];
+      Q.w2 = (int)woff[2]; Q.b2 = (int)boff[2]; Q.wo = (int)woff[3]; Q.bo = (int)boff[3];
+      Q.n_packed = 4 * H + H * H + 4;
+    }
+  }
+  Q.H = H > 0 ? H : 0;
+  Q.width = width;
+  int rc = ensure_buffer(h, &h->mlp_theta_dev, np);
+  if (rc) return rc;
+  rc = ensure_buffer(h, &h->mlp_packed_dev, (size_t)Q.n_packed);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->prec == PYVES_F64) {
+    CU(launch_mlp_pack<double>(theta_dev, Q, static_cast<double*>(h->mlp_theta_dev), static_cast<double*>(h->mlp_packed_dev), st));
+  } else {
+    CU(launch_mlp_pack<float>(theta_dev, Q, static_cast<float*>(h->mlp_theta_dev), static_cast<float*>(h->mlp_packed_dev), st));
+  }
+  g_launches++;
+  h->mlp_axis = axis;
+  h->mlp_act = act;
+  h->mlp_lo = lo;
+  h->mlp_hi = hi;
+  h->mlp_sizes.assign(sizes, sizes + n_hidden);
+  h->mlp_np = np;
+  h->mlp_linear = 0;
+  h->mlp_H = H;
+  h->mlp_width = width;
+  h->mlp_bout = 0;
+  h->mlp_u0 = 0;
+  h->bias_kind = PYVES_BIAS_MLP_1D;
+  return PYVES_OK;
+}
+
+int pyves_optimizer_step(int device, int kind, int64_t P, const double* sum_w, const double* sum_wf, const double* f_target, int grad_average,
+                         double grad_decay, int64_t n_average, double* grad_state, double* theta, double* state1, double* state2,
+                         const double* hyper, int64_t step, void* stream) {
+  pyves_ctx* h = nullptr;
+  if (P < 1 || !sum_w || !sum_wf || !f_target || !theta || !hyper) return fail(h, PYVES_EINVAL, "optimizer_step: NULL argument or P < 1");
+  if (kind != PYVES_OPT_SGD && kind != PYVES_OPT_RMSPROP && kind != PYVES_OPT_ADAM) return fail(h, PYVES_EINVAL, "Requested optimizer not yet supported.");
+  if (grad_average < 0 || grad_average > 2 || (grad_average != 0 && (!grad_state || n_average < 1))) return fail(h, PYVES_EINVAL, "optimizer_step: gradient averaging needs its state vector and n_average >= 1");
+  if (step < 1) return fail(h, PYVES_EINVAL, "optimizer_step: step counts from 1");
+  OptHyper H;
+  H.lr = hyper[0];
+  H.a = hyper[1];
+  H.b = hyper[2];
+  H.eps = hyper[3];
+  H.bc1 = H.bc2_sqrt = 1.0;
+  if (kind == PYVES_OPT_ADAM) {
+    if (!state1 || !state2) return fail(h, PYVES_EINVAL, "optimizer_step: Adam needs exp_avg and exp_avg_sq");
+    H.bc1 = 1.0 - std::pow(H.a, (double)step);
+    H.bc2_sqrt = std::sqrt(1.0 - std::pow(H.b, (double)step));
+  } else if (kind == PYVES_OPT_RMSPROP) {
+    if (!state1) return fail(h, PYVES_EINVAL, "optimizer_step: RMSprop needs square_avg");
+  } else if (H.a != 0.0 && !state1) {
+    return fail(h, PYVES_EINVAL, "optimizer_step: SGD with momentum needs its buffer");
+  }
+  DeviceGuard g(device);
+  cudaError_t e = launch_optimizer_step(kind, (long long)P, sum_w, sum_wf, f_target, grad_average, grad_decay, (long long)n_average, grad_state,
+                                        theta, state1, state2, H, (long long)step, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(h, PYVES_ECUDA, cudaGetErrorString(e));
+  g_launches++;
+  return PYVES_OK;
+}
+
+int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, const double* y_i, double lam, const double* w, double phi, void* stream) {
   if (!h) return fail(h, PYVES_EINVAL, "handle is NULL");
   if (degree < 0 || degree > PYVES_MAX_DEGREE) return fail(h, PYVES_EINVAL, "degree must be in [0, 63]");
   if (npath < 1 || npath > PYVES_MAX_PATH) return fail(h, PYVES_EINVAL, "path needs 1..256 images");
@@ -1010,7 +1132,7 @@ int pyves_set_bias_pathcv(pyves_t* h, int degree, int npath, const double* x_i, 
   DeviceGuard g(h->device);
   std::vector<double> path(x_i, x_i + npath);
   path.insert(path.end(), y_i, y_i + npath);
-  const int rc = upload(h, &h->pc_path_dev, path.data(), path.size());
+  const int rc = upload(h, &h->pc_path_dev, path.data(), path.size(), static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   h->pc_degree = degree;
   h->pc_npath = npath;

@@ -434,16 +434,18 @@ template <typename T, int RB, int NRB, int UNR> struct BiasLegendre2DSmem {
 // dV/ds is carried in forward mode next to the value, so each weight read from shared memory
 // feeds two FMAs.
 //   H == 0 : two hidden layers (no matmul left after folding), any width (padded to 4):
-//            streamed, no per-thread arrays.       shared (T): u[W] c[W] wout[W]
+//            streamed, no per-thread arrays.       shared (T): u[W] c[W] wout[W] bout pad[3]
 //   H  > 0 : three hidden layers = one H x H matmul, widths padded to H.
-//                                                  shared (T): u[H] c[H] wout[H] b2[H] W2T[H][H]  (W2T[i][j] = W2[j][i])
-// A single hidden layer is the reference's degenerate linear case V = u0 s + bout.
+//                                                  shared (T): u[H] c[H] wout[H] b2[H] W2T[H][H] bout pad[3] (W2T[i][j] = W2[j][i])
+// A single hidden layer is the reference's degenerate linear case V = u0 s + bout (scalars by value).
+// The output bias travels at the end of the packed buffer, not by value, so that a device-resident optimiser
+// (pyves_set_bias_mlp_device) can refresh every parameter without a host copy.
 template <typename T> struct MlpParams {
   int axis;
   int linear;      // 1: single hidden layer
   int width;       // padded width of the streamed (H == 0) variant
   T lo, inv_range;
-  T bout, u0;
+  T bout, u0;       // single hidden layer only
   const T* packed;  // device, layout above
 };
 
@@ -464,18 +466,19 @@ template <typename T, int H, int ACT> struct BiasMlp {
   struct alignas(16) Vec { T v[V]; };
   static size_t smem_bytes(const Params& P) {
     if (P.linear) return 0;
-    return (size_t)(H > 0 ? 4 * H + H * H : 3 * P.width) * sizeof(T);
+    return (size_t)packed_count(P) * sizeof(T);
   }
+  static __host__ __device__ int packed_count(const Params& P) { return (H > 0 ? 4 * H + H * H : 3 * P.width) + 4; }
   static PV_DEV void stage(const Params& P, void* smem) {
     if (P.linear) return;
     T* d = reinterpret_cast<T*>(smem);
-    const int n = H > 0 ? 4 * H + H * H : 3 * P.width;
+    const int n = packed_count(P);
     for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = P.packed[i];
   }
   template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
     const T s = ((P.axis ? y : x) - P.lo) * P.inv_range;
-    T val = P.bout, dval = T(0);
     const T* sm = reinterpret_cast<const T*>(smem);
+    T val = P.linear ? P.bout : sm[packed_count(P) - 4], dval = T(0);
     if (P.linear) {
       val = Math<T>::fma(P.u0, s, P.bout);
       dval = P.u0;

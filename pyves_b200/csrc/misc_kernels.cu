@@ -294,6 +294,13 @@ __global__ void __launch_bounds__(256) averaged_sgd_kernel(int K, const double* 
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (k >= K) return;
+  if (!(sum_w[0] > 0.0)) {   // no sample in the averaging domain (every walker outside the basis box): keep the state
+    if (lane == 0) {
+      alpha_out[k] = alpha[k];
+      abar_out[k] = abar[k];
+    }
+    return;
+  }
   const double inv_w = 1.0 / sum_w[0];
   const double mean_k = sum_wf[k] * inv_w;
   double h = 0.0;
@@ -332,11 +339,130 @@ cudaError_t launch_convert_weights1d(const double* w64, int n, T* w_t, double* k
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One optimiser step of the NN-bias parameters on the device (FP64, elementwise, in place): the gradient of the
+// VES functional from the ensemble sums, its optional running / exponentially weighted average over updates, and
+// the torch.optim rule the reference delegates to (ves/bias.py:193-200 picks SGD / RMSprop / Adam, :236-245 steps).
+// Same arithmetic, operation by operation, as torch's single-tensor CPU implementations (lerp as an FMA, addcmul,
+// addcdiv), so the device loop tracks the host loop to rounding.
+//   g = f_target - sum_wf / sum_w
+//   gavg 1: G = n == 1 ? g : G + (g - G) / n          gavg 2: G = n == 1 ? g : decay G + (1 - decay) g      g <- G
+//   SGD     : buf = t == 1 ? g : momentum buf + g (momentum != 0);  theta -= lr (buf | g)
+//   RMSprop : sq = alpha sq + (1 - alpha) g g;  theta -= lr g / (sqrt(sq) + eps)
+//   Adam    : m = m + (1 - b1)(g - m);  v = b2 v + (1 - b2) g g;  theta -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) optimizer_step_kernel(int kind, long long P, const double* __restrict__ sum_w,
+                                                             const double* __restrict__ sum_wf, const double* __restrict__ f_target,
+                                                             int gavg, double gdecay, long long n_avg, double* __restrict__ gstate,
+                                                             double* __restrict__ theta, double* __restrict__ s1, double* __restrict__ s2,
+                                                             OptHyper H, long long t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double sw = sum_w[0];
+  if (!(sw > 0.0)) return;   // no sample in the averaging domain: parameters and optimiser state stay as they are
+  double g = f_target[i] - sum_wf[i] / sw;
+  if (gavg != 0) {
+    double G = gstate[i];
+    if (n_avg == 1) G = g;
+    else if (gavg == 1) G = G + (g - G) / (double)n_avg;
+    else G = gdecay * G + (1.0 - gdecay) * g;
+    gstate[i] = G;
+    g = G;
+  }
+  double th = theta[i];
+  if (kind == PYVES_OPT_SGD) {
+    if (H.a != 0.0) {                       // momentum (dampening 0, no Nesterov)
+      const double buf = t == 1 ? g : H.a * s1[i] + g;
+      s1[i] = buf;
+      g = buf;
+    }
+    th = th + (-H.lr) * g;
+  } else if (kind == PYVES_OPT_RMSPROP) {
+    const double sq = s1[i] * H.a + (1.0 - H.a) * g * g;
+    s1[i] = sq;
+    th = th + (-H.lr) * g / (sqrt(sq) + H.eps);
+  } else {
+    const double m = fma(1.0 - H.a, g - s1[i], s1[i]);
+    const double v = s2[i] * H.b + (1.0 - H.b) * g * g;
+    s1[i] = m;
+    s2[i] = v;
+    const double denom = sqrt(v) / H.bc2_sqrt + H.eps;
+    th = th + (-(H.lr / H.bc1)) * m / denom;
+  }
+  theta[i] = th;
+}
+
+cudaError_t launch_optimizer_step(int kind, long long P, const double* sum_w, const double* sum_wf, const double* f_target, int gavg,
+                                  double gdecay, long long n_avg, double* gstate, double* theta, double* s1, double* s2,
+                                  const OptHyper& H, long long t, cudaStream_t st) {
+  optimizer_step_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(kind, P, sum_w, sum_wf, f_target, gavg, gdecay, n_avg, gstate, theta,
+                                                                     s1, s2, H, t);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// NN parameters from a device-resident optimiser: theta64 (FP64, torch parameters() order) -> element-type copy
+// theta_t (generic functor, gradient-moment kernels) and the packed layout of BiasMlp (bias.cuh): the activation-free
+// pair Linear(1, h0) -> Linear(h0, h1) folded to z1 = u s + c in FP64 (same summation order as the host fold in
+// pyves_set_bias_mlp), the third layer transposed, zero padding, the output bias at the end.  One thread per output.
+template <typename T>
+__global__ void __launch_bounds__(256) mlp_pack_kernel(const double* __restrict__ th, MlpPackPlan Q, T* __restrict__ theta_t,
+                                                       T* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < Q.np) theta_t[idx] = (T)th[idx];
+  const int p = idx - Q.np;
+  if (p < 0 || p >= Q.n_packed) return;
+  const int h0 = Q.h0, h1 = Q.h1, h2 = Q.h2;
+  const double* W0 = th + Q.w0;
+  const double* b0 = th + Q.b0;
+  const double* W1 = th + Q.w1;
+  const double* b1 = th + Q.b1;
+  auto fold_u = [&](int j) {
+    double su = 0.0;
+    for (int i = 0; i < h0; ++i) su = __dadd_rn(su, __dmul_rn(W1[j * h0 + i], W0[i]));   // unfused, as the host compiler rounds it
+    return su;
+  };
+  auto fold_c = [&](int j) {
+    double sc = b1[j];
+    for (int i = 0; i < h0; ++i) sc = __dadd_rn(sc, __dmul_rn(W1[j * h0 + i], b0[i]));
+    return sc;
+  };
+  double v = 0.0;
+  if (Q.H == 0) {                         // two hidden layers: u[Wp] c[Wp] wout[Wp] bout
+    const int Wp = Q.width, r = p / Wp, j = p - r * Wp;
+    if (p == 3 * Wp) v = th[Q.bo];
+    else if (p < 3 * Wp && j < h1) v = r == 0 ? fold_u(j) : (r == 1 ? fold_c(j) : th[Q.wo + j]);
+  } else {                                // three hidden layers: u[H] c[H] wout[H] b2[H] W2T[H][H] bout
+    const int H = Q.H;
+    if (p < 4 * H) {
+      const int r = p / H, j = p - r * H;
+      if (r == 0 && j < h1) v = fold_u(j);
+      else if (r == 1 && j < h1) v = fold_c(j);
+      else if (r == 2 && j < h2) v = th[Q.wo + j];
+      else if (r == 3 && j < h2) v = th[Q.b2 + j];
+    } else if (p < 4 * H + H * H) {
+      const int q = p - 4 * H, i = q / H, j = q - i * H;
+      if (i < h1 && j < h2) v = th[Q.w2 + j * h1 + i];      // transposed: W2T[i][j]
+    } else if (p == 4 * H + H * H) {
+      v = th[Q.bo];
+    }
+  }
+  packed[p] = (T)v;
+}
+
+template <typename T>
+cudaError_t launch_mlp_pack(const double* theta64, const MlpPackPlan& Q, T* theta_t, T* packed, cudaStream_t st) {
+  const int total = Q.np + Q.n_packed;
+  mlp_pack_kernel<T><<<(total + 255) / 256, 256, 0, st>>>(theta64, Q, theta_t, packed);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 #define PV_INST(T)                                                                                                 \
   template cudaError_t launch_eval_bias<T>(const T*, int64_t, int, T*, T*, const BiasAnyParams<T>&, cudaStream_t); \
   template cudaError_t launch_convert_weights2d<T>(const double*, int, int, T*, T*, cudaStream_t);                 \
   template cudaError_t launch_convert_weights1d<T>(const double*, int, T*, double*, cudaStream_t);                 \
+  template cudaError_t launch_mlp_pack<T>(const double*, const MlpPackPlan&, T*, T*, cudaStream_t);                \
   template cudaError_t launch_energies<T>(const T*, const T*, int64_t, int, T*, T*, T, T, const PotParams<T>&,     \
                                           const BiasAnyParams<T>&, cudaStream_t);                                  \
   template cudaError_t launch_init_positions<T>(T*, int64_t, int, uint64_t, const double*, double, int,            \

@@ -22,10 +22,31 @@ cudaError_t launch_convert_weights1d(const double* w64, int n, T* w_t, double* k
 //   mean = sum_wf / sum_w;  d = f_target - mean  (+ beta (sum_wff / sum_w - mean mean^T) (alpha - abar) when sum_wff)
 //   d *= scale (optional);  alpha' = alpha - mu d;  abar' = decay abar + (1 - decay) alpha'   (averaging 0, EWMA)
 //                                                   abar' = abar + (alpha' - abar) / (n + 1)  (averaging 1, running)
-// alpha_out / abar_out must not alias the inputs (the Hessian term reads every old entry).
+// alpha_out / abar_out must not alias the inputs (the Hessian term reads every old entry).  sum_w <= 0 (no sample
+// in the averaging domain): alpha and abar are copied through unchanged.
 cudaError_t launch_averaged_sgd_step(int K, const double* sum_w, const double* sum_wf, const double* sum_wff, const double* f_target,
                                      const double* alpha, const double* abar, const double* scale, double mu, double beta, int averaging,
                                      double decay, long long n_after, double* alpha_out, double* abar_out, cudaStream_t st);
+
+// torch.optim step on device-resident NN parameters (see optimizer_step_kernel).  a / b: SGD momentum | RMSprop alpha |
+// Adam beta1, beta2;  bc1 = 1 - beta1^t, bc2_sqrt = sqrt(1 - beta2^t) (Adam bias corrections, computed by the caller).
+struct OptHyper {
+  double lr, a, b, eps, bc1, bc2_sqrt;
+};
+cudaError_t launch_optimizer_step(int kind, long long P, const double* sum_w, const double* sum_wf, const double* f_target, int gavg,
+                                  double gdecay, long long n_avg, double* gstate, double* theta, double* s1, double* s2,
+                                  const OptHyper& H, long long t, cudaStream_t st);
+
+// layout of an NNBasis1D parameter vector (offsets into theta) and of the packed BiasMlp buffer it folds into
+struct MlpPackPlan {
+  int np;                 // parameters
+  int n_packed;           // elements of the packed buffer (0: no fast functor, only the converted copy is written)
+  int H, width;           // BiasMlp variant: H > 0 one H x H matmul; H == 0 streamed with padded width
+  int h0, h1, h2;
+  int w0, b0, w1, b1, w2, b2, wo, bo;
+};
+template <typename T>
+cudaError_t launch_mlp_pack(const double* theta64, const MlpPackPlan& Q, T* theta_t, T* packed, cudaStream_t st);
 
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>

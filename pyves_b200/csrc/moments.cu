@@ -576,11 +576,13 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp_kernel(const RowSourc
       if (r < rows) {
         const int64_t gr = r0 + r;
         const T q = (M.axis && S.ncols > 1) ? S.pos[gr * S.stride_row + S.stride_col] : S.pos[gr * S.stride_row];
-        const T wt = S.w != nullptr ? S.w[gr] : T(1);
+        T wt = S.w != nullptr ? S.w[gr] : T(1);
+        const T sq = (q - M.lo) * M.inv_range;
+        if (M.inside_only && !(sq >= T(0) && sq <= T(1))) wt = T(0);
         wsum += (double)wt;
         // forward.  h block l (offset hoff) = inputs of Linear l; d block l (offset doff) = its
         // outputs: first the activation gates are stashed there, then the deltas overwrite them.
-        h[r] = (q - M.lo) * M.inv_range;
+        h[r] = sq;
         const T* th = M.theta;
         int hoff = 0, doff = 0;
         for (int l = 0; l < L; ++l) {
@@ -765,6 +767,7 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSour
         const T q = (M.axis && S.ncols > 1) ? S.pos[gr * S.stride_row + S.stride_col] : S.pos[gr * S.stride_row];
         sv = (q - M.lo) * M.inv_range;
         wt = S.w != nullptr ? S.w[gr] : T(1);
+        if (M.inside_only && !(sv >= T(0) && sv <= T(1))) wt = T(0);   // conditional average on the support of the target
       }
       h[tid] = sv;
       wrow[tid] = wt;

@@ -34,6 +34,7 @@ template <typename T> struct MlpGradParams {
   T lo, inv_range;
   const T* theta;      // device, torch parameter order
   int n_params;
+  int inside_only;     // 1: rows whose scaled coordinate leaves [0, 1] (the support of the target) get weight 0
 };
 
 // scratch must hold moments_scratch_doubles(K, cov) doubles

@@ -13,8 +13,10 @@ New keywords: ``n_walkers`` (ensemble size; sharded over the ranks of an initial
 ('openmm_langevin' | 'middle'), ``dims`` (2 drops the decoupled z coordinate, 3 keeps it),
 ``traj_walkers`` (how many walkers are recorded), ``sample_every`` (moment sampling stride of the
 ensemble VES update), ``device_update`` (keep optimiser state and coefficients of a ``VESBias_Ensemble`` on the
-GPU between updates, ``bias.DeviceUpdater``; the bias object is synchronised when the run returns and the
-per-update ``model_loc.iter{n}`` archive is not written).  With ``n_walkers=1`` the behaviour and file contents follow the reference:
+GPU between updates, ``bias.DeviceUpdater``; the bias object is synchronised when the run returns and at every
+checkpoint; the per-update ``model_loc.iter{n}`` archive is written only with ``archive_updates=True``, which costs a
+synchronisation per update).  Checkpoints of a dynamic ``VESBias_Ensemble`` run carry the whole update state
+(``State``), and a run resumed from one continues the update cadence on the global loop index.  With ``n_walkers=1`` the behaviour and file contents follow the reference:
 frame ``t`` is the position before step ``t`` (``:180-188``), ``bias.update(self.traj)`` runs at
 ``i == startafter`` and then whenever ``i % learnevery == 0`` (``:134-159``).
 """
@@ -33,14 +35,23 @@ KB = 8.31446261815324e-3      # kJ/mol/K as OpenMM defines it (the integrator's 
 
 
 class State:
-    """Picklable snapshot (replaces ``openmm.State``): positions / velocities [n_walkers, dims]."""
+    """Picklable snapshot (replaces ``openmm.State``): positions / velocities [n_walkers, dims], the Philox step
+    counter and seed, and -- for a dynamic ``VESBias_Ensemble`` -- the whole update state (``bias.state_dict()``:
+    coefficients / NN parameters, optimiser iterates and averages, gradient running average, target density, update
+    count), the loop index of the run and of its last update, and the moment sums sampled since that update.  A run
+    resumed from it (``init_state=``, then ``init_ves`` with a bias of the same construction) continues the
+    uninterrupted run exactly (tested bit for bit in FP64)."""
 
-    def __init__(self, positions, velocities, step, seed, walker_offset=0):
+    def __init__(self, positions, velocities, step, seed, walker_offset=0, loop_step=0, last_update_step=None, bias_state=None, pending=None):
         self.positions = np.asarray(positions)
         self.velocities = np.asarray(velocities)
         self.step = int(step)
         self.seed = int(seed)
         self.walker_offset = int(walker_offset)
+        self.loop_step = int(loop_step)
+        self.last_update_step = last_update_step
+        self.bias_state = bias_state
+        self.pending = pending
 
     def getPositions(self, asNumpy=True):
         return self.positions
@@ -73,7 +84,8 @@ class SingleParticleSimulation:
                  traj_walkers: int = 1,
                  sample_every: int = None,
                  process_group=None,
-                 device_update: bool = False):
+                 device_update: bool = False,
+                 archive_updates: bool = False):
         # units as upstream: Da, K, 1/ps, fs
         self.mass = float(mass)
         self.temp = float(temp)
@@ -94,6 +106,8 @@ class SingleParticleSimulation:
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", 0)) if self.world > 1 else torch.cuda.current_device()
         self.device = device
+        # the bias objects create their evaluator handles and CUDA tensors on the CURRENT device: make it this rank's
+        torch.cuda.set_device(self.device)
         self.seed = int.from_bytes(os.urandom(7), "little") if seed is None else int(seed)
         if init_state is not None:
             self.seed = getattr(init_state, "seed", self.seed) if seed is None else self.seed
@@ -127,8 +141,11 @@ class SingleParticleSimulation:
         self.traj_walkers = max(1, min(int(traj_walkers), self.n_walkers))
         self.sample_every = sample_every
         self.device_update = bool(device_update)
+        self.archive_updates = bool(archive_updates)       # device_update: also write model_loc + ".iter{n}" per update (costs a sync)
         self._updater = None
         self.biased = False
+        self._g0 = 0                    # loop index this run continues from (set by init_ves when the state carries a bias)
+        self._last_update_step = None
 
     # ------------------------------------------------------------------------------------------------
     def _cols(self, a):
@@ -147,9 +164,18 @@ class SingleParticleSimulation:
         ensemble_init_coord(self.ens, self.temp, ntrials, xmin, xmax, ymin, ymax)
         self.ens.init_velocities()
 
-    def get_state(self):
+    def get_state(self, loop_step=0):
         pos, vel = self.ens.get_state(host=True)
-        return State(pos.T.copy(), vel.T.copy(), self.ens.step_counter, self.seed, self.walker_offset)
+        bias_state = pending = None
+        if self.biased and not self.static and hasattr(self.bias, "state_dict"):
+            if self._updater is not None:
+                self._updater.sync_to_host()                          # device-resident optimiser state -> bias object
+            bias_state = self.bias.state_dict()
+            if getattr(self, "_acc", None) is not None:
+                pending = dict(acc=[None if t is None else t.detach().cpu().numpy().copy() for t in self._acc],
+                               sampled_at=getattr(self, "_sampled_at", None))
+        return State(pos.T.copy(), vel.T.copy(), self.ens.step_counter, self.seed, self.walker_offset, loop_step=loop_step,
+                     last_update_step=self._last_update_step, bias_state=bias_state, pending=pending)
 
     # ------------------------------------------------------------------------------------------------
     def init_ves(self, bias: Bias, static: bool = False, startafter: int = 2, learnevery: int = 50):
@@ -168,15 +194,36 @@ class SingleParticleSimulation:
         self.bias = bias
         self.update_on = False
         self._updater = None
+        self._g0, self._last_update_step, self._pending0 = 0, None, None
+        st = getattr(self, "init_state", None)
+        if not static and getattr(st, "bias_state", None) is not None and hasattr(bias, "load_state_dict"):
+            # continuation of a checkpointed dynamic run: restore the update state and keep the update cadence on the
+            # global loop index (the reference restarts both, ves/langevin_dynamics.py:75-76 resumes positions only)
+            bias.load_state_dict(st.bias_state)
+            self._g0 = int(st.loop_step)
+            self._last_update_step = st.last_update_step
+            self._pending0 = st.pending
 
     # ------------------------------------------------------------------------------------------------
+    def _attach_ensemble_bias(self):
+        """The bias starts acting (ves/langevin_dynamics.py:141-145): defines the basis for the moment kernels."""
+        if self._attached:
+            return
+        if self.device_update and self._updater is None and DeviceUpdater.supports(self.bias):
+            self._updater = DeviceUpdater(self.bias, self.ens)    # optimiser state + coefficients stay on the GPU
+        else:
+            self.bias.force.apply(self.ens)
+        self._attached = True
+
+    def _archive_device_update(self):
+        if self.archive_updates and self.bias.model_loc is not None:
+            self._updater.sync_to_host()
+            self.bias._export(self.bias.model_loc, self.bias.model_loc + ".iter{}".format(self.bias.n_updates))
+
     def _update_bias(self, i, ves_update_params):
+        self._last_update_step = i
         if isinstance(self.bias, VESBias_Ensemble):
-            if i == self.startafter:
-                if self.device_update and self._updater is None and DeviceUpdater.supports(self.bias):
-                    self._updater = DeviceUpdater(self.bias, self.ens)    # optimiser state + coefficients stay on the GPU
-                else:
-                    self.bias.force.apply(self.ens)  # defines the basis for the moment kernels; forces start now
+            self._attach_ensemble_bias()
             if self._updater is not None and self._acc is None:
                 # lean path: moments into the updater's persistent flat buffer, ONE in-place all-reduce, one optimiser
                 # kernel, coefficient hand-over -- four library calls and one NCCL call per update, nothing else
@@ -184,12 +231,14 @@ class SingleParticleSimulation:
                 self.ens.moments(cov=self.bias.needs_covariance, out=bufs)
                 self._updater.reduce_flat(self.process_group)
                 self._updater.update(*bufs)
+                self._archive_device_update()
                 return
             self._sample_moments()
             sw, sf, sff = reduce_moments(*self._acc, group=self.process_group)   # one allreduce per update
             self._acc = None
             if self._updater is not None:
                 self._updater.update(sw, sf, sff)                         # enqueue only: no host round trip
+                self._archive_device_update()
                 return
             self.bias.update_from_moments(sw, sf, sff)
         else:
@@ -216,11 +265,13 @@ class SingleParticleSimulation:
             if every:
                 nxt = min(nxt, (i // every + 1) * every)
         if self.biased and not self.static:
-            if i < self.startafter:
-                nxt = min(nxt, self.startafter)
-            nxt = min(nxt, max((i // self.learnevery + 1) * self.learnevery, self.startafter + 1))
+            g0 = self._g0
+            g = g0 + i                                   # update cadence runs on the global loop index
+            if g < self.startafter:
+                nxt = min(nxt, self.startafter - g0)
+            nxt = min(nxt, max((g // self.learnevery + 1) * self.learnevery, self.startafter + 1) - g0)
             if isinstance(self.bias, VESBias_Ensemble) and self.sample_every:
-                nxt = min(nxt, (i // self.sample_every + 1) * self.sample_every)
+                nxt = min(nxt, (g // self.sample_every + 1) * self.sample_every - g0)
         return nxt
 
     def __call__(self,
@@ -236,6 +287,16 @@ class SingleParticleSimulation:
         self.PE = []
         self.KE = []
         self._acc = None
+        self._attached = False
+        g0 = self._g0
+        if self.biased and not self.static and g0 > 0 and isinstance(self.bias, VESBias_Ensemble):
+            # continuation: the bias was already acting when the checkpoint was written
+            if g0 > self.startafter or self._last_update_step == g0:
+                self._attach_ensemble_bias()
+            if self._pending0 is not None:
+                dev = torch.device("cuda", self.device)
+                self._acc = [None if a is None else torch.as_tensor(a, device=dev) for a in self._pending0["acc"]]
+                self._sampled_at = self._pending0["sampled_at"]
         self._traj_written = 0
         self.traj_ensemble = None
         frames = []
@@ -255,22 +316,25 @@ class SingleParticleSimulation:
                 # ---- VES bookkeeping at iteration i (ves/langevin_dynamics.py:134-169)
                 if self.biased:
                     if not self.static:
-                        if i == self.startafter:
-                            print("[VES] {} bias: Initializing dynamic bias at timestep {}.".format(type(self.bias).__name__, i))
+                        g = g0 + i
+                        if g == self._last_update_step and i == 0 and g0 > 0:
+                            pass                                    # the checkpoint was written after the update at this index
+                        elif g == self.startafter:
+                            print("[VES] {} bias: Initializing dynamic bias at timestep {}.".format(type(self.bias).__name__, g))
                             self._sync_traj(frames)
-                            self._update_bias(i, ves_update_params)
-                        elif i > self.startafter and i % self.learnevery == 0:
-                            print("[VES] {} bias: Updating dynamic bias at timestep {}.".format(type(self.bias).__name__, i))
+                            self._update_bias(g, ves_update_params)
+                        elif g > self.startafter and g % self.learnevery == 0:
+                            print("[VES] {} bias: Updating dynamic bias at timestep {}.".format(type(self.bias).__name__, g))
                             self._sync_traj(frames)
-                            self._update_bias(i, ves_update_params)
-                        elif (isinstance(self.bias, VESBias_Ensemble) and self.sample_every and i > self.startafter
-                              and i % self.sample_every == 0):
+                            self._update_bias(g, ves_update_params)
+                        elif (isinstance(self.bias, VESBias_Ensemble) and self.sample_every and g > self.startafter
+                              and g % self.sample_every == 0):
                             self._sample_moments()
                     elif i == 0:
                         print("[VES] {} bias: Initializing static bias.".format(type(self.bias).__name__))
                         self.bias.force.apply(ens)
                 if i > 0 and chkevery and i % chkevery == 0:
-                    self._dump_state(chkfile, i)
+                    self._dump_state(chkfile, i, loop_step=g0 + i)
                 if energyevery and i % energyevery == 0:
                     PE, KE = ens.energies(host=True)
                     self.PE.append(float(PE[0]) if self.n_walkers_total == 1 else float(np.mean(PE)))
@@ -298,6 +362,9 @@ class SingleParticleSimulation:
                 if len(frames) >= 64:
                     self._sync_traj(frames)
             self._sync_traj(frames)
+            # Finalize: checkpoint named after the last loop index, as upstream (:195); written while the device-resident
+            # update state is still alive so that it carries the optimiser
+            self._dump_state(chkfile, max(i_last - 1, 0), loop_step=g0 + i_last)
         finally:
             if getattr(self, "_updater", None) is not None:       # coefficients, optimiser state, target back to the bias object
                 self._updater.sync_to_host()
@@ -310,8 +377,6 @@ class SingleParticleSimulation:
                 ftraj.close()
             if fener:
                 fener.close()
-        # Finalize: checkpoint named after the last loop index, as upstream (:195)
-        self._dump_state(chkfile, max(i_last - 1, 0))
 
     # ------------------------------------------------------------------------------------------------
     def _sync_traj(self, frames):
@@ -341,11 +406,11 @@ class SingleParticleSimulation:
                 ftraj.write("{:10.5f}\t{:10.7f}\t{:10.7f}\t{:10.7f}\n".format((k0 + k) * trajevery * self.dt_ps, p[0], p[1], z))
         self._traj_written += new.shape[0]
 
-    def _dump_state(self, ofilename, i):
+    def _dump_state(self, ofilename, i, loop_step=None):
         t = i * self.dt_ps
         print("Checkpoint at {:10.7f} ps".format(t))
         if not ofilename:
             return
         name = ofilename if self.world == 1 else "{}.rank{}".format(ofilename, self.rank)
         with open(name, "wb") as fh:
-            pickle.dump(self.get_state(), fh)
+            pickle.dump(self.get_state(loop_step=i if loop_step is None else loop_step), fh)

@@ -11,8 +11,15 @@ is against ``oracle/ves.py`` (literature restatement), not against reference cod
 import numpy as np
 
 
+class EmptyEnsembleAverage(ValueError):
+    """The ensemble average has no sample (sum of weights <= 0)."""
+
+
 def gradient_hessian(sum_w, sum_wf, sum_wff, f_target, beta):
-    """(gradient [K], Hessian [K, K] or None) from ensemble moments and target averages."""
+    """(gradient [K], Hessian [K, K] or None) from ensemble moments and target averages.  ``sum_w <= 0`` (no
+    sample in the averaging domain, e.g. every walker outside the basis box) raises ``EmptyEnsembleAverage``."""
+    if not float(sum_w) > 0.0:
+        raise EmptyEnsembleAverage("sum of the row weights is %r: no walker inside the averaging domain" % float(sum_w))
     mean = np.asarray(sum_wf, dtype=np.float64) / float(sum_w)
     grad = np.asarray(f_target, dtype=np.float64) - mean
     hess = None
@@ -67,6 +74,8 @@ class AveragedSGD:
                     averaging=self.averaging, decay=self.decay, n=self.n)
 
     def load_state_dict(self, d):
+        if len(d["alpha"]) != len(self.alpha):
+            raise ValueError("checkpointed coefficients do not match the basis size")
         self.alpha = np.array(d["alpha"], dtype=np.float64)
         self.abar = np.array(d["abar"], dtype=np.float64)
         self.mu, self.second_order, self.n = float(d["mu"]), bool(d["second_order"]), int(d["n"])

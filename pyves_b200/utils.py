@@ -26,10 +26,13 @@ class TrajectoryReader:
         return np.array(rows)
 
     def read_traj(self, skip=1):
-        """(times [T], coordinates [T, 3])"""
-        data = self._rows(skip)
-        if self.format != 'txyz':
+        """``format='txyz'``: (times [T], coordinates [T, 3]); ``format='xyz'``: coordinates [T, 3] only
+        (``ves/utils.py:37-40,53-69``)."""
+        if self.format not in ('txyz', 'xyz'):
             raise ValueError("Invalid format")
+        data = self._rows(skip)
+        if self.format == 'xyz':
+            return data[:, 0:3]
         return data[:, 0], data[:, 1:4]
 
     def read_energies(self, skip=1):

@@ -411,14 +411,16 @@ def test_chunked_handles_async_copies_match_single_handle():
     for e in subs[1:]:
         upd.add_handle(e)
     main = torch.cuda.current_stream()
+    # per-chunk moment buffers allocated once on the main stream and written through out=: nothing allocated on a side
+    # stream is consumed on the main stream (the caching allocator could recycle such a block too early)
+    mom = [(torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros(256, dtype=torch.float64, device="cuda"), None) for _ in range(nch)]
     for _ in range(iters):
-        mom = []
         for c in range(nch):
             streams[c].wait_stream(main)
             with torch.cuda.stream(streams[c]):
                 subs[c].set_state(hp[c], hv[c], async_copy=True)
                 subs[c].step(stride)
-                mom.append(subs[c].moments())
+                subs[c].moments(out=mom[c])
                 subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)
         for c in range(nch):
             main.wait_stream(streams[c])

@@ -48,7 +48,7 @@ def rng_spec(kind, rng, **kw):
 # ---------------------------------------------------------------------------------------------------
 def test_abi_version_and_errors():
     lib = _lib.load()
-    assert lib.pyves_abi_version() == 1
+    assert lib.pyves_abi_version() == 2
     with pytest.raises(ValueError):
         _lib.Ensemble(0)
     with pytest.raises(ValueError):

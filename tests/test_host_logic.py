@@ -28,7 +28,7 @@ def test_abi_header_binding_and_library_agree():
     lib = _lib.load()                       # dlopen only; no compute call without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pyves_abi_version() == 1
+    assert lib.pyves_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (pyves_[a-z0-9_]+)", out))
     assert exported == declared, exported ^ declared
@@ -187,8 +187,16 @@ def test_ensemble_bias_host_logic_without_gpu():
         assert d.kind == "legendre2d" and d.moment_inside is flag
         assert bias.DeviceUpdater.supports(b)
     assert bias.StaticBias_SingleParticle(m2, None).force.moment_inside is None      # static biases leave the domain alone
+    # NN bases: SGD / RMSprop / Adam in their plain form run on the device; options the kernel lacks stay on the host
     nn = basis.NNBasis1D(-4, 4, hidden_layer_sizes=[8, 8])
-    assert not bias.DeviceUpdater.supports(bias.VESBias_Ensemble(nn, target.Target_Uniform_HardSwitch_x(50), 1 / kT, "Adam", {"lr": 1e-3}))
+    tx = target.Target_Uniform_HardSwitch_x(50)
+    for opt, prm in (("Adam", {"lr": 1e-3}), ("SGD", {"lr": 1e-2, "momentum": 0.5}), ("RMSprop", {"lr": 1e-3}),
+                     ("Adam", {"lr": 1e-3, "betas": (0.8, 0.99), "eps": 1e-6})):
+        assert bias.DeviceUpdater.supports(bias.VESBias_Ensemble(nn, tx, 1 / kT, opt, prm, gradient_average='running'))
+    for opt, prm in (("Adam", {"lr": 1e-3, "amsgrad": True}), ("Adam", {"lr": 1e-3, "weight_decay": 1e-2}), ("SGD", {"lr": 1e-2, "nesterov": True, "momentum": 0.5}),
+                     ("RMSprop", {"lr": 1e-3, "centered": True})):
+        assert bias.DeviceUpdater.why_not(bias.VESBias_Ensemble(nn, tx, 1 / kT, opt, prm)) is not None
+    assert not bias.DeviceUpdater.supports(bias.VESBias_Ensemble(basis.NNBasis1D(-4, 4, hidden_layer_sizes=[8]), tx, 1 / kT, "Adam", {"lr": 1e-3}))
     assert not bias.DeviceUpdater.supports(bias.VESBias_Ensemble(m2, target.Target_Uniform_2D(8, 8), 1 / kT, "averaged_sgd", sgd,
                                                                  gradient_average='running'))
     # path CV: uniform target on [-1, 1] -> <P_k>_p = delta_k0 (trapezoid rule on 2001 nodes); well-tempered refresh
@@ -327,3 +335,92 @@ def test_histogram_fes_semantics():
     est[3] = 0.0                                                # ... and bins above the clip are ignored
     assert fes.rmse_kt(est, ref, clip=20.0) < 1e-12
     assert abs(fes.rmse_kt(ref + np.array([0.0, 0.3, 0.0, 0.0]), ref, clip=20.0) - 0.3 / np.sqrt(3)) < 1e-12
+
+
+def test_update_state_checkpoint_round_trip_without_gpu():
+    """bias.state_dict() / load_state_dict(): averaged-SGD iterates and averages, torch.optim state, gradient running
+    average, target density and update count survive a pickle round trip into a freshly constructed bias (SURVEY 8(f3);
+    the reference archives only the TorchScript module, ves/bias.py:249-253)."""
+    import pickle
+    import torch
+    from pyves_b200 import basis, bias, target
+    from pyves_b200.langevin_dynamics import State
+    kT = 8.3145e-3 * 300
+    rng = np.random.default_rng(1)
+
+    def make_leg():
+        return bias.VESBias_Ensemble(basis.LegendreBasis1D(6, -2.5, 2.5, weights=np.zeros(7)), target.Target_WellTempered_x(101, 5.0), 1 / kT,
+                                     "averaged_sgd", {"mu": 0.7, "second_order": True, "averaging": "running"})
+    a = make_leg()
+    a._f_target = rng.standard_normal(7)              # stands in for the device quadrature (no GPU here)
+    for _ in range(5):
+        g = rng.standard_normal(7)
+        a.optimizer.step(g, np.eye(7) * 0.1)
+    a.n_updates = 5
+    a.target._p = rng.uniform(0.2, 0.8, 101)
+    st = State(np.zeros((4, 2)), np.zeros((4, 2)), 1234, 7, loop_step=600, last_update_step=600, bias_state=a.state_dict(),
+               pending=[np.ones(1), np.arange(7.0), None])
+    st2 = pickle.loads(pickle.dumps(st))
+    assert st2.loop_step == 600 and st2.last_update_step == 600 and st2.step == 1234 and st2.pending[2] is None
+    b = make_leg()
+    b.load_state_dict(st2.bias_state)
+    assert np.array_equal(b.optimizer.alpha, a.optimizer.alpha) and np.array_equal(b.optimizer.abar, a.optimizer.abar)
+    assert b.optimizer.n == 5 and b.n_updates == 5 and np.array_equal(b.target.p, a.target.p) and np.array_equal(b._f_target, a._f_target)
+    g = rng.standard_normal(7)
+    assert np.array_equal(a.optimizer.step(g, np.eye(7)), b.optimizer.step(g, np.eye(7)))      # continues identically
+    with pytest.raises(ValueError, match="optimizer"):
+        bias.VESBias_Ensemble(basis.NNBasis1D(-4, 4, hidden_layer_sizes=[8, 8]), target.Target_Uniform_HardSwitch_x(50), 1 / kT, "Adam",
+                              {"lr": 1e-3}).load_state_dict(st2.bias_state)
+
+    def make_nn():
+        torch.manual_seed(3)
+        return bias.VESBias_Ensemble(basis.NNBasis1D(-4, 4, hidden_layer_sizes=[8, 8]), target.Target_Uniform_HardSwitch_x(50), 1 / kT, "Adam",
+                                     {"lr": 1e-3}, gradient_average=0.9)
+    c = make_nn()
+    for _ in range(3):
+        grad = c.grad_avg.update(rng.standard_normal(105))
+        c.optimizer.zero_grad()
+        bias._set_grads(c.model, grad)
+        c.optimizer.step()
+    c.n_updates = 3
+    d = make_nn()
+    d.load_state_dict(pickle.loads(pickle.dumps(c.state_dict())))
+    g = rng.standard_normal(105)
+    for x in (c, d):
+        x.optimizer.zero_grad()
+        bias._set_grads(x.model, x.grad_avg.update(g))
+        x.optimizer.step()
+    for p, q in zip(c.model.parameters(), d.model.parameters()):
+        assert torch.equal(p, q)
+    assert d.grad_avg.n == 4
+
+
+def test_empty_ensemble_average_skips_the_update():
+    """sum_w == 0 (every walker outside the basis box with sample_domain='box'): the host update changes nothing and
+    warns, the same rule the device kernels apply (averaged_sgd_kernel / optimizer_step_kernel)."""
+    from pyves_b200 import basis, bias, optim, target
+    kT = 8.3145e-3 * 300
+    b = bias.VESBias_Ensemble(basis.LegendreBasis1D(4, -1, 1, weights=np.array([0.0, 1.0, 0.5, 0.0, -0.2])), target.Target_Uniform_HardSwitch_x(11),
+                              1 / kT, "averaged_sgd", {"mu": 0.5})
+    b._f_target = np.array([1.0, 0, 0, 0, 0])
+    before = (b.optimizer.alpha.copy(), b.optimizer.abar.copy())
+    with pytest.warns(UserWarning, match="VES update skipped"):
+        b.update_from_moments(np.zeros(1), np.zeros(5), None)
+    assert np.array_equal(b.optimizer.alpha, before[0]) and np.array_equal(b.optimizer.abar, before[1]) and b.n_updates == 1
+    with pytest.raises(optim.EmptyEnsembleAverage):
+        optim.gradient_hessian(0.0, np.zeros(5), None, np.zeros(5), 1 / kT)
+
+
+def test_trajectory_reader_formats(tmp_path):
+    """TrajectoryReader: 'txyz' -> (t, xyz), 'xyz' -> xyz only (ves/utils.py:37-40), anything else raises before reading."""
+    from pyves_b200.utils import TrajectoryReader
+    f = tmp_path / "t.dat"
+    f.write_text("# t x y z\n0.0 1 2 3\n0.1 4 5 6\n0.2 7 8 9\n")
+    t, xyz = TrajectoryReader(str(f)).read_traj()
+    assert t.tolist() == [0.0, 0.1, 0.2] and xyz.shape == (3, 3) and xyz[2].tolist() == [7, 8, 9]
+    g = tmp_path / "x.dat"
+    g.write_text("# x y z\n1 2 3\n4 5 6\n")
+    assert TrajectoryReader(str(g), format='xyz').read_traj().tolist() == [[1, 2, 3], [4, 5, 6]]
+    assert TrajectoryReader(str(f)).read_traj(skip=2)[1].shape == (2, 3)
+    with pytest.raises(ValueError, match="Invalid format"):
+        TrajectoryReader(str(tmp_path / "missing.dat"), format='tx').read_traj()
