@@ -248,6 +248,12 @@ class VESBias_Ensemble(NNBias):
         model_loc: TorchScript export path or None.
         target_update_every: refresh a well-tempered target every this many updates.
         gradient_average: None, ``'running'`` or a decay in (0, 1) for an exponentially weighted mean.
+        bias_average: None or a decay d in (0, 1): keep ``V_avg <- d V_avg + (1 - d) (V - mean V)`` of the bias at the
+            target nodes over the updates and read the free energy from it (``fes()``).  Averaged SGD applies and reads
+            the AVERAGED coefficients; a ``torch.optim`` optimiser on an NN has no such average, its bias jitters around
+            the optimum with the step size, and the update-averaged bias is the estimator with the same role
+            (measured on configs[3], ``profiles/r02_nn_ves_convergence.md``: 0.03-0.05 kT against 0.13-0.15 kT for the
+            instantaneous bias).
         sample_domain: ``'box'`` (default) -- <f>_V is the average over the walkers INSIDE the basis interval
             (the support of the target), so walkers that wander outside, where the scaled coordinate clamps
             (``ves/basis.py:143``), do not pile up on the edge of the histogram the bias is matched to;
@@ -257,7 +263,7 @@ class VESBias_Ensemble(NNBias):
     """
 
     def __init__(self, V_module, target, beta, optimizer_type='averaged_sgd', optimizer_params=None, model_loc=None,
-                 target_update_every=10, gradient_average=None, sample_domain='box'):
+                 target_update_every=10, gradient_average=None, sample_domain='box', bias_average=None):
         if sample_domain not in ('box', 'all'):
             raise ValueError("sample_domain must be 'box' or 'all'")
         self.sample_domain = sample_domain
@@ -289,6 +295,10 @@ class VESBias_Ensemble(NNBias):
             self.grad_avg = None
         else:
             self.grad_avg = RunningAverage(None if gradient_average == 'running' else float(gradient_average))
+        if bias_average is not None and not 0.0 < float(bias_average) < 1.0:
+            raise ValueError("bias_average must be a decay in (0, 1)")
+        self.bias_average = None if bias_average is None else float(bias_average)
+        self._V_avg = None               # exponentially weighted mean over the updates of the (mean-free) bias at the target nodes
         self.n_updates = 0
         self._f_target = None
         self.last_gradient = None
@@ -387,6 +397,10 @@ class VESBias_Ensemble(NNBias):
             _set_grads(self.model, grad)
             self.optimizer.step()
         self.n_updates += 1
+        if self.bias_average is not None:
+            V = self._bias_at_nodes()
+            V = V - V.mean()
+            self._V_avg = V if self._V_avg is None else self.bias_average * self._V_avg + (1.0 - self.bias_average) * V
         if self.target_update_every > 0 and self.n_updates % self.target_update_every == 0:
             self.refresh_target()
         if self.model_loc is not None:
@@ -411,7 +425,8 @@ class VESBias_Ensemble(NNBias):
                  model=[p.detach().cpu().numpy().copy() for p in self.model.parameters()],
                  target_p=np.array(self.target.p, dtype=np.float64, copy=True),
                  f_target=None if self._f_target is None else np.array(self._f_target, dtype=np.float64, copy=True),
-                 sgd_steps=int(getattr(self, "_sgd_steps", 0)))
+                 sgd_steps=int(getattr(self, "_sgd_steps", 0)),
+                 V_avg=None if self._V_avg is None else np.array(self._V_avg, dtype=np.float64, copy=True))
         if self.optimizer_type == 'averaged_sgd':
             d["optimizer"] = self.optimizer.state_dict()
         else:
@@ -437,19 +452,29 @@ class VESBias_Ensemble(NNBias):
             raise ValueError("checkpointed target density does not match the target mesh")
         self.target._p = np.array(d["target_p"], dtype=np.float64, copy=True)
         self._f_target = None if d.get("f_target") is None else np.array(d["f_target"], dtype=np.float64, copy=True)
+        self._V_avg = None if d.get("V_avg") is None else np.array(d["V_avg"], dtype=np.float64, copy=True)
         if self.grad_avg is not None and "grad_avg" in d:
             self.grad_avg.n = int(d["grad_avg"]["n"])
             v = d["grad_avg"]["value"]
             self.grad_avg.value = None if v is None else np.array(v, dtype=np.float64, copy=True)
 
-    def fes(self, nodes_scaled=None):
-        """F(s) = -V(s) - (1/beta) ln p(s) at the target nodes, shifted to min 0 (kJ/mol)."""
+    def _bias_at_nodes(self):
+        """Bias energy at the target nodes (numpy, kJ/mol)."""
         if isinstance(self.model, LegendreBasis2DPathCV):
-            F = -self._pathcv_bias_at_nodes() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
-            return F - F.min()
+            return self._pathcv_bias_at_nodes()
         ens, tpos = _device_eval(self.model, self._target_positions())
         V, _ = ens.eval_bias(tpos, want_force=False)
-        F = -V.cpu().numpy() - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
+        return V.cpu().numpy()
+
+    def fes(self, nodes_scaled=None, averaged=None):
+        """F(s) = -V(s) - (1/beta) ln p(s) at the target nodes, shifted to min 0 (kJ/mol).  ``averaged``: read V from the
+        update-averaged bias (default: whenever ``bias_average`` is set and at least one update was made)."""
+        if averaged is None:
+            averaged = self._V_avg is not None
+        if averaged and self._V_avg is None:
+            raise ValueError("no averaged bias: construct the bias with bias_average=decay and run updates")
+        V = self._V_avg if averaged else self._bias_at_nodes()
+        F = -V - np.log(np.maximum(self.target.p, 1e-300)) / self.beta
         return F - F.min()
 
 
@@ -547,6 +572,7 @@ class DeviceUpdater:
             self.trap = torch.tensor(tw, **f64)
         self.handles = [ens]                 # every handle that receives the parameters (add_handle)
         self._flat = None
+        self.V_avg = None if bias._V_avg is None else torch.tensor(bias._V_avg, **f64)
         if self.nn:
             self._init_nn(f64)
         else:
@@ -655,6 +681,7 @@ class DeviceUpdater:
         for hdl in self.handles:
             self._upload(hdl)
         self._upload(self.ev)
+        self._average_bias(uploaded=True)
         b = self.bias
         if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
             self.p = self._refreshed_density()
@@ -672,10 +699,22 @@ class DeviceUpdater:
         self.n_updates += 1
         for hdl in self.handles:
             self._upload(hdl)
+        self._average_bias(uploaded=False)
         b = self.bias
         if self.refreshable and b.target_update_every > 0 and self.n_updates % b.target_update_every == 0:
             self.p = self._refreshed_density()
             self.f_target = self._target_average()
+
+    def _average_bias(self, uploaded):
+        """VESBias_Ensemble's ``bias_average`` on the device: EWMA over the updates of the mean-free bias at the target nodes."""
+        d = self.bias.bias_average
+        if d is None:
+            return
+        if not uploaded:
+            self._upload(self.ev)
+        V, _ = self.ev.eval_bias(self.tpos, want_force=False)
+        V = V - V.mean()
+        self.V_avg = V if self.V_avg is None else d * self.V_avg + (1.0 - d) * V
 
     def moment_buffers(self, cov=None):
         """Views (sum_w, sum_wf, sum_wff or None) of ONE persistent flat FP64 buffer for ``ens.moments(out=...)``:
@@ -751,6 +790,7 @@ class DeviceUpdater:
         if self.refreshable:
             b.target._p = self.p.cpu().numpy().copy()
         b._f_target = self.f_target.cpu().numpy().copy()
+        b._V_avg = None if self.V_avg is None else self.V_avg.cpu().numpy().copy()
 
     def close(self):
         self.ev.close()

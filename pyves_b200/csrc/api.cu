@@ -541,7 +541,7 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
   }
   S.w = static_cast<const T*>(w);
   const int64_t K = basis_size(h);
-  int rc = ensure_scratch(h, moments_scratch_doubles(K, sum_wff != nullptr));
+  int rc = ensure_scratch(h, moments_scratch_doubles(K, sum_wff != nullptr, S.n, S.w != nullptr));
   if (rc) return rc;
   int launches = 0;
   if (h->bias_kind == PYVES_BIAS_MLP_1D) {
@@ -759,6 +759,10 @@ int pyves_set_tuning(pyves_t* h, int variant) {
   if (!h) return PYVES_EINVAL;
   if (variant == 98 || variant == 97) {   // 98: covariance on CUDA cores only; 97: tensor cores allowed again
     set_no_tensor_cores(variant == 98);
+    return PYVES_OK;
+  }
+  if (variant >= 1000 && variant <= 1030) {   // rows per CTA of the tensor-core covariance: 2^(variant - 1000)
+    cov_tc_set_max_rows((int64_t)1 << (variant - 1000));
     return PYVES_OK;
   }
   h->variant = variant;

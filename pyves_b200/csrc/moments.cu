@@ -437,7 +437,7 @@ static int cov_chunks(int64_t n, int rows_per_tile, int npt) {
   return (int)g;
 }
 
-size_t moments_scratch_doubles(int64_t K, bool cov) {
+size_t moments_scratch_doubles(int64_t K, bool cov, int64_t n, bool weighted) {
   size_t first = (size_t)kMaxBlocks * (size_t)(K + 1);
   if (!cov) return first;
   const int K64 = (int)((K + kPairTile - 1) / kPairTile);
@@ -446,7 +446,7 @@ size_t moments_scratch_doubles(int64_t K, bool cov) {
   if (g < 1) g = 1;
   size_t total = first + (size_t)g * npt * kPairTile * kPairTile;
   if (K > 64 && K <= 4096) {   // room for the tensor-core path's FP32 partial tiles
-    const size_t tc = first + (cov_tc_scratch_floats(kMaxSmForScratch) + 1) / 2;
+    const size_t tc = first + (cov_tc_scratch_floats((int)K, n, kMaxSmForScratch, weighted) + 1) / 2;
     if (tc > total) total = tc;
   }
   return total;

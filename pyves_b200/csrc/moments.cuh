@@ -37,19 +37,21 @@ template <typename T> struct MlpGradParams {
   int inside_only;     // 1: rows whose scaled coordinate leaves [0, 1] (the support of the target) get weight 0
 };
 
-// scratch must hold moments_scratch_doubles(K, cov) doubles
-size_t moments_scratch_doubles(int64_t K, bool cov);
+// scratch must hold moments_scratch_doubles(K, cov, n, weighted) doubles (n rows, with / without row weights)
+size_t moments_scratch_doubles(int64_t K, bool cov, int64_t n, bool weighted);
 
 template <typename T>
 cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B, double* sum_w, double* sum_wf,
                                  double* sum_wff, double* scratch, cudaStream_t st, int* launches);
 
-// tcgen05 / TF32 covariance (cov_tc.cu): used for FP32 handles, unit row weights, 2D Legendre bases with
-// 64 < K <= 4096; everything else runs moments_small_kernel / moments2_kernel on the CUDA cores.
+// tcgen05 covariance (cov_tc.cu, FP16 operand tiles = the 10-bit mantissa of TF32 on |f| <= 1, FP32 accumulate): used
+// for FP32 handles and 2D Legendre bases with 64 < K <= 4096, with or without row weights; everything else runs
+// moments_small_kernel / moments2_kernel on the CUDA cores.
 bool cov_tc_supported(const RowSource<float>& S, const BasisParams<float>& B);
-size_t cov_tc_scratch_floats(int n_sm);
+size_t cov_tc_scratch_floats(int K, int64_t n, int n_sm, bool weighted);
 cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B, double* sum_wff, float* scratch, int n_sm,
                           cudaStream_t st, int* launches);
+void cov_tc_set_max_rows(int64_t rows);   // rows one CTA accumulates in FP32 before its partial goes to the FP64 sum (tuning)
 constexpr int kMaxSmForScratch = 160;
 bool no_tensor_cores();
 void set_no_tensor_cores(bool v);   // tuning / test switch: force the CUDA-core covariance

@@ -268,32 +268,6 @@ def test_ensemble_ves_converges_to_analytic_fes(device_update):
     assert bF.max() < 0.5
 
 
-def test_ensemble_second_order_slip_bond():
-    """configs[2] shape at test size: slip bond, LegendreBasis1D(12) along x, uniform target, 2nd-order averaged SGD
-    with the full 13 x 13 covariance.  The CV range must cover the accessible region (the x marginal of the slip bond
-    is soft: F_x(-8) is only 3.8 kT), otherwise walkers pile up in the clamped, force-free zone and no bias can make
-    the in-range density uniform."""
-    pot = potentials.SlipBondPotential2D()
-    kT = 8.3145e-3 * 300
-    lo, hi = -12.0, 14.0
-    model = basis.LegendreBasis1D(12, lo, hi, weights=np.zeros(13))
-    b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(801), 1 / kT, "averaged_sgd",
-                              {"mu": 3.0, "second_order": True, "averaging": "ewma", "decay": 0.9})
-    assert b.needs_covariance
-    sim, _ = quiet(SingleParticleSimulation, pot, n_walkers=32768, seed=3)
-    sim.place_walkers(ntrials=2000, xmin=-8, xmax=10, ymin=-6, ymax=8)   # acceptance ~3 % per draw
-    sim.init_ves(b, startafter=200, learnevery=200)
-    quiet(sim, nsteps=240001, chkevery=0, trajevery=0, energyevery=0, chkfile=None, trajfile=None, energyfile=None)
-    assert b.n_updates == 1200
-    x, Fx = fes.projection_x(pot, 300, [lo + 1, hi - 1], [-12, 14], mesh=300)
-    V = model(torch.tensor(np.stack([x, 0 * x], 1), device="cuda")).detach().cpu().numpy()
-    F_est = (-V - (-V).min()) / kT
-    rmse = fes.rmse_kt(F_est, Fx, clip=10.0)
-    assert rmse < 0.3, rmse
-    pos = sim.get_state().positions
-    assert (pos[:, 0] < -2).mean() > 0.2 and (pos[:, 0] > 4).mean() > 0.2
-
-
 def _device_vs_host(make_bias, pot_kind, pot_params, box, cov, n_updates=24, stride=20, precision="fp32"):
     from pyves_b200 import _lib
     from pyves_b200.bias import DeviceUpdater

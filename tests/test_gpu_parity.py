@@ -570,13 +570,15 @@ def test_equilibrium_sampling_double_well_fes():
     e.close()
 
 
-@pytest.mark.parametrize("deg,sizes", [(9, (10007,)), (15, (31, 10007, 300000)), (19, (10007,)), (31, (77, 5003))],
-                         ids=["K100", "K256", "K400", "K1024"])
+@pytest.mark.parametrize("deg,sizes", [(9, (10007,)), (15, (31, 10007, 300000)), (19, (10007,)), (31, (77, 5003)), (63, (2003,))],
+                         ids=["K100", "K256", "K400", "K1024", "K4096"])
 def test_covariance_tensor_core_path(deg, sizes):
-    """K > 64 covariance of an FP32 ensemble runs on tcgen05 (TF32 inputs, FP32 accumulate in TMEM), tiled into
-    256 x 256 output tiles (K = 400: padded tiles, K = 1024: 10 upper-triangular tiles): agrees with the FP64
-    oracle to TF32 rounding (2^-11 per factor, averaging out over rows) and with the CUDA-core kernel;
-    symmetric exactly; row 0 reproduces the first moments (f_0 = 1)."""
+    """K > 64 covariance of an FP32 ensemble runs on tcgen05 (FP16 operand tiles: the 10-bit mantissa of TF32 for factors
+    |f| <= 1; FP32 accumulate in TMEM), tiled into 256 x 256 output tiles (K = 400: padded tiles, K = 1024: 10
+    upper-triangular tiles, K = 4096: all 136 tiles of the largest basis the ABI accepts): agrees with the FP64 oracle
+    to the operand rounding (2^-11 per table entry and per product, averaging out over the rows) and with the CUDA-core
+    kernel; symmetric exactly; row 0 reproduces the first moments (f_0 = 1).  Also the in-box domain (rows outside get
+    weight 0) and row weights of either sign (sqrt(|w|) folded into the operands, negative rows in a second pass)."""
     from oracle import ves
     rng = np.random.default_rng(12)
     spec = rng_spec("leg2d", rng, deg_x=deg, deg_y=deg)
@@ -592,11 +594,63 @@ def test_covariance_tensor_core_path(deg, sizes):
         scale = np.sqrt(np.outer(np.diag(sff_r), np.diag(sff_r)))          # |C_kl| <= sqrt(C_kk C_ll)
         assert np.max(np.abs(sff - sff_r) / scale) < 1e-3, n
         assert np.max(np.abs(sff[0] - sf_r) / np.maximum(np.abs(fr).sum(0), 1.0)) < 1e-3
-        e.set_tuning(98)                                                    # same call on the CUDA cores
-        _, _, sff_cc = e.moments(cov=True)
-        e.set_tuning(97)
-        assert np.max(np.abs(sff_cc.cpu().numpy() - sff_r) / scale) < 1e-5
+        if deg <= 31:
+            e.set_tuning(98)                                                # same call on the CUDA cores
+            _, _, sff_cc = e.moments(cov=True)
+            e.set_tuning(97)
+            assert np.max(np.abs(sff_cc.cpu().numpy() - sff_r) / scale) < 1e-5
+        if n >= 2000 and deg <= 31:
+            # in-box domain: rows whose scaled coordinate clamps count with weight 0
+            mm = spec["minmax"]
+            inside = (pos[:, 0] >= mm[0]) & (pos[:, 0] <= mm[1]) & (pos[:, 1] >= mm[2]) & (pos[:, 1] <= mm[3])
+            e.set_moment_domain(True)
+            swi, _, sffi = e.moments(cov=True)
+            e.set_moment_domain(False)
+            _, _, ref_i = ves.moments(fr[inside])
+            assert float(swi) == inside.sum()
+            assert np.max(np.abs(sffi.cpu().numpy() - ref_i) / scale) < 1e-3
+            # row weights: positive only (one pass), then of both signs (second pass for the negative rows)
+            for w in (rng.uniform(0.0, 7.0, n), rng.standard_normal(n) * 3.0):
+                _, _, ref_w = ves.moments(fr, w)
+                wt = torch.tensor(w, dtype=torch.float32, device=DEV)
+                rows = torch.tensor(pos, dtype=torch.float32, device=DEV)
+                _, sfw, sffw = e.moments(pos=rows, row_weights=wt, cov=True)
+                sffw = sffw.cpu().numpy()
+                wscale = np.sqrt(np.outer(np.diag(ves.moments(fr, np.abs(w))[2]), np.diag(ves.moments(fr, np.abs(w))[2])))
+                assert np.array_equal(sffw, sffw.T)
+                assert np.max(np.abs(sffw - ref_w) / wscale) < 1e-3
         e.close()
+
+
+def test_covariance_tensor_core_at_full_size():
+    """10^7 rows (configs[2]'s ensemble on ONE GPU; 1.25 x 10^6 per GPU is the sharded case) at K = 256.  The tensor core
+    truncates when it aligns the addends of its FP32 accumulation: measured (tools/diag/cov_accum_diag.py) the diagonal
+    comes out low by 2^-27 per accumulated row, 4e-4 if a CTA kept its 67 000 rows in TMEM.  The kernel therefore drains
+    the accumulators into its partial tile every 16384 rows (rounded FP32 adds) and the partials are summed in FP64:
+    bias <= 1.1e-4 of sqrt(C_kk C_ll) whatever n is, off-diagonal entries 3e-6.  Checked against the CUDA-core kernel,
+    which promotes to FP64 every 512 rows and is itself pinned to the FP64 oracle above.  Size-independent properties at
+    full size: exact symmetry, C_00 = n, row 0 = first moments."""
+    n = 10 ** 7
+    rng = np.random.default_rng(3)
+    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    e = biasspec.make_ensemble(n, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    pos = torch.empty((2, n), dtype=torch.float32, device=DEV)
+    pos[0].uniform_(-2.5, 2.5, generator=g)
+    pos[1].uniform_(-2.0, 2.0, generator=g)
+    e.set_state(pos, None)
+    sw, sf, sff = e.moments(cov=True)
+    e.set_tuning(98)
+    _, _, ref = e.moments(cov=True)
+    e.set_tuning(97)
+    sff, ref = sff.cpu().numpy(), ref.cpu().numpy()
+    assert float(sw) == n and sff[0, 0] == n and np.array_equal(sff, sff.T)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    err = (sff - ref) / scale
+    assert np.max(np.abs(err)) < 2e-4, np.max(np.abs(err))
+    assert np.max(np.abs(err - np.diag(np.diag(err)))) < 2e-5          # entries of mixed-sign sums carry no truncation bias
+    assert np.max(np.abs(sff[0] - sf.cpu().numpy())) < 2e-4 * n
+    e.close()
 
 
 @pytest.mark.gpu
