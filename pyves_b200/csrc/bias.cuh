@@ -590,15 +590,22 @@ template <typename T> struct BiasOther {
     } else if (P.kind == PYVES_BIAS_PATHCV) {
       const T* xi = reinterpret_cast<const T*>(smem);
       const T* yi = xi + P.npath;
-      T amax = T(-1e30);
+      // nearest image m first; the exponents are then -lam (d_i^2 - d_m^2) with the difference of the squared distances
+      // taken as (x_m - x_i)(2x - x_i - x_m) + (y_m - y_i)(2y - y_i - y_m): no cancellation between two rounded squares
+      // (lam = 100 turned the FP32 rounding of d^2 into 1e-3 relative errors of the weights)
+      T dmin = T(1e30), xm = xi[0], ym = yi[0];
       for (int i = 0; i < P.npath; ++i) {
         const T dx = x - xi[i], dy = y - yi[i];
-        amax = Math<T>::max(amax, -P.lam * (dx * dx + dy * dy));
+        const T d2 = Math<T>::fma(dx, dx, dy * dy);
+        if (d2 < dmin) { dmin = d2; xm = xi[i]; ym = yi[i]; }
       }
+      const T amax = -P.lam * dmin;
+      const T tx = (x - xm) + x, ty = (y - ym) + y;       // 2x - x_m, 2y - y_m
       T S0 = 0, S1 = 0, G0x = 0, G0y = 0, G1x = 0, G1y = 0;
       for (int i = 0; i < P.npath; ++i) {
         const T dx = x - xi[i], dy = y - yi[i];
-        const T ee = Math<T>::exp(-P.lam * (dx * dx + dy * dy) - amax);
+        const T dd = Math<T>::fma(xm - xi[i], tx - xi[i], (ym - yi[i]) * (ty - yi[i]));
+        const T ee = Math<T>::exp(-P.lam * dd);
         const T ei = ee * T(i + 1);
         S0 += ee; S1 += ei;
         G0x += ee * dx; G0y += ee * dy;

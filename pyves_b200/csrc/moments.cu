@@ -29,15 +29,19 @@ PV_DEV void row_factors(const RowSource<T>& S, const BasisParams<T>& B, int64_t 
   } else if (B.kind == PYVES_BIAS_LEGENDRE_1D) {
     sa = scale_clamp(B.axis ? y : x, B.ca, B.iha, inside);
   } else {   // path CV, ves/basis.py:524-535
-    T amax = T(-1e30);
+    // nearest image first, then exponents from the difference of squares (see BiasOther, bias.cuh)
+    T dmin = T(1e30), xm = B.path[0], ym = B.path[B.npath];
     for (int i = 0; i < B.npath; ++i) {
       const T dx = x - B.path[i], dy = y - B.path[B.npath + i];
-      amax = Math<T>::max(amax, -B.lam * (dx * dx + dy * dy));
+      const T d2 = Math<T>::fma(dx, dx, dy * dy);
+      if (d2 < dmin) { dmin = d2; xm = B.path[i]; ym = B.path[B.npath + i]; }
     }
+    const T tx = (x - xm) + x, ty = (y - ym) + y;
     T S0 = 0, S1 = 0;
     for (int i = 0; i < B.npath; ++i) {
-      const T dx = x - B.path[i], dy = y - B.path[B.npath + i];
-      const T ee = Math<T>::exp(-B.lam * (dx * dx + dy * dy) - amax);
+      const T xi = B.path[i], yi = B.path[B.npath + i];
+      const T dd = Math<T>::fma(xm - xi, tx - xi, (ym - yi) * (ty - yi));
+      const T ee = Math<T>::exp(-B.lam * dd);
       S0 += ee;
       S1 += ee * T(i + 1);
     }
