@@ -64,6 +64,9 @@ def parse_args():
                          "host<->device copies of one chunk overlap the step kernel of another (1 = one handle, serial copies)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--comm", default="native", choices=["native", "torch"],
+                    help="the all-reduce of the moments: 'native' = pyves_allreduce_moments (NCCL bound by the C-ABI library itself, "
+                         "communicator bootstrapped through the torch process group), 'torch' = torch.distributed.all_reduce")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configurations")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default); strong: --walkers-total sharded over the ranks")
@@ -187,6 +190,8 @@ def run_ours(args):
 
     from pyves_b200.bias import DeviceUpdater
     upd = DeviceUpdater(bias, ens) if args.update == "device" else None
+    comm = _lib.Communicator.from_process_group(local) if (world > 1 and args.comm == "native") else None
+    _PEAK["comm"] = comm
 
     def iteration(timed):
         flush.zero_()                                            # evict the 126 MB L2 between iterations
@@ -203,11 +208,11 @@ def run_ours(args):
             if timed and world > 1:
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 c0.record()
-                upd.reduce_flat()                                # one NCCL all-reduce, in place
+                upd.reduce_flat(comm=comm)                       # one NCCL all-reduce, in place
                 c1.record()
                 comm_events.append((c0, c1))
             else:
-                upd.reduce_flat()
+                upd.reduce_flat(comm=comm)
             upd.update(*bufs)                                    # optimiser kernel + target + coefficient hand-over, all enqueued
         else:
             sw, sf, _ = reduce_moments(*ens.moments())           # one NCCL allreduce of 1 + K doubles
@@ -386,8 +391,9 @@ def run_ours(args):
                           "l2": "flushed between steps (256 MiB memset); state 16 MB/GPU is read once per 500 MD steps",
                           "update": args.update},
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "comm_ms": comm_ms,
-               "comm_note": "one all-reduce of %d doubles per update; CUDA events around it on the launching stream (includes the wait for "
-                            "the slowest rank), mean per iteration, max over ranks" % (K + 1)}
+               "comm_note": "one all-reduce of %d doubles per update (%s); CUDA events around it on the launching stream (includes the wait "
+                            "for the slowest rank), mean per iteration, max over ranks"
+                            % (K + 1, "pyves_allreduce_moments, C ABI" if comm is not None else "torch.distributed")}
         if legs:
             out["configs"] = legs
         if e2e:
@@ -397,6 +403,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args, seconds=12.0)
         print(json.dumps(out), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -473,7 +481,7 @@ def config_legs(args, rank, world, local, dev, peak):
         def update():
             bufs = upd.moment_buffers(cov)
             e.moments(cov=cov, out=bufs)
-            upd.reduce_flat()
+            upd.reduce_flat(comm=_PEAK.get("comm"))
             upd.update(*bufs)
         sec, kms = _leg_time(torch, dist, world, dev, e, stride, iters, 1, update)
         row(name, workload, n_rank, n_total, stride, sec, kms, kernel, flops, scaling, {"update": "device-resident (%s)" % b.optimizer_type})

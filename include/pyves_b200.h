@@ -225,6 +225,23 @@ int pyves_optimizer_step(int device, int kind, int64_t P, const double* sum_w, c
  * target distribution (ves/target.py:24-31 defines p on [-1, 1] only; README.md:10-31). */
 int pyves_set_moment_domain(pyves_t* h, int inside_only);
 
+/* ---- multi-GPU: the one exchange step of the path ----------------------------------------------------- */
+/* Walkers are independent between coefficient updates, so rank r owns a block of global walker ids
+ * (pyves_set_walker_offset) and the only collective is the sum of the moment vector pyves_moments produced,
+ * [sum_w, sum_w f (K), sum_w f f (K * K)?], once per update; every rank then applies the identical optimiser step
+ * (no broadcast).  The reference has no multi-walker code (ves/langevin_dynamics.py:43-47 adds one particle); this
+ * is the all-reduce its README's "ensemble averages" (README.md:10-31) would need.  NCCL is loaded at run time
+ * (libnccl.so.2 of the process, e.g. torch's), the communicator is bootstrapped from any out-of-band channel: rank 0
+ * calls pyves_comm_unique_id and ships the 128 bytes (torch.distributed broadcast, MPI, a file), every rank calls
+ * pyves_comm_create.  pyves_allreduce_moments sums `count` doubles in place on `stream`. */
+typedef struct pyves_comm pyves_comm_t;
+int pyves_comm_unique_id(void* id128);
+int pyves_comm_create(pyves_comm_t** out, int device, int nranks, int rank, const void* id128);
+int pyves_comm_destroy(pyves_comm_t* c);
+int pyves_allreduce_moments(pyves_comm_t* c, double* moments_dev, int64_t count, void* stream);
+int pyves_comm_nccl_version(int* version);
+const char* pyves_comm_last_error(void);
+
 /* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel;
  * 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed again) */
 int pyves_set_tuning(pyves_t* h, int variant);

@@ -67,6 +67,12 @@ SIGNATURES = {
     "pyves_set_bias_like": (_i, [_vp, _vp, _vp]),
     "pyves_set_bias_mlp_device": (_i, [_vp, _i, _d, _d, _i, _ip, _i, _vp, _vp]),
     "pyves_optimizer_step": (_i, [_i, _i, _i64, _vp, _vp, _vp, _i, _d, _i64, _vp, _vp, _vp, _vp, _dp, _i64, _vp]),
+    "pyves_comm_unique_id": (_i, [_vp]),
+    "pyves_comm_create": (_i, [_c.POINTER(_vp), _i, _i, _i, _vp]),
+    "pyves_comm_destroy": (_i, [_vp]),
+    "pyves_allreduce_moments": (_i, [_vp, _vp, _i64, _vp]),
+    "pyves_comm_nccl_version": (_i, [_c.POINTER(_i)]),
+    "pyves_comm_last_error": (_c.c_char_p, []),
     "pyves_fp32_fma_peak": (_i, [_i, _dp]),
     "pyves_fp32_fma2_peak": (_i, [_i, _dp]),
     "pyves_launch_count": (_i64, []),
@@ -130,6 +136,73 @@ def optimizer_step(device, kind, sum_w, sum_wf, f_target, grad_average, grad_dec
                                   _stream(device))
     if rc:
         raise (ValueError if rc == -1 else RuntimeError)(lib.pyves_last_error(None).decode())
+
+
+class Communicator:
+    """The path's one collective through the C ABI (``pyves_comm_*`` / ``pyves_allreduce_moments``): an NCCL
+    communicator over the ranks that share one ensemble.  ``from_process_group`` bootstraps it from an initialised
+    ``torch.distributed`` group (rank 0's unique id is broadcast through it); any other channel that can ship 128 bytes
+    works the same way (``unique_id()`` on rank 0, ``Communicator(device, nranks, rank, id)`` everywhere)."""
+
+    def __init__(self, device, nranks, rank, unique_id):
+        self.lib = load()
+        self.device, self.nranks, self.rank = int(device), int(nranks), int(rank)
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self.h = _vp()
+        rc = self.lib.pyves_comm_create(ctypes.byref(self.h), self.device, self.nranks, self.rank, ctypes.cast(buf, _vp))
+        if rc:
+            self.h = _vp()
+            self._raise(rc)
+
+    def _raise(self, rc):
+        msg = self.lib.pyves_comm_last_error().decode()
+        raise (ValueError if rc == EINVAL else NotImplementedError if rc == EUNSUPPORTED else RuntimeError)(msg)
+
+    @staticmethod
+    def unique_id():
+        lib = load()
+        buf = (ctypes.c_char * 128)()
+        rc = lib.pyves_comm_unique_id(ctypes.cast(buf, _vp))
+        if rc:
+            raise RuntimeError(lib.pyves_comm_last_error().decode())
+        return bytes(buf)
+
+    @staticmethod
+    def nccl_version():
+        v = _i(0)
+        rc = load().pyves_comm_nccl_version(ctypes.byref(v))
+        return v.value if rc == 0 else None
+
+    @classmethod
+    def from_process_group(cls, device, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        torch.cuda.synchronize(device)
+        return cls(device, world, rank, box[0])
+
+    def allreduce_(self, flat):
+        """In-place sum of a contiguous CUDA float64 tensor over the ranks, enqueued on the current stream."""
+        import torch
+        if not (torch.is_tensor(flat) and flat.is_cuda and flat.dtype == torch.float64 and flat.is_contiguous() and flat.device.index == self.device):
+            raise ValueError("allreduce_ needs a contiguous CUDA float64 tensor on device %d" % self.device)
+        rc = self.lib.pyves_allreduce_moments(self.h, ctypes.c_void_p(flat.data_ptr()), flat.numel(), _stream(self.device))
+        if rc:
+            self._raise(rc)
+        return flat
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pyves_comm_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def launch_count():

@@ -727,7 +727,13 @@ class DeviceUpdater:
         f = self._flat
         return f[:1], f[1:1 + K], (f[1 + K:].view(K, K) if cov else None)
 
-    def reduce_flat(self, group=None):
+    def reduce_flat(self, group=None, comm=None):
+        """Sum the flat moment buffer over the ranks in place: through the library's own collective
+        (``comm``: a ``pyves_b200._lib.Communicator``, ``pyves_allreduce_moments``) or through ``torch.distributed``."""
+        if comm is not None:
+            if comm.nranks > 1:
+                comm.allreduce_(self._flat)
+            return
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=group)

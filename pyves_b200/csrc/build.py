@@ -17,7 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]
 
-UNITS = [("api.cu", []), ("misc_kernels.cu", []), ("moments.cu", []), ("cov_tc.cu", [])]
+UNITS = [("api.cu", []), ("misc_kernels.cu", []), ("moments.cu", []), ("cov_tc.cu", []), ("comm.cu", [])]
 for grp in range(4):
     for t in ("float", "double"):
         UNITS.append(("langevin_inst.cu", ["-DPV_T=%s" % t, "-DPV_GROUP=%d" % grp]))
@@ -55,7 +55,7 @@ def build(force=False, verbose=True):
         return LIB
     with concurrent.futures.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(compile_unit, UNITS))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

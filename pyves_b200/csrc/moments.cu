@@ -710,7 +710,9 @@ template <typename T> PV_DEV void lds8(const T* p, T (&v)[8]) {
   }
 }
 
-template <typename T, int TS>
+// NB big layers per block (blockIdx.y picks the group): with NB = 2 the 3 x 48 net of configs[3] runs its forward / backward
+// pass ONCE per tile instead of once per big layer (2.7 -> 1.7 ms per 10^6 rows).
+template <typename T, int TS, int NB>
 __global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSource<T> S, const MlpGradParams<T> M, const MlpPlan P,
                                                                    double* __restrict__ part, double* __restrict__ part_w) {
   using X = Mlp2<T>;
@@ -721,14 +723,18 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSour
   T* wrow = d + (size_t)P.units_out * RS;       // [R] row weights
   const int tid = threadIdx.x;
   const int y = blockIdx.y;
-  const int bl = P.nbig > 0 ? P.big[y] : -1;
+  int bls[NB];
+#pragma unroll
+  for (int g = 0; g < NB; ++g) bls[g] = (y * NB + g) < P.nbig ? P.big[y * NB + g] : -1;
   const int tj = tid >> 4, ti = tid & 15;
 
-  T acc[TS][TS];
+  T acc[NB][TS][TS];
 #pragma unroll
-  for (int a = 0; a < TS; ++a)
+  for (int g = 0; g < NB; ++g)
 #pragma unroll
-    for (int b = 0; b < TS; ++b) acc[a][b] = T(0);
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+      for (int b = 0; b < TS; ++b) acc[g][a][b] = T(0);
   // small parameters of this thread (y == 0 only): gradient = sum_r d[srow_d][r] * (srow_h >= 0 ? h[srow_h][r] : 1)
   int srow_d[kMlp2Small], srow_h[kMlp2Small], sidx[kMlp2Small];
   T sacc[kMlp2Small];
@@ -878,35 +884,39 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSour
       }
       __syncthreads();
     }
-    // ---- phase 2: outer products of the big layer of this block, register tile, strided ownership
-    if (bl >= 0) {
-      const int nin = P.nin[bl], nout = P.nout[bl];
-      const T* dl = d + (size_t)P.doff[bl] * RS;
-      const T* hl = h + (size_t)P.hoff[bl] * RS;
-      for (int r = 0; r < R; r += X::V) {
-        T dv[TS][X::V], hv[TS][X::V];
+    // ---- phase 2: outer products of the big layers of this block, register tiles, strided ownership
 #pragma unroll
-        for (int a = 0; a < TS; ++a) {
-          const int j = tj + 16 * a;
-          if (j < nout) lds_vec(dl + (size_t)j * RS + r, dv[a]);
-          else
+    for (int g = 0; g < NB; ++g) {
+      const int bl = bls[g];
+      if (bl >= 0) {
+        const int nin = P.nin[bl], nout = P.nout[bl];
+        const T* dl = d + (size_t)P.doff[bl] * RS;
+        const T* hl = h + (size_t)P.hoff[bl] * RS;
+        for (int r = 0; r < R; r += X::V) {
+          T dv[TS][X::V], hv[TS][X::V];
 #pragma unroll
-            for (int q = 0; q < X::V; ++q) dv[a][q] = T(0);
+          for (int a = 0; a < TS; ++a) {
+            const int j = tj + 16 * a;
+            if (j < nout) lds_vec(dl + (size_t)j * RS + r, dv[a]);
+            else
+#pragma unroll
+              for (int q = 0; q < X::V; ++q) dv[a][q] = T(0);
+          }
+#pragma unroll
+          for (int b = 0; b < TS; ++b) {
+            const int i = ti + 16 * b;
+            if (i < nin) lds_vec(hl + (size_t)i * RS + r, hv[b]);
+            else
+#pragma unroll
+              for (int q = 0; q < X::V; ++q) hv[b][q] = T(0);
+          }
+#pragma unroll
+          for (int a = 0; a < TS; ++a)
+#pragma unroll
+            for (int b = 0; b < TS; ++b)
+#pragma unroll
+              for (int q = 0; q < X::V; ++q) acc[g][a][b] = Math<T>::fma(dv[a][q], hv[b][q], acc[g][a][b]);
         }
-#pragma unroll
-        for (int b = 0; b < TS; ++b) {
-          const int i = ti + 16 * b;
-          if (i < nin) lds_vec(hl + (size_t)i * RS + r, hv[b]);
-          else
-#pragma unroll
-            for (int q = 0; q < X::V; ++q) hv[b][q] = T(0);
-        }
-#pragma unroll
-        for (int a = 0; a < TS; ++a)
-#pragma unroll
-          for (int b = 0; b < TS; ++b)
-#pragma unroll
-            for (int q = 0; q < X::V; ++q) acc[a][b] = Math<T>::fma(dv[a][q], hv[b][q], acc[a][b]);
       }
     }
 #pragma unroll
@@ -927,15 +937,19 @@ __global__ void __launch_bounds__(kMomThreads) moments_mlp2_kernel(const RowSour
   }
 
   double* mypart = part + (int64_t)blockIdx.x * M.n_params;
-  if (bl >= 0) {
-    const int nin = P.nin[bl], nout = P.nout[bl];
 #pragma unroll
-    for (int a = 0; a < TS; ++a)
+  for (int g = 0; g < NB; ++g) {
+    const int bl = bls[g];
+    if (bl >= 0) {
+      const int nin = P.nin[bl], nout = P.nout[bl];
 #pragma unroll
-      for (int b = 0; b < TS; ++b) {
-        const int j = tj + 16 * a, i = ti + 16 * b;
-        if (j < nout && i < nin) mypart[P.poff[bl] + j * nin + i] = (double)acc[a][b];
-      }
+      for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b) {
+          const int j = tj + 16 * a, i = ti + 16 * b;
+          if (j < nout && i < nin) mypart[P.poff[bl] + j * nin + i] = (double)acc[g][a][b];
+        }
+    }
   }
 #pragma unroll
   for (int q = 0; q < kMlp2Small; ++q)
@@ -1001,11 +1015,15 @@ cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M,
     const size_t sm2 = ((size_t)(plan.units_in + plan.units_out) * X::kStride + X::kRows) * sizeof(T);
     int wmax = 0;
     for (int l = 0; l <= M.n_layers; ++l) wmax = M.sizes[l] > wmax ? M.sizes[l] : wmax;
-    auto kern2 = wmax <= 32 ? moments_mlp2_kernel<T, 2> : (wmax <= 64 ? moments_mlp2_kernel<T, 4> : moments_mlp2_kernel<T, 8>);
+    // narrow nets with several big layers: two of them per block (one forward / backward pass feeds both outer products)
+    const bool pair = plan.nbig >= 2 && wmax <= 64;
+    auto kern2 = pair ? (wmax <= 32 ? moments_mlp2_kernel<T, 2, 2> : moments_mlp2_kernel<T, 4, 2>)
+                      : (wmax <= 32 ? moments_mlp2_kernel<T, 2, 1> : (wmax <= 64 ? moments_mlp2_kernel<T, 4, 1> : moments_mlp2_kernel<T, 8, 1>));
+    const int ngroups = plan.nbig > 0 ? (pair ? (plan.nbig + 1) / 2 : plan.nbig) : 1;
     cudaError_t e2 = cudaSuccess;
     if (sm2 > 48 * 1024) e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
     if (e2 != cudaSuccess) return e2;
-    kern2<<<dim3(G2, plan.nbig > 0 ? plan.nbig : 1), kMomThreads, sm2, st>>>(S, M, plan, part2, part_w2);
+    kern2<<<dim3(G2, ngroups), kMomThreads, sm2, st>>>(S, M, plan, part2, part_w2);
     launch_reduce_partials(part2, G2, P, sum_wf, part_w2, sum_w, st);
     *launches += 2;
     return cudaGetLastError();

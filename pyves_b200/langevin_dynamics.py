@@ -11,6 +11,8 @@ the fused step kernel of the CUDA library advances whole stretches between two "
 New keywords: ``n_walkers`` (ensemble size; sharded over the ranks of an initialised
 ``torch.distributed`` process group), ``device``, ``precision`` ('fp32' | 'fp64'), ``scheme``
 ('openmm_langevin' | 'middle'), ``dims`` (2 drops the decoupled z coordinate, 3 keeps it),
+``communicator`` (a ``pyves_b200._lib.Communicator``: the device-resident update loop sums the moments through the
+library's own NCCL entry point ``pyves_allreduce_moments`` instead of ``torch.distributed``),
 ``traj_walkers`` (how many walkers are recorded), ``sample_every`` (moment sampling stride of the
 ensemble VES update), ``device_update`` (keep optimiser state and coefficients of a ``VESBias_Ensemble`` on the
 GPU between updates, ``bias.DeviceUpdater``; the bias object is synchronised when the run returns and at every
@@ -85,7 +87,8 @@ class SingleParticleSimulation:
                  sample_every: int = None,
                  process_group=None,
                  device_update: bool = False,
-                 archive_updates: bool = False):
+                 archive_updates: bool = False,
+                 communicator=None):
         # units as upstream: Da, K, 1/ps, fs
         self.mass = float(mass)
         self.temp = float(temp)
@@ -142,6 +145,7 @@ class SingleParticleSimulation:
         self.sample_every = sample_every
         self.device_update = bool(device_update)
         self.archive_updates = bool(archive_updates)       # device_update: also write model_loc + ".iter{n}" per update (costs a sync)
+        self.communicator = communicator    # a pyves_b200._lib.Communicator: the device-resident loop reduces through the C ABI
         self._updater = None
         self.biased = False
         self._g0 = 0                    # loop index this run continues from (set by init_ves when the state carries a bias)
@@ -229,7 +233,7 @@ class SingleParticleSimulation:
                 # kernel, coefficient hand-over -- four library calls and one NCCL call per update, nothing else
                 bufs = self._updater.moment_buffers(self.bias.needs_covariance)
                 self.ens.moments(cov=self.bias.needs_covariance, out=bufs)
-                self._updater.reduce_flat(self.process_group)
+                self._updater.reduce_flat(self.process_group, comm=self.communicator)
                 self._updater.update(*bufs)
                 self._archive_device_update()
                 return

@@ -310,3 +310,23 @@ def test_device_update_archive_is_optional(tmp_path):
             assert torch.allclose(mod.weights.detach(), b.model.weights.detach())
         else:
             assert names == ["m0.pt"]
+
+
+def test_native_communicator_single_rank():
+    """pyves_comm_* / pyves_allreduce_moments (the collective of the path in the C ABI, NCCL bound at run time): a
+    one-rank communicator is created from a unique id, the in-place all-reduce is the identity, bad arguments raise.
+    The multi-rank case runs in bench.py (--comm native is the default; SCALE_r02 covers 2 / 4 / 8 ranks)."""
+    assert _lib.Communicator.nccl_version() >= 20000
+    uid = _lib.Communicator.unique_id()
+    assert len(uid) == 128
+    c = _lib.Communicator(0, 1, 0, uid)
+    t = torch.arange(257, dtype=torch.float64, device="cuda") * 0.5
+    ref = t.clone()
+    c.allreduce_(t)
+    torch.cuda.synchronize()
+    assert torch.equal(t, ref)
+    with pytest.raises(ValueError):
+        c.allreduce_(t.float())
+    with pytest.raises(ValueError):
+        _lib.Communicator(0, 2, 5, uid)
+    c.close()
