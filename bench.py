@@ -173,6 +173,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
+    if world > 1 and os.environ.get("PYVES_NO_NUMA_BIND", "0") != "1":
+        from pyves_b200.parallel import bind_to_gpu_numa_node
+        numa_cores = bind_to_gpu_numa_node(local)          # before any pinned allocation: host buffers land next to this GPU
     beta = 1.0 / (KB_PY * TEMP)
     from pyves_b200.potentials import _Potential
     _Potential.quiet = True
@@ -245,10 +249,10 @@ def run_ours(args):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
     # the one collective per update: CUDA events around the all-reduce on the launching stream (includes the wait for the
     # slowest rank's moments, i.e. the skew), mean per iteration, MAX over ranks
-    comm = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in comm_events])) if comm_events else 0.0], dtype=torch.float64, device=dev)
+    comm_t = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in comm_events])) if comm_events else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(comm, op=dist.ReduceOp.MAX)
-    comm_ms = float(comm)
+        dist.all_reduce(comm_t, op=dist.ReduceOp.MAX)
+    comm_ms = float(comm_t)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     # every iteration: walker state from pinned host memory -> GPU, the VES iteration, then the result (the 1 + K
@@ -331,7 +335,7 @@ def run_ours(args):
         state_bytes = 2 * 2 * args.walkers * 4
         e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
                "h2d_bytes_per_step": state_bytes + (0 if upd is not None else K * 8), "d2h_bytes_per_step": state_bytes + (K + 1) * 8,
-               "chunks": nch}
+               "chunks": nch, "numa_bound_cores": None if numa_cores is None else len(numa_cores)}
         if nch > 1:
             for e in subs:
                 upd.handles.remove(e)

@@ -33,3 +33,25 @@ def reduce_moments(sum_w, sum_wf, sum_wff=None, group=None):
     flat = torch.cat(parts)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat[:1], flat[1:1 + K], (flat[1 + K:].reshape(K, K) if sum_wff is not None else None)
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), so that the
+    pinned host buffers it allocates afterwards (first touch) and the threads that feed the copies sit next to that GPU's
+    PCIe root.  With one process per GPU all moving walker state through host memory at once, remote-node buffers make the
+    ranks collide on the inter-socket link.  Returns the core list, or None when NVML / affinity control is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
