@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--comm", default="native", choices=["native", "torch"],
                     help="the all-reduce of the moments: 'native' = pyves_allreduce_moments (NCCL bound by the C-ABI library itself, "
                          "communicator bootstrapped through the torch process group), 'torch' = torch.distributed.all_reduce")
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "cuda", "tensor"],
+                    help="2D Legendre step kernel of the headline: 'auto' = the library's table (tensor-core contraction from ~14 x 14 "
+                         "functions on), 'cuda' = CUDA-core column sweep (pyves_set_tuning 6), 'tensor' = tensor cores forced (7)")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configurations")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default); strong: --walkers-total sharded over the ranks")
@@ -182,6 +185,7 @@ def run_ours(args):
     _Potential.quiet = True
     bias = make_bias(args, beta)
     ens = make_ensemble(args, rank, local)
+    ens.set_tuning({"auto": -1, "cuda": 6, "tensor": 7}[args.step_kernel])
     bias.force.apply(ens)
     K = args.basis * args.basis
     n_total = args.walkers * world
@@ -276,6 +280,7 @@ def run_ours(args):
                 e.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
                 e.set_potential(_lib.POT_DOUBLE_WELL_2D)
                 e.set_walker_offset(rank * args.walkers + c * cn)
+                e.set_tuning({"auto": -1, "cuda": 6, "tensor": 7}[args.step_kernel])
                 e.step_counter = ens.step_counter
                 upd.add_handle(e)
                 subs.append(e)
@@ -370,12 +375,15 @@ def run_ours(args):
         roof = None
         if flops:
             achieved = args.walkers * args.stride * flops / (kern_ms * 1e-3) * 1e-12
+            tensor_path = args.step_kernel == "tensor" or (args.step_kernel == "auto" and 14 <= args.basis <= 64)
             roof = {"bound": "fp32-fma (CUDA cores; neither HBM nor tensor bound)", "kernel": "langevin2d_kernel",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "FFMA micro-benchmark run in this process (pyves_fp32_fma_peak); nominal 74.4",
                     "flops_per_walker_step": flops, "kernel_ms": kern_ms,
                     "kernel_share_of_step": kern_ms * args.steps / (elapsed * 1e3),
                     **ncu_traffic(args)}
+            if tensor_path:
+                roof.update(tensor_roofline(args.basis, args.walkers * args.stride / (kern_ms * 1e-3)))
             # the HBM view of the same kernel, against the driver-measured copy bandwidth: why "hbm" is not the bound
             hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
             try:
@@ -477,9 +485,11 @@ def config_legs(args, rank, world, local, dev, peak):
             r.update(extra)
         out[name] = r
 
-    def updater_leg(name, workload, make_bias, pot_kind, pot_params, box, n_rank, gid0, n_total, stride, iters, kernel, flops, scaling, cov=False):
+    def updater_leg(name, workload, make_bias, pot_kind, pot_params, box, n_rank, gid0, n_total, stride, iters, kernel, flops, scaling, cov=False,
+                    variant=-1):
         b = make_bias()
         e = _leg_ensemble(n_rank, gid0, pot_kind, pot_params, box, local, args.seed)
+        e.set_tuning(variant)
         upd = DeviceUpdater(b, e)
 
         def update():
@@ -488,7 +498,11 @@ def config_legs(args, rank, world, local, dev, peak):
             upd.reduce_flat(comm=_PEAK.get("comm"))
             upd.update(*bufs)
         sec, kms = _leg_time(torch, dist, world, dev, e, stride, iters, 1, update)
-        row(name, workload, n_rank, n_total, stride, sec, kms, kernel, flops, scaling, {"update": "device-resident (%s)" % b.optimizer_type})
+        extra = {"update": "device-resident (%s)" % b.optimizer_type}
+        if "tc_kernel" in kernel:
+            K = int(name.split("_")[1].split("x")[0]) if name.startswith("cfg5_") else args.basis
+            extra["tensor"] = tensor_roofline(K, n_rank * stride / (kms * 1e-3))["tensor"]
+        row(name, workload, n_rank, n_total, stride, sec, kms, kernel, flops, scaling, extra)
         upd.close()
         e.close()
 
@@ -523,8 +537,20 @@ def config_legs(args, rank, world, local, dev, peak):
     def leg2d(K):
         return lambda: bias.VESBias_Ensemble(basis.LegendreBasis2D(K - 1, K - 1, *MINMAX), target.Target_Uniform_2D(100, 100), beta, "averaged_sgd",
                                              {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=0)
-    kern = {8: "langevin2d_kernel<DoubleWell, Legendre2DStaticT<8,8>>", 32: "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,1,5>>",
-            64: "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,2,5>>"}
+    kern = {8: "langevin2d_kernel<DoubleWell, Legendre2DStaticT<8,8>>", 32: "langevin2d_tc_kernel<32,32,3,2> (tensor-core contraction)",
+            64: "langevin2d_tc_kernel<64,64,3,1> (tensor-core contraction)"}
+    # the headline workload on the CUDA-core column sweep (the FP32-roofline kernel of round 1) and the 32 x 32 / 64 x 64 sweeps,
+    # for the comparison with the tensor-core contraction that is the default now
+    def headline_bias():
+        return bias.VESBias_Ensemble(basis.LegendreBasis2D(15, 15, *MINMAX), target.Target_WellTempered_2D(100, 100, bias_factor=10.0), beta,
+                                     "averaged_sgd", {"mu": args.mu, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=10)
+    updater_leg("cfg2_cuda_cores", "configs[1] (the headline workload) with the step kernel forced onto the CUDA cores (pyves_set_tuning 6)",
+                headline_bias, _lib.POT_DOUBLE_WELL_2D, (), MINMAX, 1000000, rank * 1000000, 1000000 * world, args.stride, 3,
+                "langevin2d_kernel<DoubleWell, Legendre2DStaticT<16,16,const,4>> (CUDA cores, FFMA2 column sweep)", LEG_FLOPS[16], "weak", variant=6)
+    for K, stride, vkern in ((32, 100, "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,1,5>> (CUDA cores)"),
+                             (64, 30, "langevin2d_kernel<DoubleWell, Legendre2DSmem<32,2,5>> (CUDA cores)")):
+        updater_leg("cfg5_%dx%d_cuda_cores" % (K, K), "configs[4]: %dx%d Legendre on the CUDA cores (pyves_set_tuning 6), 10^6 walkers per GPU" % (K, K),
+                    leg2d(K), _lib.POT_DOUBLE_WELL_2D, (), MINMAX, 1000000, rank * 1000000, 1000000 * world, stride, 2, vkern, LEG_FLOPS[K], "weak", variant=6)
     for K, stride in ((8, 500), (32, 100), (64, 30)):
         updater_leg("cfg5_%dx%d" % (K, K), "configs[4]: 2D double well + %dx%d Legendre, uniform target, 10^6 walkers per GPU" % (K, K), leg2d(K),
                     _lib.POT_DOUBLE_WELL_2D, (), MINMAX, 1000000, rank * 1000000, 1000000 * world, stride, 2, kern[K], LEG_FLOPS[K], "weak")
@@ -553,6 +579,27 @@ def single_walker_rate(local, seed):
     e.close()
     return {"value": 2e5 / dt, "unit": "steps/s", "note": "one walker, dims 3, FP64, general kernel, 20 launches of 10^4 steps (latency bound: "
             "one thread does the work); the reference's per-step Python/TorchForce loop is the torchforce_style figure of cpu_baseline"}
+
+
+def tensor_roofline(basis, walker_steps_per_s):
+    """Roofline keys of the step kernel whose contraction runs on the tensor cores (csrc/langevin_tc.cu).  `achieved` / `frac`
+    stay the ALGORITHMIC flops of SURVEY 8(d) against the FP32 FMA peak -- the bound of the CUDA-core formulation the
+    north-star names, which this kernel is allowed to beat because the 4 Kx Ky flops of the contraction left the FMA pipe;
+    what bounds it instead is instruction issue (generation of the operand rows, x sweep, noise: profiles/r02_ncu_tc_step.md)
+    and, for 64 x 64, shared-memory bandwidth.  `tensor` gives the executed tensor work against the FP16 dense peak."""
+    kp = 16 if basis <= 16 else (32 if basis <= 32 else 64)
+    executed = 12.0 * kp * kp                      # 2 matrices (P, P') x 3 MMAs (hi hi, hi lo, lo hi) x 2 N K flops per walker-step
+    peak16 = 1643.1
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak16 = float(json.load(fh)["bf16_tflops"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return {"bound": "instruction issue; the contraction runs on the tensor pipe (FP16 hi + lo split, tcgen05), so the FP32 FMA peak "
+                     "is the bound of the CUDA-core formulation this kernel replaces, not of this kernel",
+            "kernel": "langevin2d_tc_kernel",
+            "tensor": {"executed_flops_per_walker_step": executed, "achieved": executed * walker_steps_per_s * 1e-12, "peak": peak16,
+                       "unit": "TFLOP/s", "frac": executed * walker_steps_per_s * 1e-12 / peak16, "peak_source": "MEASURED_PEAKS.json bf16_tflops"}}
 
 
 def workload_string(args):

@@ -242,8 +242,10 @@ int pyves_allreduce_moments(pyves_comm_t* c, double* moments_dev, int64_t count,
 int pyves_comm_nccl_version(int* version);
 const char* pyves_comm_last_error(void);
 
-/* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel;
- * 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed again) */
+/* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel; 7 / 6 = the 2D Legendre
+ * contraction of the step kernel on the tensor cores for every size <= 64 x 64 / on the CUDA cores for every size (default:
+ * tensor cores from ~14 x 14 functions on, FP32 handles); 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed
+ * again; 1000 + k = process-wide: rows the tensor-core covariance accumulates in TMEM between two drains = 2^k) */
 int pyves_set_tuning(pyves_t* h, int variant);
 
 /* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */

@@ -417,6 +417,16 @@ template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaSt
   return PYVES_OK;
 }
 
+// tuning variant 7: the 2D Legendre contraction on the tensor cores (langevin_tc.cu); returns 1 when it did not apply
+template <typename T> int run_tc(pyves_ctx*, const StepArgs<T>&, cudaStream_t) { return 1; }
+template <> int run_tc<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream_t st) {
+  const cudaError_t rc = launch_langevin2d_tc(A, integrator_params<float>(h), pot_params<float>(h), l2_params<float>(h), make_keys(h->seed), st);
+  if (rc == cudaErrorNotSupported) return 1;
+  if (rc != cudaSuccess) return fail(h, PYVES_ECUDA, std::string("launch_langevin2d_tc: ") + cudaGetErrorString(rc));
+  g_launches++;
+  return PYVES_OK;
+}
+
 template <typename T>
 int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t every, int64_t n_rec, cudaStream_t st) {
   StepArgs<T> A;
@@ -462,6 +472,10 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
     }
     case PYVES_BIAS_LEGENDRE_2D: {
       const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
+      if (h->variant == 7 || (h->variant == -1 && (kx > 16 || ky > 16 || kx * ky >= 196))) {
+        const int rc = run_tc<T>(h, A, st);
+        if (rc <= 0) return rc;
+      }
       const Legendre2DSmemParams<T> BP = l2_params<T>(h);
       // FP64 16 x 16: the static functor feeds every DFMA with its own LDC.64 (196 per step, ADU bound); the
       // shared-memory column sweep is 19 % faster there (1.83e10 vs 1.54e10 walker-steps/s), so doubles skip it

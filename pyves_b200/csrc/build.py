@@ -17,7 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]
 
-UNITS = [("api.cu", []), ("misc_kernels.cu", []), ("moments.cu", []), ("cov_tc.cu", []), ("comm.cu", [])]
+UNITS = [("api.cu", []), ("misc_kernels.cu", []), ("moments.cu", []), ("cov_tc.cu", []), ("comm.cu", []), ("langevin_tc.cu", [])]
 for grp in range(4):
     for t in ("float", "double"):
         UNITS.append(("langevin_inst.cu", ["-DPV_T=%s" % t, "-DPV_GROUP=%d" % grp]))

@@ -368,6 +368,10 @@ langevin_general_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const 
 // BiasLegendre2DStaticT<.., true> kernels read (same translation unit as those kernels); stream ordered
 template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n, cudaStream_t st);
 
+// experimental tensor-core step kernel for the 2D Legendre bias (langevin_tc.cu); cudaErrorNotSupported when it does not apply
+cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st);
+
 // launchers implemented in the langevin_*.cu translation units
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 cudaError_t launch_langevin2d(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,

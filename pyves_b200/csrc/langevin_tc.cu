@@ -1,0 +1,394 @@
+// Experimental step kernel: the per-step contraction of the 2D tensor-product Legendre bias on the tensor cores.
+//
+//   A_i = sum_j w_ij P_j(y'),  B_i = sum_j w_ij P'_j(y')   for the 128 walkers of a warp group
+//
+// is a [128 walkers x KY] x [KY x KX] product per step and per group.  The CUDA-core kernels (bias.cuh) spend 4 KX KY flops per
+// walker-step on it (64 x 64: 94 % of the step); here a group of 128 threads (thread = walker) writes its rows
+// (P_j, P'_j), split into FP16 hi + lo parts (22 mantissa bits together: FP32-level accuracy), straight into shared memory
+// in the canonical K-major SWIZZLE_128B UMMA layout, one thread issues
+//     D_A = P_hi W_hi^T + P_hi W_lo^T + P_lo W_hi^T            D_B = the same with P'
+// as tcgen05.mma kind::f16 (M = 128, N = KX, K = 16) into the group's TMEM columns, and after the commit every thread
+// reads ITS walker's row (A_i, B_i) back with tcgen05.ld (TMEM lane = walker) and finishes the step (x recursion, row
+// sweep, potential, noise, integrator) in registers.  A walker's steps are sequential, so the MMA round trip is latency
+// for that group; G groups per CTA (each with its own tiles, TMEM columns and mbarrier) keep the SM busy meanwhile.
+//
+// Selected with pyves_set_tuning(h, 7) for FP32 handles, kx, ky <= 64 (profiles/r02_tc_step.md has the measurements).
+#include <cuda_fp16.h>
+
+#include "langevin.cuh"
+
+namespace pv {
+
+namespace {
+
+constexpr int kGT = 128;                    // threads (= walkers) per group
+constexpr int kTileBytes = 128 * 128;       // [128 walkers][64 FP16] operand tile, 16 KB
+constexpr int kWBytes = 64 * 128;           // [64 i][64 j FP16] weight tile, 8 KB
+constexpr float kScaleP = 1024.f;           // P_j is carried as 1024 P_j, P'_j as 16 P'_j (|P'_63| = 2016): the FP16 lo parts stay normal
+constexpr float kScaleD = 16.f;
+
+PV_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PV_DEV uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+PV_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+PV_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TCS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TCS_DONE;\n\t"
+      "bra TCS_WAIT;\n\t"
+      "TCS_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+PV_DEV void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+PV_DEV void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+PV_DEV void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+PV_DEV void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 8 FP32 values -> 8 FP16 hi + 8 FP16 lo (x = hi + lo up to 2^-22 |x|), packed in memory order
+PV_DEV void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+    const float2 f = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v[2 * q] - f.x, v[2 * q + 1] - f.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+PV_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+}
+
+// The four operand matrices of a group (P_hi, P_lo, P'_hi, P'_lo: [128 walkers] x [KYP functions] FP16 each) share 128-byte rows:
+// operand s starts at byte s * 2 KYP of the concatenated row, i.e. in tile (2 s KYP) / 128 at byte offset (2 s KYP) % 128 --
+// one 16 KB tile per group for KYP = 16, two for 32, four for 64.  A UMMA descriptor may start anywhere inside the swizzle row
+// (that is how the K slabs of one matrix are addressed as well).
+template <int KYP> struct TcLayout {
+  static constexpr int kTiles = 4 * KYP * 2 / 128;                                   // 16 KB tiles per group
+  static __host__ __device__ constexpr int tile(int s) { return (s * KYP * 2) / 128; }
+  static __host__ __device__ constexpr int chunk0(int s) { return ((s * KYP * 2) % 128) / 16; }   // first 16-byte chunk of operand s
+};
+
+template <int KYP, int G, int WPT> struct TcSmem {
+  alignas(1024) unsigned char a[G][WPT][TcLayout<KYP>::kTiles][kTileBytes];
+  alignas(1024) unsigned char w[2][kWBytes];         // W_hi, W_lo: [64 i][64 j] FP16, 128-byte rows
+  alignas(8) uint64_t bar[G][WPT];                   // contraction done (tcgen05.commit)
+  alignas(8) uint64_t ready[G][WPT];                 // all 128 rows of the set written and last step's TMEM reads done (128 arrivals)
+  float red[32];
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr uint32_t tmem_cols(int need) { return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u; }
+
+// KXP / KYP = number of x / y functions padded to 16, 32 or 64 (UMMA N / K extent; weights beyond kx, ky are zero).
+// WPT walker sets per group (thread = one walker of each set): while the contraction of set 0 is in flight the threads
+// generate the rows of set 1, and sweep set 0 while set 1's is in flight -- the MMA round trip (store -> proxy fence ->
+// barrier -> MMA -> commit -> TMEM load, ~1.3 us) is latency that only independent walkers can hide.
+template <int KXP, int KYP, int G, int WPT, bool INJECT>
+__global__ void __launch_bounds__(kGT* G, 1)
+langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
+                     const Legendre2DSmemParams<float> BP, const RngKeys K) {
+  using LY = TcLayout<KYP>;
+  extern __shared__ unsigned char smem_raw[];
+  TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = tid / kGT, tl = tid % kGT;
+  constexpr uint32_t kCols = tmem_cols(G * WPT * 2 * KXP);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int q = 0; q < G * WPT; ++q) {
+      mbar_init(&sm.bar[0][0] + q, 1);
+      mbar_init(&sm.ready[0][0] + q, kGT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // scale of the weights: a power of two that brings max |w_ij| into [2^12, 2^13) (FP16 range), found by every block itself so
+  // that coefficients handed over on the device need no host copy
+  float wscale;
+  {
+    float m = 0.f;
+    for (int q = tid; q < BP.kx * BP.ky; q += blockDim.x) m = fmaxf(m, fabsf(BP.w[q]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm.red[warp] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm.red[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3e38f) frexpf(m, &ex);
+    wscale = ldexpf(1.f, 13 - ex);
+  }
+  // weights -> W_hi, W_lo tiles: row i (N index), 64 j (K index), scaled by wscale (undone after the sweep)
+  for (int item = tid; item < 64 * 8; item += blockDim.x) {
+    const int i = item >> 3, c = item & 7;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = 8 * c + q;
+      v[q] = (i < BP.kx && j < BP.ky) ? BP.w[i * BP.ky + j] * wscale : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)(i >> 3) * 1024u + (uint32_t)(i & 7) * 128u + (uint32_t)((c ^ (i & 7)) << 4);
+    sts128(smem_u32(sm.w[0]) + off, hi);
+    sts128(smem_u32(sm.w[1]) + off, lo);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;           // this warp's TMEM lanes
+  const uint32_t row_off = (uint32_t)(tl >> 3) * 1024u + (uint32_t)(tl & 7) * 128u;
+  const uint64_t dWhi = umma_desc_k_sw128(smem_u32(sm.w[0])), dWlo = umma_desc_k_sw128(smem_u32(sm.w[1]));
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(KXP >> 3) << 17) | ((128u >> 4) << 24);
+  const float inv_a = 1.f / (kScaleP * wscale), inv_b = 1.f / (kScaleD * wscale);   // powers of two: exact
+
+  // operand s of set k: tile LY::tile(s), starting LY::chunk0(s) 16-byte chunks into the 128-byte row
+  uint64_t dsc[WPT][4];
+#pragma unroll
+  for (int k = 0; k < WPT; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dsc[k][q] = umma_desc_k_sw128(smem_u32(sm.a[g][k][0]) + LY::tile(q) * kTileBytes) + (uint64_t)LY::chunk0(q);
+
+  int64_t wk[WPT];
+  bool live[WPT];
+  float x[WPT], y[WPT], vx[WPT], vy[WPT], zodd_x[WPT], zodd_y[WPT];
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const int64_t idx = (((int64_t)blockIdx.x * G + g) * WPT + k) * kGT + tl;
+    live[k] = idx < A.n;
+    wk[k] = live[k] ? idx : A.n - 1;
+    x[k] = A.pos[wk[k]];
+    y[k] = A.pos[A.n + wk[k]];
+    vx[k] = A.vel[wk[k]];
+    vy[k] = A.vel[A.n + wk[k]];
+    zodd_x[k] = zodd_y[k] = 0.f;
+  }
+
+  uint32_t parity = 0;
+  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+    const int64_t t = A.step0 + ts;
+    float sx[WPT], gx[WPT], gy[WPT], zx[WPT], zy[WPT];
+    bool inx[WPT], iny[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const uint32_t tiles = smem_u32(sm.a[g][k][0]);
+      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // D_A [0, KXP), D_B [KXP, 2 KXP)
+      sx[k] = scale_clamp(x[k], BP.cx, BP.ihx, inx[k]);
+      const float sy = scale_clamp(y[k], BP.cy, BP.ihy, iny[k]);
+      // ---- rows (1024 P_j(sy), 16 P'_j(sy)), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
+      {
+        float pm = kScaleP, p = kScaleP * sy;              // 1024 P_0, 1024 P_1
+        float dpm = 0.f, dp = kScaleD;                     // 16 P'_0, 16 P'_1
+#pragma unroll
+        for (int c = 0; c < KYP / 8; ++c) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int j = 8 * c + q;
+            if (j == 0) {
+              pv[q] = pm;
+              dv[q] = dpm;
+            } else if (j == 1) {
+              pv[q] = p;
+              dv[q] = dp;
+            } else {
+              const float pn = leg_a<float>(j - 1) * sy * p - leg_b<float>(j - 1) * pm;
+              const float dn = fmaf(leg_c<float>(j - 1) * (kScaleD / kScaleP), p, dpm);
+              pm = p; p = pn; dpm = dp; dp = dn;
+              pv[q] = pn;
+              dv[q] = dn;
+            }
+          }
+          uint4 hi, lo;
+          auto addr = [&](int sidx) {     // 16-byte chunk c of operand sidx in this walker's row (Swizzle<3,4,3>: chunk ^ row % 8)
+            return tiles + (uint32_t)(LY::tile(sidx) * kTileBytes) + row_off + (uint32_t)(((LY::chunk0(sidx) + c) ^ (tl & 7)) << 4);
+          };
+          split8(pv, hi, lo);
+          sts128(addr(0), hi);
+          sts128(addr(1), lo);
+          split8(dv, hi, lo);
+          sts128(addr(2), hi);
+          sts128(addr(3), lo);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      // no block-wide barrier: every thread ARRIVES (its row is written, its TMEM reads of the last step are done) and goes on
+      // with the work that does not need the contraction; only the issuing thread waits for the 128 arrivals
+      mbar_arrive(&sm.ready[g][k]);
+      if (tl == 0) {
+        mbar_wait(&sm.ready[g][k], parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dPhi = dsc[k][0], dPlo = dsc[k][1], dDhi = dsc[k][2], dDlo = dsc[k][3];
+#pragma unroll
+        for (int kk = 0; kk < KYP / 16; ++kk) {                      // K = 16 per instruction: 32 bytes = +2 in 16-byte units
+          const uint64_t o = (uint64_t)(kk * 2);
+          umma_f16(tmem, dPhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+          umma_f16(tmem, dPhi + o, dWlo + o, kIdesc, 1u);
+          umma_f16(tmem, dPlo + o, dWhi + o, kIdesc, 1u);
+          umma_f16(tmem + (uint32_t)KXP, dDhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+          umma_f16(tmem + (uint32_t)KXP, dDhi + o, dWlo + o, kIdesc, 1u);
+          umma_f16(tmem + (uint32_t)KXP, dDlo + o, dWhi + o, kIdesc, 1u);
+        }
+        umma_commit(&sm.bar[g][k]);
+      }
+      // ---- independent of the contraction: potential gradient and noise (overlaps the MMA round trip)
+      float e = 0.f;
+      gx[k] = gy[k] = 0.f;
+      PotGeneric<float>::template grad<false>(PP, x[k], y[k], e, gx[k], gy[k]);
+      if (INJECT) {
+        zx[k] = A.noise[(ts * 2) * A.n + wk[k]];
+        zy[k] = A.noise[(ts * 2 + 1) * A.n + wk[k]];
+      } else if (!(t & 1) || ts == 0) {
+        const uint4 r = philox_call(A.gid0 + (uint64_t)wk[k], (uint64_t)(t >> 1), kStreamDyn2, K);
+        float z0, z1, z2, z3;
+        box_muller(r.x, r.y, z0, z1);
+        box_muller(r.z, r.w, z2, z3);
+        if (t & 1) {
+          zx[k] = z2;
+          zy[k] = z3;
+        } else {
+          zx[k] = z0;
+          zy[k] = z1;
+          zodd_x[k] = z2;
+          zodd_y[k] = z3;
+        }
+      } else {
+        zx[k] = zodd_x[k];
+        zy[k] = zodd_y[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
+      // ---- this walker's (A_i, B_i) from TMEM, x recursion and row sweep, 16 functions at a time
+      mbar_wait(&sm.bar[g][k], parity);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
+      {
+        float pxm = 1.f, px = sx[k], dpxm = 0.f, dpx = 1.f;
+#pragma unroll
+        for (int i0 = 0; i0 < KXP; i0 += 16) {
+          float av[16], bv[16];
+          tmem_ld16(tmem + tlane + (uint32_t)i0, av);
+          tmem_ld16(tmem + tlane + (uint32_t)(KXP + i0), bv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int i = i0 + q;
+            float pi, di;
+            if (i == 0) {
+              pi = 1.f;
+              di = 0.f;
+            } else if (i == 1) {
+              pi = px;
+              di = dpx;
+            } else {
+              const float pn = leg_a<float>(i - 1) * sx[k] * px - leg_b<float>(i - 1) * pxm;
+              const float dn = fmaf(leg_c<float>(i - 1), px, dpxm);
+              pxm = px; px = pn; dpxm = dpx; dpx = dn;
+              pi = pn;
+              di = dn;
+            }
+            if (q & 1) {
+              Gx1 = fmaf(di, av[q], Gx1);
+              Gy1 = fmaf(pi, bv[q], Gy1);
+            } else {
+              Gx0 = fmaf(di, av[q], Gx0);
+              Gy0 = fmaf(pi, bv[q], Gy0);
+            }
+          }
+        }
+      }
+      const float fx = gx[k] + (inx[k] ? (Gx0 + Gx1) * inv_a * BP.ihx : 0.f);
+      const float fy = gy[k] + (iny[k] ? (Gy0 + Gy1) * inv_b * BP.ihy : 0.f);
+      vx[k] = fmaf(I.c_over_sqrtm, zx[k], fmaf(-I.b_over_m, fx, I.a * vx[k]));
+      vy[k] = fmaf(I.c_over_sqrtm, zy[k], fmaf(-I.b_over_m, fy, I.a * vy[k]));
+      x[k] = fmaf(I.dt, vx[k], x[k]);
+      y[k] = fmaf(I.dt, vy[k], y[k]);
+    }
+    parity ^= 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    if (live[k]) {
+      A.pos[wk[k]] = x[k];
+      A.pos[A.n + wk[k]] = y[k];
+      A.vel[wk[k]] = vx[k];
+      A.vel[A.n + wk[k]] = vy[k];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
+}
+
+template <int KXP, int KYP, int G, int WPT>
+cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                      const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
+  auto kern = A.noise != nullptr ? langevin2d_tc_kernel<KXP, KYP, G, WPT, true> : langevin2d_tc_kernel<KXP, KYP, G, WPT, false>;
+  const size_t smem = sizeof(TcSmem<KYP, G, WPT>) + 1024;
+  static_assert(sizeof(TcSmem<KYP, G, WPT>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
+  static_assert(G * WPT * 2 * KXP <= 512, "accumulators do not fit the TMEM columns of an SM");
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t per_block = (int64_t)kGT * G * WPT;
+  const unsigned grid = (unsigned)((A.n + per_block - 1) / per_block);
+  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
+
+template <int KXP>
+cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                         const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
+  // groups per CTA: 64 KB of operand tiles per group at KYP = 64 (three fit), 32 / 16 KB below (four: 512 threads at <= 128 registers)
+  if (BP.ky <= 16) return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+  if (BP.ky <= 32) return launch_tc<KXP, 32, 3, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+  return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, st);
+}
+
+}  // namespace
+
+cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
+  if (BP.kx > 64 || BP.ky > 64 || BP.kx < 1 || BP.ky < 1 || A.traj != nullptr) return cudaErrorNotSupported;
+  if (BP.kx <= 16) return launch_tc_ky<16>(A, I, PP, BP, K, st);
+  if (BP.kx <= 32) return launch_tc_ky<32>(A, I, PP, BP, K, st);
+  return launch_tc_ky<64>(A, I, PP, BP, K, st);
+}
+
+}  // namespace pv

