@@ -502,6 +502,9 @@ def config_legs(args, rank, world, local, dev, peak):
         if "tc_kernel" in kernel:
             K = int(name.split("_")[1].split("x")[0]) if name.startswith("cfg5_") else args.basis
             extra["tensor"] = tensor_roofline(K, n_rank * stride / (kms * 1e-3))["tensor"]
+        elif "tc_mlp_kernel" in kernel:
+            ex = 12.0 * 48 * 48
+            extra["tensor"] = {"executed_flops_per_walker_step": ex, "achieved": ex * n_rank * stride / (kms * 1e-3) * 1e-12, "unit": "TFLOP/s"}
         row(name, workload, n_rank, n_total, stride, sec, kms, kernel, flops, scaling, extra)
         upd.close()
         e.close()
@@ -531,7 +534,10 @@ def config_legs(args, rank, world, local, dev, peak):
                                      beta, "Adam", {"lr": 1e-3}, target_update_every=0, gradient_average='running')
     updater_leg("cfg4", "configs[3]: Szabo-Berezhkovskii + NNBasis1D [48,48,48] (ReLU), Adam 1e-3, running-average gradients, uniform target, "
                 "10^6 walkers per GPU", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII, (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000,
-                1000000 * world, args.stride, 2, "langevin2d_kernel<SzaboBerezhkovskii, Mlp<48>>", LEG_FLOPS["cfg4"], "weak")
+                1000000 * world, args.stride, 2, "langevin2d_tc_mlp_kernel<48, ReLU, 3> (48 x 48 layer on the tensor cores)", LEG_FLOPS["cfg4"], "weak")
+    updater_leg("cfg4_cuda_cores", "configs[3] with the step kernel forced onto the CUDA cores (pyves_set_tuning 6)", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII,
+                (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000, 1000000 * world, args.stride, 2,
+                "langevin2d_kernel<SzaboBerezhkovskii, Mlp<48>> (CUDA cores, FFMA2 input sweep)", LEG_FLOPS["cfg4"], "weak", variant=6)
 
     # cfg5 (configs[4]): K x K bases, uniform target; weak points at 10^6 walkers per GPU and a 64 x 64 strong point at 10^7 in total
     def leg2d(K):

@@ -427,6 +427,17 @@ template <> int run_tc<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream
   return PYVES_OK;
 }
 
+// the H x H layer of the three-hidden-layer NN bias on the tensor cores (langevin_tc.cu); same conventions as run_tc
+template <typename T> int run_tc_mlp(pyves_ctx*, const StepArgs<T>&, cudaStream_t) { return 1; }
+template <> int run_tc_mlp<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream_t st) {
+  const cudaError_t rc = launch_langevin2d_tc_mlp(A, integrator_params<float>(h), pot_params<float>(h), mlp_params<float>(h), h->mlp_H, h->mlp_act,
+                                                  make_keys(h->seed), st);
+  if (rc == cudaErrorNotSupported) return 1;
+  if (rc != cudaSuccess) return fail(h, PYVES_ECUDA, std::string("launch_langevin2d_tc_mlp: ") + cudaGetErrorString(rc));
+  g_launches++;
+  return PYVES_OK;
+}
+
 template <typename T>
 int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t every, int64_t n_rec, cudaStream_t st) {
   StepArgs<T> A;
@@ -511,6 +522,10 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       const MlpParams<T> BP = mlp_params<T>(h);
       const bool relu = h->mlp_act == PYVES_ACT_RELU;
       const bool sb = pk == PYVES_POT_SZABO_BEREZHKOVSKII && relu;
+      if (h->mlp_H > 0 && (h->variant == -1 || h->variant == 7)) {      // one H x H layer: on the tensor cores (variant 6: CUDA cores)
+        const int rc = run_tc_mlp<T>(h, A, st);
+        if (rc <= 0) return rc;
+      }
       switch (h->mlp_H) {
         case 0:
           if (sb) return run_fast<T, SB, BiasMlp<T, 0, PYVES_ACT_RELU>, 2, 1>(h, A, BP, st);

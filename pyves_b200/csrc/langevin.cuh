@@ -372,6 +372,9 @@ template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n,
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                                  const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st);
 
+cudaError_t launch_langevin2d_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                                     const MlpParams<float>& BP, int H, int act, const RngKeys& K, cudaStream_t st);
+
 // launchers implemented in the langevin_*.cu translation units
 template <typename T, class Pot, class Bias, int WPT, int MINB>
 cudaError_t launch_langevin2d(const StepArgs<T>& A, const IntegratorParams<T>& I, const PotParams<T>& PP,

@@ -372,6 +372,224 @@ cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// NN bias (NNBasis1D with three hidden layers, folded as in bias.cuh: z1 = u s + c): the one H x H layer
+//     z2_j = b2_j + sum_i W2[j][i] h_i,   dz2_j/ds = sum_i W2[j][i] dh_i/ds          (h_i = act(z1_i), dh_i = act'(z1_i) u_i)
+// is the same [128 walkers x H] x [H x H] product per step: rows (h_i | dh_i) as FP16 hi + lo, B = W2 (row j = output unit),
+// epilogue per thread: activation of z2_j, output layer, chain rule.  The vectors u, c, wout, b2 are read from shared memory
+// as 128-bit broadcasts.  H = 32 / 48 / 64 (the padded width the host packs, pyves_set_bias_mlp).
+template <int H, int G> struct TcMlpSmem {
+  alignas(1024) unsigned char a[G][4][kTileBytes];   // per group: h_hi, h_lo, dh_hi, dh_lo
+  alignas(1024) unsigned char w[2][kWBytes];         // W2_hi, W2_lo: [H j][H i] FP16, 128-byte rows
+  alignas(16) float vec[4 * H + 4];                  // u, c, wout, b2, bout
+  alignas(8) uint64_t bar[G];
+  alignas(8) uint64_t ready[G];
+  float red[32];
+  uint32_t tmem_base;
+};
+
+template <int H, int ACT, int G, bool INJECT>
+__global__ void __launch_bounds__(kGT* G, 1)
+langevin2d_tc_mlp_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
+                         const MlpParams<float> BP, const RngKeys K) {
+  extern __shared__ unsigned char smem_raw[];
+  TcMlpSmem<H, G>& sm = *reinterpret_cast<TcMlpSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = tid / kGT, tl = tid % kGT;
+  constexpr uint32_t kCols = tmem_cols(G * 2 * H);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int q = 0; q < G; ++q) {
+      mbar_init(&sm.bar[q], 1);
+      mbar_init(&sm.ready[q], kGT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const float* W2T = BP.packed + 4 * H;              // W2T[i][j] = W2[j][i]
+  for (int q = tid; q < 4 * H + 4; q += blockDim.x) sm.vec[q] = q < 4 * H ? BP.packed[q] : BP.packed[4 * H + H * H + (q - 4 * H)];
+  float wscale;
+  {
+    float m = 0.f;
+    for (int q = tid; q < H * H; q += blockDim.x) m = fmaxf(m, fabsf(W2T[q]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm.red[warp] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm.red[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3e38f) frexpf(m, &ex);
+    wscale = ldexpf(1.f, 13 - ex);
+  }
+  for (int item = tid; item < H * (H / 8); item += blockDim.x) {     // row j (N index), chunk c of 8 inputs i (K index)
+    const int j = item / (H / 8), c = item % (H / 8);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = W2T[(8 * c + q) * H + j] * wscale;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)(j >> 3) * 1024u + (uint32_t)(j & 7) * 128u + (uint32_t)((c ^ (j & 7)) << 4);
+    sts128(smem_u32(sm.w[0]) + off, hi);
+    sts128(smem_u32(sm.w[1]) + off, lo);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t row_off = (uint32_t)(tl >> 3) * 1024u + (uint32_t)(tl & 7) * 128u;
+  const uint64_t dWhi = umma_desc_k_sw128(smem_u32(sm.w[0])), dWlo = umma_desc_k_sw128(smem_u32(sm.w[1]));
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((128u >> 4) << 24);
+  const float inv_w = 1.f / wscale;
+  const uint32_t tiles = smem_u32(sm.a[g][0]);
+  uint64_t dsc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dsc[q] = umma_desc_k_sw128(tiles + q * kTileBytes);
+  const uint32_t tmem = sm.tmem_base + (uint32_t)(g * 2 * H);       // D_z [0, H), D_dz [H, 2 H)
+  const float* uvec = sm.vec;
+  const float* cvec = sm.vec + H;
+  const float* wout = sm.vec + 2 * H;
+  const float* b2 = sm.vec + 3 * H;
+  const float bout = sm.vec[4 * H];
+
+  const int64_t idx = ((int64_t)blockIdx.x * G + g) * kGT + tl;
+  const bool live = idx < A.n;
+  const int64_t w = live ? idx : A.n - 1;
+  float x = A.pos[w], y = A.pos[A.n + w], vx = A.vel[w], vy = A.vel[A.n + w];
+  float zodd_x = 0.f, zodd_y = 0.f;
+  uint32_t parity = 0;
+  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+    const int64_t t = A.step0 + ts;
+    const float sc = ((BP.axis ? y : x) - BP.lo) * BP.inv_range;
+    // ---- rows (h_i, dh_i/ds), i < H, as FP16 hi / lo
+#pragma unroll
+    for (int c = 0; c < H / 8; ++c) {
+      float hv[8], dv[8];
+#pragma unroll
+      for (int q4 = 0; q4 < 2; ++q4) {
+        float u4[4], c4[4];
+        lds_vec(uvec + 8 * c + 4 * q4, u4);
+        lds_vec(cvec + 8 * c + 4 * q4, c4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float d;
+          hv[4 * q4 + q] = act_fn<float, ACT>(fmaf(u4[q], sc, c4[q]), d);
+          dv[4 * q4 + q] = d * u4[q];
+        }
+      }
+      uint4 hi, lo;
+      const uint32_t off = row_off + (uint32_t)((c ^ (tl & 7)) << 4);
+      split8(hv, hi, lo);
+      sts128(tiles + off, hi);
+      sts128(tiles + kTileBytes + off, lo);
+      split8(dv, hi, lo);
+      sts128(tiles + 2 * kTileBytes + off, hi);
+      sts128(tiles + 3 * kTileBytes + off, lo);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&sm.ready[g]);
+    if (tl == 0) {
+      mbar_wait(&sm.ready[g], parity);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < H / 16; ++kk) {
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_f16(tmem, dsc[0] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+        umma_f16(tmem, dsc[0] + o, dWlo + o, kIdesc, 1u);
+        umma_f16(tmem, dsc[1] + o, dWhi + o, kIdesc, 1u);
+        umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+        umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWlo + o, kIdesc, 1u);
+        umma_f16(tmem + (uint32_t)H, dsc[3] + o, dWhi + o, kIdesc, 1u);
+      }
+      umma_commit(&sm.bar[g]);
+    }
+    float gx = 0.f, gy = 0.f, e = 0.f;
+    PotGeneric<float>::template grad<false>(PP, x, y, e, gx, gy);
+    float zx, zy;
+    if (INJECT) {
+      zx = A.noise[(ts * 2) * A.n + w];
+      zy = A.noise[(ts * 2 + 1) * A.n + w];
+    } else if (!(t & 1) || ts == 0) {
+      const uint4 r = philox_call(A.gid0 + (uint64_t)w, (uint64_t)(t >> 1), kStreamDyn2, K);
+      float z0, z1, z2, z3;
+      box_muller(r.x, r.y, z0, z1);
+      box_muller(r.z, r.w, z2, z3);
+      if (t & 1) {
+        zx = z2;
+        zy = z3;
+      } else {
+        zx = z0;
+        zy = z1;
+        zodd_x = z2;
+        zodd_y = z3;
+      }
+    } else {
+      zx = zodd_x;
+      zy = zodd_y;
+    }
+    // ---- epilogue: this walker's (z2_j, dz2_j/ds), activation, output layer
+    mbar_wait(&sm.bar[g], parity);
+    parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float dval0 = 0.f, dval1 = 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < H; j0 += 16) {
+      float zv[16], dz[16];
+      tmem_ld16(tmem + tlane + (uint32_t)j0, zv);
+      tmem_ld16(tmem + tlane + (uint32_t)(H + j0), dz);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float b4[4], w4[4];
+        lds_vec(b2 + j0 + 4 * q4, b4);
+        lds_vec(wout + j0 + 4 * q4, w4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float d;
+          (void)act_fn<float, ACT>(fmaf(zv[4 * q4 + q], inv_w, b4[q]), d);
+          if (q & 1) dval1 = fmaf(w4[q] * d, dz[4 * q4 + q], dval1);
+          else dval0 = fmaf(w4[q] * d, dz[4 * q4 + q], dval0);
+        }
+      }
+    }
+    (void)bout;
+    const float gb = (dval0 + dval1) * inv_w * BP.inv_range;
+    gx += BP.axis ? 0.f : gb;
+    gy += BP.axis ? gb : 0.f;
+    vx = fmaf(I.c_over_sqrtm, zx, fmaf(-I.b_over_m, gx, I.a * vx));
+    vy = fmaf(I.c_over_sqrtm, zy, fmaf(-I.b_over_m, gy, I.a * vy));
+    x = fmaf(I.dt, vx, x);
+    y = fmaf(I.dt, vy, y);
+  }
+  if (live) {
+    A.pos[w] = x;
+    A.pos[A.n + w] = y;
+    A.vel[w] = vx;
+    A.vel[A.n + w] = vy;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
+}
+
+template <int H, int ACT>
+cudaError_t launch_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
+                          const RngKeys& K, cudaStream_t st) {
+  constexpr int G = 3;
+  auto kern = A.noise != nullptr ? langevin2d_tc_mlp_kernel<H, ACT, G, true> : langevin2d_tc_mlp_kernel<H, ACT, G, false>;
+  const size_t smem = sizeof(TcMlpSmem<H, G>) + 1024;
+  static_assert(sizeof(TcMlpSmem<H, G>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t per_block = (int64_t)kGT * G;
+  kern<<<(unsigned)((A.n + per_block - 1) / per_block), kGT * G, smem, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
+
 template <int KXP>
 cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                          const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
@@ -389,6 +607,19 @@ cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParam
   if (BP.kx <= 16) return launch_tc_ky<16>(A, I, PP, BP, K, st);
   if (BP.kx <= 32) return launch_tc_ky<32>(A, I, PP, BP, K, st);
   return launch_tc_ky<64>(A, I, PP, BP, K, st);
+}
+
+// NN bias with three hidden layers packed at width H = 32 / 48 / 64 (MlpParams::packed of pyves_set_bias_mlp[_device])
+cudaError_t launch_langevin2d_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
+                                     const MlpParams<float>& BP, int H, int act, const RngKeys& K, cudaStream_t st) {
+  if (A.traj != nullptr || BP.linear) return cudaErrorNotSupported;
+  const bool relu = act == PYVES_ACT_RELU;
+  switch (H) {
+    case 32: return relu ? launch_tc_mlp<32, PYVES_ACT_RELU>(A, I, PP, BP, K, st) : launch_tc_mlp<32, PYVES_ACT_TANH>(A, I, PP, BP, K, st);
+    case 48: return relu ? launch_tc_mlp<48, PYVES_ACT_RELU>(A, I, PP, BP, K, st) : launch_tc_mlp<48, PYVES_ACT_TANH>(A, I, PP, BP, K, st);
+    case 64: return relu ? launch_tc_mlp<64, PYVES_ACT_RELU>(A, I, PP, BP, K, st) : launch_tc_mlp<64, PYVES_ACT_TANH>(A, I, PP, BP, K, st);
+    default: return cudaErrorNotSupported;
+  }
 }
 
 }  // namespace pv

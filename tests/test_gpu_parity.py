@@ -217,10 +217,11 @@ TRAJ_CASES = [
     ("slip_leg1d12", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg1d", r, degree=12, min=-3.0, max=6.0, scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1]),
     ("slip_forced_leg1d7y", potentials.SLIP_BOND_2D, (1.5, -0.5, 0.8, 4.0, 3.0, 0.2, 2.5), lambda r: rng_spec("leg1d", r, degree=7, axis='y', min=-4.0, max=6.0, scale=1.0), (-3.0, -2.5, -3.0, -2.5), [-1]),
     ("sb_none", potentials.SZABO_BEREZHKOVSKII, None, lambda r: dict(kind="none"), (2.0, 2.4, 2.0, 2.4), [-1]),
-    ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
     ("sb_mlp128x2", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[128, 128]), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("sb_mlp16", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[16]), (2.0, 2.4, 2.0, 2.4), [-1]),
-    ("catch_mlp_tanh", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[20, 30, 24], act=1), (-3.7, -3.2, -3.7, -3.2), [-1]),
+    ("catch_mlp_tanh", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[20, 30, 24], act=1), (-3.7, -3.2, -3.7, -3.2), [-1, 6]),
+    ("sb_mlp_64_tanh", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[64, 64, 56], act=1, scale=0.25), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
     ("catch_mlp_deep", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[8, 12, 10, 6]), (-3.7, -3.2, -3.7, -3.2), [-1]),
     ("mb_leg1d", potentials.MULLER_BROWN, None, lambda r: rng_spec("leg1d", r, degree=9, min=-1.5, max=1.0, scale=0.5), (-0.6, -0.5, 1.4, 1.5), [-1]),
     ("sw1d_leg1d", potentials.SINGLE_WELL_1D, None, lambda r: rng_spec("leg1d", r, degree=3, min=-2.0, max=2.0), (-0.3, 0.3, -0.01, 0.01), [-1]),
