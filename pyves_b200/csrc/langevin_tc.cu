@@ -15,6 +15,8 @@
 // Selected with pyves_set_tuning(h, 7) for FP32 handles, kx, ky <= 64 (profiles/r02_tc_step.md has the measurements).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "langevin.cuh"
 
 namespace pv {
@@ -206,7 +208,6 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
       const uint32_t tiles = smem_u32(sm.a[g][k][0]);
-      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // D_A [0, KXP), D_B [KXP, 2 KXP)
       sx[k] = scale_clamp(x[k], BP.cx, BP.ihx, inx[k]);
       const float sy = scale_clamp(y[k], BP.cy, BP.ihy, iny[k]);
       // ---- rows (1024 P_j(sy), 16 P'_j(sy)), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
@@ -245,11 +246,17 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
           sts128(addr(3), lo);
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      // no block-wide barrier: every thread ARRIVES (its row is written, its TMEM reads of the last step are done) and goes on
-      // with the work that does not need the contraction; only the issuing thread waits for the 128 arrivals
-      mbar_arrive(&sm.ready[g][k]);
+    }
+    // rows of every walker set are written back to back (independent recursions interleave in the instruction stream), then
+    // ONE proxy fence; no block-wide barrier: every thread ARRIVES (its rows are written, its TMEM reads of the last step are
+    // done) and goes on with the work that does not need the contraction; only the issuing thread waits for the 128 arrivals
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) mbar_arrive(&sm.ready[g][k]);
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // D_A [0, KXP), D_B [KXP, 2 KXP)
       if (tl == 0) {
         mbar_wait(&sm.ready[g][k], parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -594,8 +601,33 @@ template <int KXP>
 cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                          const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
   // groups per CTA: 64 KB of operand tiles per group at KYP = 64 (three fit), 32 / 16 KB below (four: 512 threads at <= 128 registers)
-  if (BP.ky <= 16) return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
-  if (BP.ky <= 32) return launch_tc<KXP, 32, 3, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+  // groups per CTA x walker sets per group, measured on B200 (10^6 walkers, profiles/r02_tc_step_shapes.md): the kernels are bound by
+  // instruction issue and dependent FP32 chains, so more resident warps (6 groups at <= 80 registers) beat two walker sets per thread
+  static const int shape = getenv("PYVES_TC_SHAPE") ? atoi(getenv("PYVES_TC_SHAPE")) : 0;     // experiment knob: G * 10 + WPT
+  if (BP.ky <= 16) {
+    if (KXP == 16) {
+      switch (shape) {
+        case 41: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, st);
+        case 42: return launch_tc<16, 16, 4, 2>(A, I, PP, BP, K, st);
+        case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, st);
+        case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, st);
+        case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, st);
+        default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, st);
+      }
+    }
+    return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+  }
+  if (BP.ky <= 32) {
+    if (KXP == 32) {
+      switch (shape) {
+        case 41: return launch_tc<32, 32, 4, 1>(A, I, PP, BP, K, st);
+        case 51: return launch_tc<32, 32, 5, 1>(A, I, PP, BP, K, st);
+        case 32: return launch_tc<32, 32, 3, 2>(A, I, PP, BP, K, st);
+        default: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, st);
+      }
+    }
+    return launch_tc<KXP, 32, 3, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+  }
   return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, st);
 }
 
