@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default); strong: --walkers-total sharded over the ranks")
     ap.add_argument("--walkers-total", type=int, default=10000000, help="ensemble size of --scaling strong")
-    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: wall-clock budget (s) of the whole run")
+    ap.add_argument("--ref-budget", type=float, default=280.0, help="--impl reference: wall-clock budget (s) of the whole run")
     a = ap.parse_args()
     if a.scaling == "strong":
         world = int(os.environ.get("WORLD_SIZE", 1))
