@@ -65,15 +65,22 @@ PV_DEV void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 8 FP32 values -> 8 FP16 hi + 8 FP16 lo (x = hi + lo up to 2^-22 |x|), packed in memory order
+// 8 FP32 values -> 8 FP16 hi + 8 FP16 lo (x = hi + lo up to 2^-22 |x|), packed in memory order.  The remainder x - hi is ONE
+// mixed-precision instruction per value (PTX fma.rn.f32.f16 -> SASS FHFMA: FP16 hi times -1 plus FP32 x, exact), not a
+// conversion followed by a subtraction.
+PV_DEV float sub_half(float x, uint32_t packed, int upper) {
+  const unsigned short h = (unsigned short)(upper ? packed >> 16 : packed & 0xffffu), m1 = 0xBC00;   // -1.0 in FP16
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(h), "h"(m1), "f"(x));
+  return d;
+}
 PV_DEV void split8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-    const float2 f = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(v[2 * q] - f.x, v[2 * q + 1] - f.y);
     h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+    const __half2 ll = __floats2half2_rn(sub_half(v[2 * q], h[q], 0), sub_half(v[2 * q + 1], h[q], 1));
     l[q] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
