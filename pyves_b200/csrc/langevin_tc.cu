@@ -98,6 +98,15 @@ PV_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
 }
 
+PV_DEV void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
+}
+
 // The four operand matrices of a group (P_hi, P_lo, P'_hi, P'_lo: [128 walkers] x [KYP functions] FP16 each) share 128-byte rows:
 // operand s starts at byte s * 2 KYP of the concatenated row, i.e. in tile (2 s KYP) / 128 at byte offset (2 s KYP) % 128 --
 // one 16 KB tile per group for KYP = 16, two for 32, four for 64.  A UMMA descriptor may start anywhere inside the swizzle row
@@ -212,6 +221,58 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     const int64_t t = A.step0 + ts;
     float sx[WPT], gx[WPT], gy[WPT], zx[WPT], zy[WPT];
     bool inx[WPT], iny[WPT];
+    if constexpr (WPT == 2) {
+      // two walkers per thread: both y recursions run as ONE packed FP32x2 chain (FMUL2 / FFMA2 with the recursion
+      // coefficients as broadcast immediates), the halves go to the rows of set 0 and set 1
+      using Q = Pair<float>;
+      sx[0] = scale_clamp(x[0], BP.cx, BP.ihx, inx[0]);
+      sx[1] = scale_clamp(x[1], BP.cx, BP.ihx, inx[1]);
+      const float sy0 = scale_clamp(y[0], BP.cy, BP.ihy, iny[0]), sy1 = scale_clamp(y[1], BP.cy, BP.ihy, iny[1]);
+      const Q yy = Q::make(sy0, sy1);
+      Q pm = Q::make(kScaleP, kScaleP), p = Q::mul_bcast(yy, kScaleP);
+      Q dpm = Q::make(0.f, 0.f), dp = Q::make(kScaleD, kScaleD);
+      const uint32_t tiles0 = smem_u32(sm.a[g][0][0]), tiles1 = smem_u32(sm.a[g][1][0]);
+#pragma unroll
+      for (int c = 0; c < KYP / 8; ++c) {
+        float pv0[8], dv0[8], pv1[8], dv1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = 8 * c + q;
+          Q P, D;
+          if (j == 0) {
+            P = pm;
+            D = dpm;
+          } else if (j == 1) {
+            P = p;
+            D = dp;
+          } else {
+            const Q pn = Q::fma(Q::mul_bcast(yy, leg_a<float>(j - 1)), p, Q::mul_bcast(pm, -leg_b<float>(j - 1)));
+            const Q dn = Q::fma_bcast(p, leg_c<float>(j - 1) * (kScaleD / kScaleP), dpm);
+            pm = p; p = pn; dpm = dp; dp = dn;
+            P = pn;
+            D = dn;
+          }
+          pv0[q] = P.lo(); pv1[q] = P.hi();
+          dv0[q] = D.lo(); dv1[q] = D.hi();
+        }
+        uint4 hi, lo;
+        auto off = [&](int sidx) {
+          return (uint32_t)(LY::tile(sidx) * kTileBytes) + row_off + (uint32_t)(((LY::chunk0(sidx) + c) ^ (tl & 7)) << 4);
+        };
+        split8(pv0, hi, lo);
+        sts128(tiles0 + off(0), hi);
+        sts128(tiles0 + off(1), lo);
+        split8(dv0, hi, lo);
+        sts128(tiles0 + off(2), hi);
+        sts128(tiles0 + off(3), lo);
+        split8(pv1, hi, lo);
+        sts128(tiles1 + off(0), hi);
+        sts128(tiles1 + off(1), lo);
+        split8(dv1, hi, lo);
+        sts128(tiles1 + off(2), hi);
+        sts128(tiles1 + off(3), lo);
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
       const uint32_t tiles = smem_u32(sm.a[g][k][0]);
@@ -253,6 +314,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
           sts128(addr(3), lo);
         }
       }
+    }
     }
     // rows of every walker set are written back to back (independent recursions interleave in the instruction stream), then
     // ONE proxy fence; no block-wide barrier: every thread ARRIVES (its rows are written, its TMEM reads of the last step are
@@ -306,6 +368,57 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
         zy[k] = zodd_y[k];
       }
     }
+    if constexpr (WPT == 2) {
+      // packed x recursion for the two walkers; the row sums stay scalar (the two walkers' rows come from different TMEM columns)
+      using Q = Pair<float>;
+      const uint32_t tmem0 = sm.tmem_base + (uint32_t)((g * 2) * 2 * KXP) + tlane, tmem1 = tmem0 + (uint32_t)(2 * KXP);
+      mbar_wait(&sm.bar[g][0], parity);
+      mbar_wait(&sm.bar[g][1], parity);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float Gx[2] = {0.f, 0.f}, Gy[2] = {0.f, 0.f};
+      const Q xx = Q::make(sx[0], sx[1]);
+      Q pxm = Q::make(1.f, 1.f), px = xx, dpxm = Q::make(0.f, 0.f), dpx = Q::make(1.f, 1.f);
+#pragma unroll
+      for (int i0 = 0; i0 < KXP; i0 += 8) {
+        float a0[8], b0[8], a1[8], b1[8];
+        tmem_ld8(tmem0 + (uint32_t)i0, a0);
+        tmem_ld8(tmem0 + (uint32_t)(KXP + i0), b0);
+        tmem_ld8(tmem1 + (uint32_t)i0, a1);
+        tmem_ld8(tmem1 + (uint32_t)(KXP + i0), b1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q;
+          Q P, D;
+          if (i == 0) {
+            P = pxm;
+            D = dpxm;
+          } else if (i == 1) {
+            P = px;
+            D = dpx;
+          } else {
+            const Q pn = Q::fma(Q::mul_bcast(xx, leg_a<float>(i - 1)), px, Q::mul_bcast(pxm, -leg_b<float>(i - 1)));
+            const Q dn = Q::fma_bcast(px, leg_c<float>(i - 1), dpxm);
+            pxm = px; px = pn; dpxm = dpx; dpx = dn;
+            P = pn;
+            D = dn;
+          }
+          Gx[0] = fmaf(D.lo(), a0[q], Gx[0]);
+          Gy[0] = fmaf(P.lo(), b0[q], Gy[0]);
+          Gx[1] = fmaf(D.hi(), a1[q], Gx[1]);
+          Gy[1] = fmaf(P.hi(), b1[q], Gy[1]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float fx = gx[k] + (inx[k] ? Gx[k] * inv_a * BP.ihx : 0.f);
+        const float fy = gy[k] + (iny[k] ? Gy[k] * inv_b * BP.ihy : 0.f);
+        vx[k] = fmaf(I.c_over_sqrtm, zx[k], fmaf(-I.b_over_m, fx, I.a * vx[k]));
+        vy[k] = fmaf(I.c_over_sqrtm, zy[k], fmaf(-I.b_over_m, fy, I.a * vy[k]));
+        x[k] = fmaf(I.dt, vx[k], x[k]);
+        y[k] = fmaf(I.dt, vy[k], y[k]);
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
       const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
@@ -354,6 +467,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
       vy[k] = fmaf(I.c_over_sqrtm, zy[k], fmaf(-I.b_over_m, fy, I.a * vy[k]));
       x[k] = fmaf(I.dt, vx[k], x[k]);
       y[k] = fmaf(I.dt, vy[k], y[k]);
+    }
     }
     parity ^= 1u;
   }
@@ -619,6 +733,8 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
         case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, st);
         case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, st);
         case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, st);
+        case 52: return launch_tc<16, 16, 5, 2>(A, I, PP, BP, K, st);
+        case 32: return launch_tc<16, 16, 3, 2>(A, I, PP, BP, K, st);
         default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, st);
       }
     }
