@@ -107,19 +107,28 @@ PV_DEV void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
 }
 
-// The four operand matrices of a group (P_hi, P_lo, P'_hi, P'_lo: [128 walkers] x [KYP functions] FP16 each) share 128-byte rows:
-// operand s starts at byte s * 2 KYP of the concatenated row, i.e. in tile (2 s KYP) / 128 at byte offset (2 s KYP) % 128 --
-// one 16 KB tile per group for KYP = 16, two for 32, four for 64.  A UMMA descriptor may start anywhere inside the swizzle row
-// (that is how the K slabs of one matrix are addressed as well).
+// Folded derivatives.  P'_n = sum over k = n-1, n-3, ... of (2k+1) P_k, so BOTH force components are contractions with the
+// Legendre VALUES only, against two matrices derived from the coefficients once per launch:
+//     dV/dsx = sum_k P_k(sx) A'_k,   A'_k = sum_j WA[k][j] P_j(sy),   WA[k][j] = (2k+1) sum_{i>k, i-k odd} w_ij
+//     dV/dsy = sum_i P_i(sx) B_i,    B_i  = sum_k WB[i][k] P_k(sy),   WB[i][k] = (2k+1) sum_{j>k, j-k odd} w_ij
+// A thread therefore writes ONE row per step (P_j(sy) as FP16 hi + lo; no derivative recursion, no second split), the
+// tensor core multiplies it with the stacked [2 KX x KY] matrix (WA over WB) in one N = 2 KX instruction per term, and the
+// x sweep needs P_i(sx) only.
+//
+// The two operand matrices of a group (P_hi, P_lo: [128 walkers] x [KYP functions] FP16 each) share 128-byte rows:
+// operand s starts at byte 2 s KYP of the concatenated row -- one 16 KB tile per group for KYP <= 32, two for 64.  A UMMA
+// descriptor may start anywhere inside the swizzle row (that is how the K slabs of one matrix are addressed as well).
 template <int KYP> struct TcLayout {
-  static constexpr int kTiles = 4 * KYP * 2 / 128;                                   // 16 KB tiles per group
+  static constexpr int kTiles = (2 * KYP * 2 + 127) / 128;                           // 16 KB tiles per group
   static __host__ __device__ constexpr int tile(int s) { return (s * KYP * 2) / 128; }
   static __host__ __device__ constexpr int chunk0(int s) { return ((s * KYP * 2) % 128) / 16; }   // first 16-byte chunk of operand s
 };
 
+constexpr int kW2Bytes = 128 * 128;         // [WA rows 0..KXP) | WB rows KXP..2 KXP)][64 j FP16], 128-byte rows: 16 KB
+
 template <int KYP, int G, int WPT> struct TcSmem {
-  alignas(1024) unsigned char a[G][WPT][TcLayout<KYP>::kTiles][kTileBytes];
-  alignas(1024) unsigned char w[2][kWBytes];         // W_hi, W_lo: [64 i][64 j] FP16, 128-byte rows
+  alignas(1024) unsigned char a[G][WPT][TcLayout<KYP>::kTiles][kTileBytes];   // at kernel start: scratch for WA, WB in FP32 (32 KB)
+  alignas(1024) unsigned char w[2][kW2Bytes];        // stacked weights, hi and lo parts
   alignas(8) uint64_t bar[G][WPT];                   // contraction done (tcgen05.commit)
   alignas(8) uint64_t ready[G][WPT];                 // all 128 rows of the set written and last step's TMEM reads done (128 arrivals)
   float red[32];
@@ -128,15 +137,16 @@ template <int KYP, int G, int WPT> struct TcSmem {
 
 __host__ __device__ constexpr uint32_t tmem_cols(int need) { return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u; }
 
-// KXP / KYP = number of x / y functions padded to 16, 32 or 64 (UMMA N / K extent; weights beyond kx, ky are zero).
-// WPT walker sets per group (thread = one walker of each set): while the contraction of set 0 is in flight the threads
-// generate the rows of set 1, and sweep set 0 while set 1's is in flight -- the MMA round trip (store -> proxy fence ->
-// barrier -> MMA -> commit -> TMEM load, ~1.3 us) is latency that only independent walkers can hide.
+// KXP / KYP = number of x / y functions padded to 16, 32 or 64 (UMMA N = 2 KXP, K extent KYP; weights beyond kx, ky are zero).
+// WPT walker sets per group (thread = one walker of each set; with WPT = 2 the two recursions of a thread run as one packed
+// FP32x2 chain).  The MMA round trip (store -> proxy fence -> barrier -> MMA -> commit -> TMEM load, ~1.3 us) is latency
+// that only independent groups can hide.
 template <int KXP, int KYP, int G, int WPT, bool INJECT>
 __global__ void __launch_bounds__(kGT* G, 1)
 langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
                      const Legendre2DSmemParams<float> BP, const RngKeys K) {
   using LY = TcLayout<KYP>;
+  static_assert(sizeof(TcSmem<KYP, G, WPT>::a) >= 2 * 64 * 64 * sizeof(float), "operand tiles double as the FP32 scratch of the weight transform");
   extern __shared__ unsigned char smem_raw[];
   TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -154,12 +164,33 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // scale of the weights: a power of two that brings max |w_ij| into [2^12, 2^13) (FP16 range), found by every block itself so
-  // that coefficients handed over on the device need no host copy
+  // ---- folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients), 64 x 64 FP32 each, in the tile area
+  float* const wa = reinterpret_cast<float*>(&sm.a[0][0][0][0]);
+  float* const wb = wa + 64 * 64;
+  float wmax = 0.f;
+  for (int item = tid; item < 2 * 64 * 64; item += blockDim.x) {
+    const int which = item >> 12, r = (item >> 6) & 63, c = item & 63;
+    double acc = 0.0;
+    if (which == 0) {
+      // WA[k = r][j = c]: sum over i = k + 1, k + 3, ... of w_ij
+      if (r < BP.kx && c < BP.ky)
+        for (int i = r + 1; i < BP.kx; i += 2) acc += (double)BP.w[i * BP.ky + c];
+      acc *= (double)(2 * r + 1);
+    } else {
+      // WB[i = r][k = c]: sum over j = k + 1, k + 3, ... of w_ij
+      if (r < BP.kx && c < BP.ky)
+        for (int j = c + 1; j < BP.ky; j += 2) acc += (double)BP.w[r * BP.ky + j];
+      acc *= (double)(2 * c + 1);
+    }
+    const float v = (float)acc;
+    wa[item] = v;
+    wmax = fmaxf(wmax, fabsf(v));
+  }
+  // scale: a power of two that brings max |W| into [2^12, 2^13) (FP16 range), found by every block itself so that
+  // coefficients handed over on the device need no host copy
   float wscale;
   {
-    float m = 0.f;
-    for (int q = tid; q < BP.kx * BP.ky; q += blockDim.x) m = fmaxf(m, fabsf(BP.w[q]));
+    float m = wmax;
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) sm.red[warp] = m;
     __syncthreads();
@@ -169,37 +200,35 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     if (m > 0.f && m < 3e38f) frexpf(m, &ex);
     wscale = ldexpf(1.f, 13 - ex);
   }
-  // weights -> W_hi, W_lo tiles: row i (N index), 64 j (K index), scaled by wscale (undone after the sweep)
-  for (int item = tid; item < 64 * 8; item += blockDim.x) {
-    const int i = item >> 3, c = item & 7;
+  // stacked B operand: row r < KXP = WA[r][.], row KXP + i = WB[i][.]; 64 j (K index) per 128-byte row, scaled by wscale
+  for (int item = tid; item < 2 * KXP * 8; item += blockDim.x) {
+    const int r = item >> 3, c = item & 7;
+    const float* src = (r < KXP ? wa + r * 64 : wb + (r - KXP) * 64) + 8 * c;
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = 8 * c + q;
-      v[q] = (i < BP.kx && j < BP.ky) ? BP.w[i * BP.ky + j] * wscale : 0.f;
-    }
+    for (int q = 0; q < 8; ++q) v[q] = src[q] * wscale;
     uint4 hi, lo;
     split8(v, hi, lo);
-    const uint32_t off = (uint32_t)(i >> 3) * 1024u + (uint32_t)(i & 7) * 128u + (uint32_t)((c ^ (i & 7)) << 4);
+    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
     sts128(smem_u32(sm.w[0]) + off, hi);
     sts128(smem_u32(sm.w[1]) + off, lo);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncthreads();                                                       // also: the scratch is free to become operand tiles
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;           // this warp's TMEM lanes
   const uint32_t row_off = (uint32_t)(tl >> 3) * 1024u + (uint32_t)(tl & 7) * 128u;
   const uint64_t dWhi = umma_desc_k_sw128(smem_u32(sm.w[0])), dWlo = umma_desc_k_sw128(smem_u32(sm.w[1]));
-  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(KXP >> 3) << 17) | ((128u >> 4) << 24);
-  const float inv_a = 1.f / (kScaleP * wscale), inv_b = 1.f / (kScaleD * wscale);   // powers of two: exact
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)((2 * KXP) >> 3) << 17) | ((128u >> 4) << 24);
+  const float inv_w = 1.f / (kScaleP * wscale);                       // a power of two: exact
 
   // operand s of set k: tile LY::tile(s), starting LY::chunk0(s) 16-byte chunks into the 128-byte row
-  uint64_t dsc[WPT][4];
+  uint64_t dsc[WPT][2];
 #pragma unroll
   for (int k = 0; k < WPT; ++k)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dsc[k][q] = umma_desc_k_sw128(smem_u32(sm.a[g][k][0]) + LY::tile(q) * kTileBytes) + (uint64_t)LY::chunk0(q);
+    for (int q = 0; q < 2; ++q) dsc[k][q] = umma_desc_k_sw128(smem_u32(sm.a[g][k][0]) + LY::tile(q) * kTileBytes) + (uint64_t)LY::chunk0(q);
 
   int64_t wk[WPT];
   bool live[WPT];
@@ -215,130 +244,101 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     vy[k] = A.vel[A.n + wk[k]];
     zodd_x[k] = zodd_y[k] = 0.f;
   }
+  auto row_addr = [&](uint32_t tiles, int sidx, int c) {   // 16-byte chunk c of operand sidx in this walker's row (Swizzle<3,4,3>: chunk ^ row % 8)
+    return tiles + (uint32_t)(LY::tile(sidx) * kTileBytes) + row_off + (uint32_t)(((LY::chunk0(sidx) + c) ^ (tl & 7)) << 4);
+  };
 
   uint32_t parity = 0;
   for (int64_t ts = 0; ts < A.nsteps; ++ts) {
     const int64_t t = A.step0 + ts;
     float sx[WPT], gx[WPT], gy[WPT], zx[WPT], zy[WPT];
     bool inx[WPT], iny[WPT];
+    // ---- rows 1024 P_j(sy), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
     if constexpr (WPT == 2) {
-      // two walkers per thread: both y recursions run as ONE packed FP32x2 chain (FMUL2 / FFMA2 with the recursion
-      // coefficients as broadcast immediates), the halves go to the rows of set 0 and set 1
       using Q = Pair<float>;
       sx[0] = scale_clamp(x[0], BP.cx, BP.ihx, inx[0]);
       sx[1] = scale_clamp(x[1], BP.cx, BP.ihx, inx[1]);
       const float sy0 = scale_clamp(y[0], BP.cy, BP.ihy, iny[0]), sy1 = scale_clamp(y[1], BP.cy, BP.ihy, iny[1]);
       const Q yy = Q::make(sy0, sy1);
       Q pm = Q::make(kScaleP, kScaleP), p = Q::mul_bcast(yy, kScaleP);
-      Q dpm = Q::make(0.f, 0.f), dp = Q::make(kScaleD, kScaleD);
       const uint32_t tiles0 = smem_u32(sm.a[g][0][0]), tiles1 = smem_u32(sm.a[g][1][0]);
 #pragma unroll
       for (int c = 0; c < KYP / 8; ++c) {
-        float pv0[8], dv0[8], pv1[8], dv1[8];
+        float pv0[8], pv1[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = 8 * c + q;
-          Q P, D;
+          Q P;
           if (j == 0) {
             P = pm;
-            D = dpm;
           } else if (j == 1) {
             P = p;
-            D = dp;
           } else {
             const Q pn = Q::fma(Q::mul_bcast(yy, leg_a<float>(j - 1)), p, Q::mul_bcast(pm, -leg_b<float>(j - 1)));
-            const Q dn = Q::fma_bcast(p, leg_c<float>(j - 1) * (kScaleD / kScaleP), dpm);
-            pm = p; p = pn; dpm = dp; dp = dn;
+            pm = p; p = pn;
             P = pn;
-            D = dn;
           }
-          pv0[q] = P.lo(); pv1[q] = P.hi();
-          dv0[q] = D.lo(); dv1[q] = D.hi();
+          pv0[q] = P.lo();
+          pv1[q] = P.hi();
         }
         uint4 hi, lo;
-        auto off = [&](int sidx) {
-          return (uint32_t)(LY::tile(sidx) * kTileBytes) + row_off + (uint32_t)(((LY::chunk0(sidx) + c) ^ (tl & 7)) << 4);
-        };
         split8(pv0, hi, lo);
-        sts128(tiles0 + off(0), hi);
-        sts128(tiles0 + off(1), lo);
-        split8(dv0, hi, lo);
-        sts128(tiles0 + off(2), hi);
-        sts128(tiles0 + off(3), lo);
+        sts128(row_addr(tiles0, 0, c), hi);
+        sts128(row_addr(tiles0, 1, c), lo);
         split8(pv1, hi, lo);
-        sts128(tiles1 + off(0), hi);
-        sts128(tiles1 + off(1), lo);
-        split8(dv1, hi, lo);
-        sts128(tiles1 + off(2), hi);
-        sts128(tiles1 + off(3), lo);
+        sts128(row_addr(tiles1, 0, c), hi);
+        sts128(row_addr(tiles1, 1, c), lo);
       }
     } else {
 #pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-      const uint32_t tiles = smem_u32(sm.a[g][k][0]);
-      sx[k] = scale_clamp(x[k], BP.cx, BP.ihx, inx[k]);
-      const float sy = scale_clamp(y[k], BP.cy, BP.ihy, iny[k]);
-      // ---- rows (1024 P_j(sy), 16 P'_j(sy)), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
-      {
+      for (int k = 0; k < WPT; ++k) {
+        const uint32_t tiles = smem_u32(sm.a[g][k][0]);
+        sx[k] = scale_clamp(x[k], BP.cx, BP.ihx, inx[k]);
+        const float sy = scale_clamp(y[k], BP.cy, BP.ihy, iny[k]);
         float pm = kScaleP, p = kScaleP * sy;              // 1024 P_0, 1024 P_1
-        float dpm = 0.f, dp = kScaleD;                     // 16 P'_0, 16 P'_1
 #pragma unroll
         for (int c = 0; c < KYP / 8; ++c) {
-          float pv[8], dv[8];
+          float pv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int j = 8 * c + q;
             if (j == 0) {
               pv[q] = pm;
-              dv[q] = dpm;
             } else if (j == 1) {
               pv[q] = p;
-              dv[q] = dp;
             } else {
               const float pn = leg_a<float>(j - 1) * sy * p - leg_b<float>(j - 1) * pm;
-              const float dn = fmaf(leg_c<float>(j - 1) * (kScaleD / kScaleP), p, dpm);
-              pm = p; p = pn; dpm = dp; dp = dn;
+              pm = p; p = pn;
               pv[q] = pn;
-              dv[q] = dn;
             }
           }
           uint4 hi, lo;
-          auto addr = [&](int sidx) {     // 16-byte chunk c of operand sidx in this walker's row (Swizzle<3,4,3>: chunk ^ row % 8)
-            return tiles + (uint32_t)(LY::tile(sidx) * kTileBytes) + row_off + (uint32_t)(((LY::chunk0(sidx) + c) ^ (tl & 7)) << 4);
-          };
           split8(pv, hi, lo);
-          sts128(addr(0), hi);
-          sts128(addr(1), lo);
-          split8(dv, hi, lo);
-          sts128(addr(2), hi);
-          sts128(addr(3), lo);
+          sts128(row_addr(tiles, 0, c), hi);
+          sts128(row_addr(tiles, 1, c), lo);
         }
       }
     }
-    }
-    // rows of every walker set are written back to back (independent recursions interleave in the instruction stream), then
-    // ONE proxy fence; no block-wide barrier: every thread ARRIVES (its rows are written, its TMEM reads of the last step are
-    // done) and goes on with the work that does not need the contraction; only the issuing thread waits for the 128 arrivals
+    // rows of every walker set are written back to back, then ONE proxy fence; no block-wide barrier: every thread ARRIVES
+    // (its rows are written, its TMEM reads of the last step are done) and goes on with the work that does not need the
+    // contraction; only the issuing thread waits for the 128 arrivals
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < WPT; ++k) mbar_arrive(&sm.ready[g][k]);
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
-      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // D_A [0, KXP), D_B [KXP, 2 KXP)
+      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // A'_k in [0, KXP), B_i in [KXP, 2 KXP)
       if (tl == 0) {
         mbar_wait(&sm.ready[g][k], parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dPhi = dsc[k][0], dPlo = dsc[k][1], dDhi = dsc[k][2], dDlo = dsc[k][3];
+        const uint64_t dPhi = dsc[k][0], dPlo = dsc[k][1];
 #pragma unroll
         for (int kk = 0; kk < KYP / 16; ++kk) {                      // K = 16 per instruction: 32 bytes = +2 in 16-byte units
           const uint64_t o = (uint64_t)(kk * 2);
           umma_f16(tmem, dPhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
           umma_f16(tmem, dPhi + o, dWlo + o, kIdesc, 1u);
           umma_f16(tmem, dPlo + o, dWhi + o, kIdesc, 1u);
-          umma_f16(tmem + (uint32_t)KXP, dDhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
-          umma_f16(tmem + (uint32_t)KXP, dDhi + o, dWlo + o, kIdesc, 1u);
-          umma_f16(tmem + (uint32_t)KXP, dDlo + o, dWhi + o, kIdesc, 1u);
         }
         umma_commit(&sm.bar[g][k]);
       }
@@ -368,16 +368,17 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
         zy[k] = zodd_y[k];
       }
     }
+    // ---- this walker's (A'_i, B_i) from TMEM, x recursion and the two row sums
+    float Gx[WPT], Gy[WPT];
     if constexpr (WPT == 2) {
-      // packed x recursion for the two walkers; the row sums stay scalar (the two walkers' rows come from different TMEM columns)
       using Q = Pair<float>;
       const uint32_t tmem0 = sm.tmem_base + (uint32_t)((g * 2) * 2 * KXP) + tlane, tmem1 = tmem0 + (uint32_t)(2 * KXP);
       mbar_wait(&sm.bar[g][0], parity);
       mbar_wait(&sm.bar[g][1], parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float Gx[2] = {0.f, 0.f}, Gy[2] = {0.f, 0.f};
+      float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
       const Q xx = Q::make(sx[0], sx[1]);
-      Q pxm = Q::make(1.f, 1.f), px = xx, dpxm = Q::make(0.f, 0.f), dpx = Q::make(1.f, 1.f);
+      Q pxm = Q::make(1.f, 1.f), px = xx;
 #pragma unroll
       for (int i0 = 0; i0 < KXP; i0 += 8) {
         float a0[8], b0[8], a1[8], b1[8];
@@ -389,45 +390,31 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = i0 + q;
-          Q P, D;
+          Q P;
           if (i == 0) {
             P = pxm;
-            D = dpxm;
           } else if (i == 1) {
             P = px;
-            D = dpx;
           } else {
             const Q pn = Q::fma(Q::mul_bcast(xx, leg_a<float>(i - 1)), px, Q::mul_bcast(pxm, -leg_b<float>(i - 1)));
-            const Q dn = Q::fma_bcast(px, leg_c<float>(i - 1), dpxm);
-            pxm = px; px = pn; dpxm = dpx; dpx = dn;
+            pxm = px; px = pn;
             P = pn;
-            D = dn;
           }
-          Gx[0] = fmaf(D.lo(), a0[q], Gx[0]);
-          Gy[0] = fmaf(P.lo(), b0[q], Gy[0]);
-          Gx[1] = fmaf(D.hi(), a1[q], Gx[1]);
-          Gy[1] = fmaf(P.hi(), b1[q], Gy[1]);
+          s0a = fmaf(P.lo(), a0[q], s0a);
+          s0b = fmaf(P.lo(), b0[q], s0b);
+          s1a = fmaf(P.hi(), a1[q], s1a);
+          s1b = fmaf(P.hi(), b1[q], s1b);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float fx = gx[k] + (inx[k] ? Gx[k] * inv_a * BP.ihx : 0.f);
-        const float fy = gy[k] + (iny[k] ? Gy[k] * inv_b * BP.ihy : 0.f);
-        vx[k] = fmaf(I.c_over_sqrtm, zx[k], fmaf(-I.b_over_m, fx, I.a * vx[k]));
-        vy[k] = fmaf(I.c_over_sqrtm, zy[k], fmaf(-I.b_over_m, fy, I.a * vy[k]));
-        x[k] = fmaf(I.dt, vx[k], x[k]);
-        y[k] = fmaf(I.dt, vy[k], y[k]);
-      }
+      Gx[0] = s0a; Gy[0] = s0b; Gx[1] = s1a; Gy[1] = s1b;
     } else {
 #pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
-      // ---- this walker's (A_i, B_i) from TMEM, x recursion and row sweep, 16 functions at a time
-      mbar_wait(&sm.bar[g][k], parity);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
-      {
-        float pxm = 1.f, px = sx[k], dpxm = 0.f, dpx = 1.f;
+      for (int k = 0; k < WPT; ++k) {
+        const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
+        mbar_wait(&sm.bar[g][k], parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
+        float pxm = 1.f, px = sx[k];
 #pragma unroll
         for (int i0 = 0; i0 < KXP; i0 += 16) {
           float av[16], bv[16];
@@ -437,37 +424,37 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const int i = i0 + q;
-            float pi, di;
+            float pi;
             if (i == 0) {
               pi = 1.f;
-              di = 0.f;
             } else if (i == 1) {
               pi = px;
-              di = dpx;
             } else {
               const float pn = leg_a<float>(i - 1) * sx[k] * px - leg_b<float>(i - 1) * pxm;
-              const float dn = fmaf(leg_c<float>(i - 1), px, dpxm);
-              pxm = px; px = pn; dpxm = dpx; dpx = dn;
+              pxm = px; px = pn;
               pi = pn;
-              di = dn;
             }
             if (q & 1) {
-              Gx1 = fmaf(di, av[q], Gx1);
+              Gx1 = fmaf(pi, av[q], Gx1);
               Gy1 = fmaf(pi, bv[q], Gy1);
             } else {
-              Gx0 = fmaf(di, av[q], Gx0);
+              Gx0 = fmaf(pi, av[q], Gx0);
               Gy0 = fmaf(pi, bv[q], Gy0);
             }
           }
         }
+        Gx[k] = Gx0 + Gx1;
+        Gy[k] = Gy0 + Gy1;
       }
-      const float fx = gx[k] + (inx[k] ? (Gx0 + Gx1) * inv_a * BP.ihx : 0.f);
-      const float fy = gy[k] + (iny[k] ? (Gy0 + Gy1) * inv_b * BP.ihy : 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const float fx = gx[k] + (inx[k] ? Gx[k] * inv_w * BP.ihx : 0.f);
+      const float fy = gy[k] + (iny[k] ? Gy[k] * inv_w * BP.ihy : 0.f);
       vx[k] = fmaf(I.c_over_sqrtm, zx[k], fmaf(-I.b_over_m, fx, I.a * vx[k]));
       vy[k] = fmaf(I.c_over_sqrtm, zy[k], fmaf(-I.b_over_m, fy, I.a * vy[k]));
       x[k] = fmaf(I.dt, vx[k], x[k]);
       y[k] = fmaf(I.dt, vy[k], y[k]);
-    }
     }
     parity ^= 1u;
   }
@@ -731,10 +718,9 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
         case 41: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, st);
         case 42: return launch_tc<16, 16, 4, 2>(A, I, PP, BP, K, st);
         case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, st);
+        case 71: return launch_tc<16, 16, 7, 1>(A, I, PP, BP, K, st);
         case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, st);
         case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, st);
-        case 52: return launch_tc<16, 16, 5, 2>(A, I, PP, BP, K, st);
-        case 32: return launch_tc<16, 16, 3, 2>(A, I, PP, BP, K, st);
         default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, st);
       }
     }
@@ -745,13 +731,16 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
       switch (shape) {
         case 41: return launch_tc<32, 32, 4, 1>(A, I, PP, BP, K, st);
         case 51: return launch_tc<32, 32, 5, 1>(A, I, PP, BP, K, st);
-        case 32: return launch_tc<32, 32, 3, 2>(A, I, PP, BP, K, st);
+        case 71: return launch_tc<32, 32, 7, 1>(A, I, PP, BP, K, st);
+        case 81: return launch_tc<32, 32, 8, 1>(A, I, PP, BP, K, st);
+        case 42: return launch_tc<32, 32, 4, 2>(A, I, PP, BP, K, st);
         default: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, st);
       }
     }
-    return launch_tc<KXP, 32, 3, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+    return launch_tc<KXP, 32, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
   }
-  return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, st);
+  if (KXP == 64 && shape == 31) return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, st);
+  return launch_tc<KXP, 64, 4, 1>(A, I, PP, BP, K, st);
 }
 
 }  // namespace
