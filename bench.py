@@ -68,8 +68,8 @@ def parse_args():
                     help="the all-reduce of the moments: 'native' = pyves_allreduce_moments (NCCL bound by the C-ABI library itself, "
                          "communicator bootstrapped through the torch process group), 'torch' = torch.distributed.all_reduce")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "cuda", "tensor"],
-                    help="2D Legendre step kernel of the headline: 'auto' = the library's table (tensor-core contraction from ~14 x 14 "
-                         "functions on), 'cuda' = CUDA-core column sweep (pyves_set_tuning 6), 'tensor' = tensor cores forced (7)")
+                    help="2D Legendre step kernel of the headline: 'auto' = the library's table (tensor-core contraction for FP32 bases other than the static 8 x 8 "
+                         "double-well kernel), 'cuda' = CUDA-core column sweep (pyves_set_tuning 6), 'tensor' = tensor cores forced (7)")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configurations")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default); strong: --walkers-total sharded over the ranks")
@@ -543,8 +543,8 @@ def config_legs(args, rank, world, local, dev, peak):
     def leg2d(K):
         return lambda: bias.VESBias_Ensemble(basis.LegendreBasis2D(K - 1, K - 1, *MINMAX), target.Target_Uniform_2D(100, 100), beta, "averaged_sgd",
                                              {"mu": 0.5, "averaging": "ewma", "decay": 0.8, "precondition": 1.0}, target_update_every=0)
-    kern = {8: "langevin2d_kernel<DoubleWell, Legendre2DStaticT<8,8>>", 32: "langevin2d_tc_kernel<32,32,3,2> (tensor-core contraction)",
-            64: "langevin2d_tc_kernel<64,64,3,1> (tensor-core contraction)"}
+    kern = {8: "langevin2d_kernel<DoubleWell, Legendre2DStaticT<8,8>>", 32: "langevin2d_tc_kernel<32,32,6,1> (tensor-core contraction, folded derivative matrices)",
+            64: "langevin2d_tc_kernel<64,64,4,1> (tensor-core contraction, folded derivative matrices)"}
     # the headline workload on the CUDA-core column sweep (the FP32-roofline kernel of round 1) and the 32 x 32 / 64 x 64 sweeps,
     # for the comparison with the tensor-core contraction that is the default now
     def headline_bias():
@@ -594,7 +594,7 @@ def tensor_roofline(basis, walker_steps_per_s):
     what bounds it instead is instruction issue (generation of the operand rows, x sweep, noise: profiles/r02_ncu_tc_step.md)
     and, for 64 x 64, shared-memory bandwidth.  `tensor` gives the executed tensor work against the FP16 dense peak."""
     kp = 16 if basis <= 16 else (32 if basis <= 32 else 64)
-    executed = 12.0 * kp * kp                      # 2 matrices (P, P') x 3 MMAs (hi hi, hi lo, lo hi) x 2 N K flops per walker-step
+    executed = 12.0 * kp * kp                      # 3 MMAs (hi hi, hi lo, lo hi) x 2 N K flops per walker-step, N = 2 Kx (WA over WB), K = Ky
     peak16 = 1643.1
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:

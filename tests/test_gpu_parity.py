@@ -202,7 +202,7 @@ TRAJ_CASES = [
     # (tag, potential, params, bias builder, start box, variants)
     ("dw_none", potentials.DOUBLE_WELL_2D, None, lambda r: dict(kind="none"), (-1.6, -1.2, -0.3, 0.3), [-1]),
     ("dw_leg1d5", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg1d", r, degree=5), (-1.6, -1.2, -0.3, 0.3), [-1]),
-    # variants: -1 default table (FP32: tensor-core contraction from ~14 x 14 functions on), 7 tensor cores forced, 6 CUDA cores forced
+    # variants: -1 default table (FP32: tensor-core contraction except the static 8 x 8 double-well kernel), 7 tensor cores forced, 6 CUDA cores forced
     ("dw_leg2d8", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=7, deg_y=7), (-1.6, -1.2, -0.3, 0.3), [-1, 7]),
     ("dw_leg2d16", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), (-1.6, -1.2, -0.3, 0.3), [-1, 1, 99, 6]),
     ("dw_leg2d32", potentials.DOUBLE_WELL_2D, None, lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31, scale=1.0), (-1.6, -1.2, -0.3, 0.3), [-1, 6]),
