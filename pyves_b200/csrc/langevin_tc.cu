@@ -107,6 +107,48 @@ PV_DEV void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
 }
 
+// Scaled monic recursion.  With k_j the leading coefficient of P_j and e_j = round(log2 k_j), q_j = P_j 2^e_j / k_j obeys
+//     q_{j+1} = 2^d_j s q_j - cc_j q_{j-1},   d_j = e_{j+1} - e_j in {0, 1},   cc_j = j^2 / (4 j^2 - 1) * 2^(e_{j+1} - e_{j-1})
+// -- one FMUL and one FFMA per function (the textbook form needs a second FMUL for A_j s) with |q_j| <= 1.41, and
+// P_j = kappa_j q_j, kappa_j = k_j / 2^e_j in [0.71, 1.41], is folded into the coefficient matrices.
+struct MonicTab {
+  float cc[64];
+  int d[64];
+  double kappa[64];
+};
+__host__ __device__ constexpr MonicTab make_monic_tab() {
+  MonicTab t{};
+  double kap = 1.0;
+  int e_prev = 0, e_cur = 0;                          // e_{j-1}, e_j
+  t.kappa[0] = 1.0;
+  for (int j = 0; j < 63; ++j) {                      // step j -> j + 1
+    double kn = kap * (double)(2 * j + 1) / (double)(j + 1);
+    int dn = 0;
+    if (kn >= 1.4142135623730951) {
+      kn *= 0.5;
+      dn = 1;
+    }
+    const int e_next = e_cur + dn;
+    double c = j == 0 ? 0.0 : (double)j * j / (4.0 * j * j - 1.0);
+    for (int q = 0; q < e_next - e_prev; ++q) c *= 2.0;
+    t.d[j] = dn;
+    t.cc[j] = (float)c;
+    t.kappa[j + 1] = kn;
+    kap = kn;
+    e_prev = e_cur;
+    e_cur = e_next;
+  }
+  return t;
+}
+PV_DEV double monic_kappa(int n) {                    // the same recurrence at run time (prologue only)
+  double kap = 1.0;
+  for (int j = 0; j < n; ++j) {
+    kap = kap * (double)(2 * j + 1) / (double)(j + 1);
+    if (kap >= 1.4142135623730951) kap *= 0.5;
+  }
+  return kap;
+}
+
 // Folded derivatives.  P'_n = sum over k = n-1, n-3, ... of (2k+1) P_k, so BOTH force components are contractions with the
 // Legendre VALUES only, against two matrices derived from the coefficients once per launch:
 //     dV/dsx = sum_k P_k(sx) A'_k,   A'_k = sum_j WA[k][j] P_j(sy),   WA[k][j] = (2k+1) sum_{i>k, i-k odd} w_ij
@@ -131,6 +173,7 @@ template <int KYP, int G, int WPT> struct TcSmem {
   alignas(1024) unsigned char w[2][kW2Bytes];        // stacked weights, hi and lo parts
   alignas(8) uint64_t bar[G][WPT];                   // contraction done (tcgen05.commit)
   alignas(8) uint64_t ready[G][WPT];                 // all 128 rows of the set written and last step's TMEM reads done (128 arrivals)
+  double kappa[64];
   float red[32];
   uint32_t tmem_base;
 };
@@ -164,7 +207,11 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients), 64 x 64 FP32 each, in the tile area
+  constexpr MonicTab tab = make_monic_tab();
+  if (tid < 64) sm.kappa[tid] = monic_kappa(tid);
+  __syncthreads();
+  // ---- folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients, times kappa_row kappa_column), 64 x 64 FP32
+  //      each, in the tile area
   float* const wa = reinterpret_cast<float*>(&sm.a[0][0][0][0]);
   float* const wb = wa + 64 * 64;
   float wmax = 0.f;
@@ -182,7 +229,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
         for (int j = c + 1; j < BP.ky; j += 2) acc += (double)BP.w[r * BP.ky + j];
       acc *= (double)(2 * c + 1);
     }
-    const float v = (float)acc;
+    const float v = (float)(acc * sm.kappa[r] * sm.kappa[c]);
     wa[item] = v;
     wmax = fmaxf(wmax, fabsf(v));
   }
@@ -253,13 +300,13 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     const int64_t t = A.step0 + ts;
     float sx[WPT], gx[WPT], gy[WPT], zx[WPT], zy[WPT];
     bool inx[WPT], iny[WPT];
-    // ---- rows 1024 P_j(sy), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
+    // ---- rows 1024 q_j(sy), j < KYP, as FP16 hi / lo, 8 functions per 128-bit store
     if constexpr (WPT == 2) {
       using Q = Pair<float>;
       sx[0] = scale_clamp(x[0], BP.cx, BP.ihx, inx[0]);
       sx[1] = scale_clamp(x[1], BP.cx, BP.ihx, inx[1]);
       const float sy0 = scale_clamp(y[0], BP.cy, BP.ihy, iny[0]), sy1 = scale_clamp(y[1], BP.cy, BP.ihy, iny[1]);
-      const Q yy = Q::make(sy0, sy1);
+      const Q yy = Q::make(sy0, sy1), yy2 = Q::add(yy, yy);
       Q pm = Q::make(kScaleP, kScaleP), p = Q::mul_bcast(yy, kScaleP);
       const uint32_t tiles0 = smem_u32(sm.a[g][0][0]), tiles1 = smem_u32(sm.a[g][1][0]);
 #pragma unroll
@@ -274,7 +321,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
           } else if (j == 1) {
             P = p;
           } else {
-            const Q pn = Q::fma(Q::mul_bcast(yy, leg_a<float>(j - 1)), p, Q::mul_bcast(pm, -leg_b<float>(j - 1)));
+            const Q pn = Q::fma(tab.d[j - 1] ? yy2 : yy, p, Q::mul_bcast(pm, -tab.cc[j - 1]));
             pm = p; p = pn;
             P = pn;
           }
@@ -295,7 +342,8 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
         const uint32_t tiles = smem_u32(sm.a[g][k][0]);
         sx[k] = scale_clamp(x[k], BP.cx, BP.ihx, inx[k]);
         const float sy = scale_clamp(y[k], BP.cy, BP.ihy, iny[k]);
-        float pm = kScaleP, p = kScaleP * sy;              // 1024 P_0, 1024 P_1
+        const float sy2 = sy + sy;
+        float pm = kScaleP, p = kScaleP * sy;              // 1024 q_0, 1024 q_1
 #pragma unroll
         for (int c = 0; c < KYP / 8; ++c) {
           float pv[8];
@@ -307,7 +355,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
             } else if (j == 1) {
               pv[q] = p;
             } else {
-              const float pn = leg_a<float>(j - 1) * sy * p - leg_b<float>(j - 1) * pm;
+              const float pn = fmaf(tab.d[j - 1] ? sy2 : sy, p, -(tab.cc[j - 1] * pm));
               pm = p; p = pn;
               pv[q] = pn;
             }
@@ -377,7 +425,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
       mbar_wait(&sm.bar[g][1], parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
-      const Q xx = Q::make(sx[0], sx[1]);
+      const Q xx = Q::make(sx[0], sx[1]), xx2 = Q::add(xx, xx);
       Q pxm = Q::make(1.f, 1.f), px = xx;
 #pragma unroll
       for (int i0 = 0; i0 < KXP; i0 += 8) {
@@ -396,7 +444,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
           } else if (i == 1) {
             P = px;
           } else {
-            const Q pn = Q::fma(Q::mul_bcast(xx, leg_a<float>(i - 1)), px, Q::mul_bcast(pxm, -leg_b<float>(i - 1)));
+            const Q pn = Q::fma(tab.d[i - 1] ? xx2 : xx, px, Q::mul_bcast(pxm, -tab.cc[i - 1]));
             pxm = px; px = pn;
             P = pn;
           }
@@ -414,6 +462,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
         mbar_wait(&sm.bar[g][k], parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
+        const float sx2 = sx[k] + sx[k];
         float pxm = 1.f, px = sx[k];
 #pragma unroll
         for (int i0 = 0; i0 < KXP; i0 += 16) {
@@ -430,7 +479,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
             } else if (i == 1) {
               pi = px;
             } else {
-              const float pn = leg_a<float>(i - 1) * sx[k] * px - leg_b<float>(i - 1) * pxm;
+              const float pn = fmaf(tab.d[i - 1] ? sx2 : sx[k], px, -(tab.cc[i - 1] * pxm));
               pxm = px; px = pn;
               pi = pn;
             }
