@@ -502,6 +502,9 @@ def config_legs(args, rank, world, local, dev, peak):
         if "tc_kernel" in kernel:
             K = int(name.split("_")[1].split("x")[0]) if name.startswith("cfg5_") else args.basis
             extra["tensor"] = tensor_roofline(K, n_rank * stride / (kms * 1e-3))["tensor"]
+        elif "tc_relu_kernel" in kernel:
+            ex = 2.0 * 2.0 * 96 * 48                  # 2 MMAs (mask x hi, mask x lo) x 2 N K flops per walker-step, N = 2 H, K = H
+            extra["tensor"] = {"executed_flops_per_walker_step": ex, "achieved": ex * n_rank * stride / (kms * 1e-3) * 1e-12, "unit": "TFLOP/s"}
         elif "tc_mlp_kernel" in kernel:
             ex = 12.0 * 48 * 48
             extra["tensor"] = {"executed_flops_per_walker_step": ex, "achieved": ex * n_rank * stride / (kms * 1e-3) * 1e-12, "unit": "TFLOP/s"}
@@ -534,7 +537,7 @@ def config_legs(args, rank, world, local, dev, peak):
                                      beta, "Adam", {"lr": 1e-3}, target_update_every=0, gradient_average='running')
     updater_leg("cfg4", "configs[3]: Szabo-Berezhkovskii + NNBasis1D [48,48,48] (ReLU), Adam 1e-3, running-average gradients, uniform target, "
                 "10^6 walkers per GPU", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII, (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000,
-                1000000 * world, args.stride, 2, "langevin2d_tc_mlp_kernel<48, ReLU, 3> (48 x 48 layer on the tensor cores)", LEG_FLOPS["cfg4"], "weak")
+                1000000 * world, args.stride, 2, "langevin2d_tc_relu_kernel<48, 5> (48 x 48 layer on the tensor cores, 0/1 mask operand against W2 diag(u) over W2 diag(c))", LEG_FLOPS["cfg4"], "weak")
     updater_leg("cfg4_cuda_cores", "configs[3] with the step kernel forced onto the CUDA cores (pyves_set_tuning 6)", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII,
                 (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000, 1000000 * world, args.stride, 2,
                 "langevin2d_kernel<SzaboBerezhkovskii, Mlp<48>> (CUDA cores, FFMA2 input sweep)", LEG_FLOPS["cfg4"], "weak", variant=6)

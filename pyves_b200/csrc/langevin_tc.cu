@@ -740,6 +740,213 @@ langevin2d_tc_mlp_kernel(const StepArgs<float> A, const IntegratorParams<float> 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
 }
 
+// ReLU specialisation.  With m_i = [z1_i > 0] (z1_i = u_i s + c_i) the hidden layer is h_i = m_i z1_i, dh_i/ds = m_i u_i, so
+//     dz2_j/ds = sum_i (W2[j][i] u_i) m_i,     z2_j = b2_j + s dz2_j/ds + sum_i (W2[j][i] c_i) m_i :
+// ONE operand row per walker, the 0 / 1 mask -- exact in FP16, no lo part, no split --, against the stacked matrices
+// WU = W2 diag(u) over WC = W2 diag(c) (N = 2 H, hi + lo): two MMAs per K slab instead of six, a 16 KB tile per group
+// instead of four (five groups per SM; the 512 TMEM columns are the limit), 2.5 instructions per hidden unit instead of ~9.
+template <int H, int G> struct TcReluSmem {
+  alignas(1024) unsigned char a[G][kTileBytes];      // per group: mask rows [128 walkers][H] FP16
+  alignas(1024) unsigned char w[2][kW2Bytes];        // (WU over WC) hi, lo: [2 H rows][H i] FP16, 128-byte rows
+  alignas(16) float vec[4 * H + 4];                  // u, c, wout, b2, bout
+  alignas(8) uint64_t bar[G];
+  alignas(8) uint64_t ready[G];
+  float red[32];
+  uint32_t tmem_base;
+};
+
+template <int H, int G, bool INJECT>
+__global__ void __launch_bounds__(kGT* G, 1)
+langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
+                          const MlpParams<float> BP, const RngKeys K) {
+  extern __shared__ unsigned char smem_raw[];
+  TcReluSmem<H, G>& sm = *reinterpret_cast<TcReluSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = tid / kGT, tl = tid % kGT;
+  constexpr uint32_t kCols = tmem_cols(G * 2 * H);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int q = 0; q < G; ++q) {
+      mbar_init(&sm.bar[q], 1);
+      mbar_init(&sm.ready[q], kGT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const float* W2T = BP.packed + 4 * H;              // W2T[i][j] = W2[j][i]
+  for (int q = tid; q < 4 * H + 4; q += blockDim.x) sm.vec[q] = q < 4 * H ? BP.packed[q] : BP.packed[4 * H + H * H + (q - 4 * H)];
+  float wscale;
+  {
+    float m = 0.f;
+    for (int q = tid; q < H * H; q += blockDim.x) {
+      const int i = q / H;
+      const float w2 = W2T[q];
+      m = fmaxf(m, fmaxf(fabsf(w2 * BP.packed[i]), fabsf(w2 * BP.packed[H + i])));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm.red[warp] = m;
+    __syncthreads();                                 // also: sm.vec is complete
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm.red[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3e38f) frexpf(m, &ex);
+    wscale = ldexpf(1.f, 13 - ex);
+  }
+  for (int item = tid; item < 2 * H * (H / 8); item += blockDim.x) {   // row r (N index), chunk c of 8 inputs i (K index)
+    const int r = item / (H / 8), c = item % (H / 8);
+    const int j = r < H ? r : r - H;
+    const float* fac = sm.vec + (r < H ? 0 : H);     // u for the WU rows, c for the WC rows
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = (float)((double)W2T[(8 * c + q) * H + j] * (double)fac[8 * c + q]) * wscale;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    sts128(smem_u32(sm.w[0]) + off, hi);
+    sts128(smem_u32(sm.w[1]) + off, lo);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t row_off = (uint32_t)(tl >> 3) * 1024u + (uint32_t)(tl & 7) * 128u;
+  const uint64_t dWhi = umma_desc_k_sw128(smem_u32(sm.w[0])), dWlo = umma_desc_k_sw128(smem_u32(sm.w[1]));
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)((2 * H) >> 3) << 17) | ((128u >> 4) << 24);
+  const float inv_w = 1.f / wscale;
+  const uint32_t tile = smem_u32(sm.a[g]);
+  const uint64_t dM = umma_desc_k_sw128(tile);
+  const uint32_t tmem = sm.tmem_base + (uint32_t)(g * 2 * H);       // wscale dz2_j/ds in [0, H), wscale sum_i WC m_i in [H, 2 H)
+  const float* uvec = sm.vec;
+  const float* cvec = sm.vec + H;
+  const float* wout = sm.vec + 2 * H;
+  const float* b2 = sm.vec + 3 * H;
+
+  const int64_t idx = ((int64_t)blockIdx.x * G + g) * kGT + tl;
+  const bool live = idx < A.n;
+  const int64_t w = live ? idx : A.n - 1;
+  float x = A.pos[w], y = A.pos[A.n + w], vx = A.vel[w], vy = A.vel[A.n + w];
+  float zodd_x = 0.f, zodd_y = 0.f;
+  uint32_t parity = 0;
+  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+    const int64_t t = A.step0 + ts;
+    const float sc = ((BP.axis ? y : x) - BP.lo) * BP.inv_range;
+    // ---- mask row m_i = [u_i s + c_i > 0], i < H, as FP16 0 / 1
+#pragma unroll
+    for (int c = 0; c < H / 8; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 2; ++q4) {
+        float u4[4], c4[4], m4[4];
+        lds_vec(uvec + 8 * c + 4 * q4, u4);
+        lds_vec(cvec + 8 * c + 4 * q4, c4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m4[q] = fmaf(u4[q], sc, c4[q]) > 0.f ? 1.f : 0.f;
+        const __half2 h0 = __floats2half2_rn(m4[0], m4[1]), h1 = __floats2half2_rn(m4[2], m4[3]);
+        pk[2 * q4] = *reinterpret_cast<const uint32_t*>(&h0);
+        pk[2 * q4 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      sts128(tile + row_off + (uint32_t)((c ^ (tl & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&sm.ready[g]);
+    if (tl == 0) {
+      mbar_wait(&sm.ready[g], parity);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < H / 16; ++kk) {
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_f16(tmem, dM + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+        umma_f16(tmem, dM + o, dWlo + o, kIdesc, 1u);
+      }
+      umma_commit(&sm.bar[g]);
+    }
+    float gx = 0.f, gy = 0.f, e = 0.f;
+    PotGeneric<float>::template grad<false>(PP, x, y, e, gx, gy);
+    float zx, zy;
+    if (INJECT) {
+      zx = A.noise[(ts * 2) * A.n + w];
+      zy = A.noise[(ts * 2 + 1) * A.n + w];
+    } else if (!(t & 1) || ts == 0) {
+      const uint4 r = philox_call(A.gid0 + (uint64_t)w, (uint64_t)(t >> 1), kStreamDyn2, K);
+      float z0, z1, z2, z3;
+      box_muller(r.x, r.y, z0, z1);
+      box_muller(r.z, r.w, z2, z3);
+      if (t & 1) {
+        zx = z2;
+        zy = z3;
+      } else {
+        zx = z0;
+        zy = z1;
+        zodd_x = z2;
+        zodd_y = z3;
+      }
+    } else {
+      zx = zodd_x;
+      zy = zodd_y;
+    }
+    // ---- epilogue: z2_j = b2_j + (s D_j + D_{H+j}) / wscale, second ReLU, output layer, chain rule
+    mbar_wait(&sm.bar[g], parity);
+    parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float dval0 = 0.f, dval1 = 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < H; j0 += 16) {
+      float dz[16], zc[16];
+      tmem_ld16(tmem + tlane + (uint32_t)j0, dz);
+      tmem_ld16(tmem + tlane + (uint32_t)(H + j0), zc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float b4[4], w4[4];
+        lds_vec(b2 + j0 + 4 * q4, b4);
+        lds_vec(wout + j0 + 4 * q4, w4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float z2 = fmaf(fmaf(sc, dz[4 * q4 + q], zc[4 * q4 + q]), inv_w, b4[q]);
+          const float wd = z2 > 0.f ? w4[q] : 0.f;
+          if (q & 1) dval1 = fmaf(wd, dz[4 * q4 + q], dval1);
+          else dval0 = fmaf(wd, dz[4 * q4 + q], dval0);
+        }
+      }
+    }
+    const float gb = (dval0 + dval1) * inv_w * BP.inv_range;
+    gx += BP.axis ? 0.f : gb;
+    gy += BP.axis ? gb : 0.f;
+    vx = fmaf(I.c_over_sqrtm, zx, fmaf(-I.b_over_m, gx, I.a * vx));
+    vy = fmaf(I.c_over_sqrtm, zy, fmaf(-I.b_over_m, gy, I.a * vy));
+    x = fmaf(I.dt, vx, x);
+    y = fmaf(I.dt, vy, y);
+  }
+  if (live) {
+    A.pos[w] = x;
+    A.pos[A.n + w] = y;
+    A.vel[w] = vx;
+    A.vel[A.n + w] = vy;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
+}
+
+template <int H, int G>
+cudaError_t launch_tc_relu(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
+                           const RngKeys& K, cudaStream_t st) {
+  auto kern = A.noise != nullptr ? langevin2d_tc_relu_kernel<H, G, true> : langevin2d_tc_relu_kernel<H, G, false>;
+  const size_t smem = sizeof(TcReluSmem<H, G>) + 1024;
+  static_assert(sizeof(TcReluSmem<H, G>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
+  static_assert(G * 2 * H <= 512, "accumulators do not fit the TMEM columns of an SM");
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t per_block = (int64_t)kGT * G;
+  kern<<<(unsigned)((A.n + per_block - 1) / per_block), kGT * G, smem, st>>>(A, I, PP, BP, K);
+  return cudaGetLastError();
+}
+
 template <int H, int ACT>
 cudaError_t launch_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
                           const RngKeys& K, cudaStream_t st) {
@@ -807,6 +1014,16 @@ cudaError_t launch_langevin2d_tc_mlp(const StepArgs<float>& A, const IntegratorP
                                      const MlpParams<float>& BP, int H, int act, const RngKeys& K, cudaStream_t st) {
   if (A.traj != nullptr || BP.linear) return cudaErrorNotSupported;
   const bool relu = act == PYVES_ACT_RELU;
+  static const int general = getenv("PYVES_TC_MLP_GENERAL") ? atoi(getenv("PYVES_TC_MLP_GENERAL")) : 0;   // experiment knob: 1 = no ReLU specialisation
+  static const int rg = getenv("PYVES_TC_RELU_GROUPS") ? atoi(getenv("PYVES_TC_RELU_GROUPS")) : 0;        // experiment knob
+  if (relu && !general) {
+    switch (H) {
+      case 32: return rg == 4 ? launch_tc_relu<32, 4>(A, I, PP, BP, K, st) : rg == 6 ? launch_tc_relu<32, 6>(A, I, PP, BP, K, st) : launch_tc_relu<32, 8>(A, I, PP, BP, K, st);
+      case 48: return rg == 3 ? launch_tc_relu<48, 3>(A, I, PP, BP, K, st) : rg == 4 ? launch_tc_relu<48, 4>(A, I, PP, BP, K, st) : launch_tc_relu<48, 5>(A, I, PP, BP, K, st);
+      case 64: return rg == 3 ? launch_tc_relu<64, 3>(A, I, PP, BP, K, st) : launch_tc_relu<64, 4>(A, I, PP, BP, K, st);
+      default: return cudaErrorNotSupported;
+    }
+  }
   switch (H) {
     case 32: return relu ? launch_tc_mlp<32, PYVES_ACT_RELU>(A, I, PP, BP, K, st) : launch_tc_mlp<32, PYVES_ACT_TANH>(A, I, PP, BP, K, st);
     case 48: return relu ? launch_tc_mlp<48, PYVES_ACT_RELU>(A, I, PP, BP, K, st) : launch_tc_mlp<48, PYVES_ACT_TANH>(A, I, PP, BP, K, st);

@@ -218,6 +218,9 @@ TRAJ_CASES = [
     ("slip_forced_leg1d7y", potentials.SLIP_BOND_2D, (1.5, -0.5, 0.8, 4.0, 3.0, 0.2, 2.5), lambda r: rng_spec("leg1d", r, degree=7, axis='y', min=-4.0, max=6.0, scale=1.0), (-3.0, -2.5, -3.0, -2.5), [-1]),
     ("sb_none", potentials.SZABO_BEREZHKOVSKII, None, lambda r: dict(kind="none"), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
+    # ReLU nets with one H x H layer run the mask-operand tensor-core kernel (H padded to 32 / 48 / 64)
+    ("sb_mlp_relu_32", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[30, 32, 28]), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
+    ("catch_mlp_relu_64", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[64, 60, 64], scale=0.25), (-3.7, -3.2, -3.7, -3.2), [-1, 6]),
     ("sb_mlp128x2", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[128, 128]), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("sb_mlp16", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[16]), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("catch_mlp_tanh", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[20, 30, 24], act=1), (-3.7, -3.2, -3.7, -3.2), [-1, 6]),
