@@ -63,6 +63,7 @@ struct pyves_ctx {
   size_t mlp_np = 0;                // number of parameters (torch parameters() order)
   void* mlp_theta_dev = nullptr;
   void* mlp_packed_dev = nullptr;
+  void* tc_img = nullptr;          // operand image of the tensor-core Legendre step kernel (langevin2d_tc_scratch_bytes())
   int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
   int mlp_width = 0, mlp_linear = 0;
   double mlp_bout = 0, mlp_u0 = 0;
@@ -420,10 +421,11 @@ template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaSt
 // tuning variant 7: the 2D Legendre contraction on the tensor cores (langevin_tc.cu); returns 1 when it did not apply
 template <typename T> int run_tc(pyves_ctx*, const StepArgs<T>&, cudaStream_t) { return 1; }
 template <> int run_tc<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream_t st) {
-  const cudaError_t rc = launch_langevin2d_tc(A, integrator_params<float>(h), pot_params<float>(h), l2_params<float>(h), make_keys(h->seed), st);
+  if (!h->tc_img) CU(cudaMalloc(&h->tc_img, langevin2d_tc_scratch_bytes()));
+  const cudaError_t rc = launch_langevin2d_tc(A, integrator_params<float>(h), pot_params<float>(h), l2_params<float>(h), make_keys(h->seed), h->tc_img, st);
   if (rc == cudaErrorNotSupported) return 1;
   if (rc != cudaSuccess) return fail(h, PYVES_ECUDA, std::string("launch_langevin2d_tc: ") + cudaGetErrorString(rc));
-  g_launches++;
+  g_launches += 2;   // tc_weight_prep_kernel + langevin2d_tc_kernel
   return PYVES_OK;
 }
 
@@ -688,7 +690,7 @@ int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
   void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->l1_wt_dev, h->l1_w64_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
-                  h->scratch, h->stage, h->fail_dev};
+                  h->scratch, h->stage, h->fail_dev, h->tc_img};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;

@@ -369,8 +369,11 @@ langevin_general_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const 
 template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n, cudaStream_t st);
 
 // experimental tensor-core step kernel for the 2D Legendre bias (langevin_tc.cu); cudaErrorNotSupported when it does not apply
+// `scratch`: device buffer of langevin2d_tc_scratch_bytes() bytes owned by the caller (the operand image of the folded coefficient
+// matrices, rebuilt by a one-block kernel on `st` at every launch, so coefficients updated on the device are picked up)
+size_t langevin2d_tc_scratch_bytes();
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
-                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st);
+                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, void* scratch, cudaStream_t st);
 
 cudaError_t launch_langevin2d_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                                      const MlpParams<float>& BP, int H, int act, const RngKeys& K, cudaStream_t st);

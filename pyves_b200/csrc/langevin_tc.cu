@@ -169,16 +169,68 @@ template <int KYP> struct TcLayout {
 constexpr int kW2Bytes = 128 * 128;         // [WA rows 0..KXP) | WB rows KXP..2 KXP)][64 j FP16], 128-byte rows: 16 KB
 
 template <int KYP, int G, int WPT> struct TcSmem {
-  alignas(1024) unsigned char a[G][WPT][TcLayout<KYP>::kTiles][kTileBytes];   // at kernel start: scratch for WA, WB in FP32 (32 KB)
+  alignas(1024) unsigned char a[G][WPT][TcLayout<KYP>::kTiles][kTileBytes];
   alignas(1024) unsigned char w[2][kW2Bytes];        // stacked weights, hi and lo parts
   alignas(8) uint64_t bar[G][WPT];                   // contraction done (tcgen05.commit)
   alignas(8) uint64_t ready[G][WPT];                 // all 128 rows of the set written and last step's TMEM reads done (128 arrivals)
-  double kappa[64];
-  float red[32];
   uint32_t tmem_base;
 };
 
 __host__ __device__ constexpr uint32_t tmem_cols(int need) { return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u; }
+
+// Once per launch, one block: folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients, times kappa_row
+// kappa_column), their common power-of-two scale (max |W| into [2^12, 2^13): FP16 range; found on the device so that coefficients
+// handed over on the device need no host copy), and the stacked B operand image -- row r < KXP = WA[r][.], row KXP + i = WB[i][.],
+// 64 j (K index) per 128-byte row, hi and lo parts, K-major SWIZZLE_128B -- exactly as the step kernel's shared memory holds it.
+// img: [hi 16 KB][lo 16 KB][wscale].
+__global__ void __launch_bounds__(1024, 1) tc_weight_prep_kernel(const Legendre2DSmemParams<float> BP, const int KXP, unsigned char* __restrict__ img) {
+  __shared__ float wab[2 * 64 * 64];
+  __shared__ double kappa[64];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < 64) kappa[tid] = monic_kappa(tid);
+  __syncthreads();
+  float wmax = 0.f;
+  for (int item = tid; item < 2 * 64 * 64; item += blockDim.x) {
+    const int which = item >> 12, r = (item >> 6) & 63, c = item & 63;
+    double acc = 0.0;
+    if (which == 0) {
+      // WA[k = r][j = c]: (2k+1) times the sum over i = k + 1, k + 3, ... of w_ij
+      if (r < BP.kx && c < BP.ky)
+        for (int i = r + 1; i < BP.kx; i += 2) acc += (double)BP.w[i * BP.ky + c];
+      acc *= (double)(2 * r + 1);
+    } else {
+      // WB[i = r][k = c]: (2k+1) times the sum over j = k + 1, k + 3, ... of w_ij
+      if (r < BP.kx && c < BP.ky)
+        for (int j = c + 1; j < BP.ky; j += 2) acc += (double)BP.w[r * BP.ky + j];
+      acc *= (double)(2 * c + 1);
+    }
+    const float v = (float)(acc * kappa[r] * kappa[c]);
+    wab[item] = v;
+    wmax = fmaxf(wmax, fabsf(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if ((tid & 31) == 0) red[warp] = wmax;
+  __syncthreads();
+  float m = 0.f;
+  for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, red[q]);
+  int ex = 0;
+  if (m > 0.f && m < 3e38f) frexpf(m, &ex);
+  const float wscale = ldexpf(1.f, 13 - ex);
+  if (tid == 0) *reinterpret_cast<float*>(img + 2 * kW2Bytes) = wscale;
+  for (int item = tid; item < 2 * KXP * 8; item += blockDim.x) {
+    const int r = item >> 3, c = item & 7;
+    const float* src = (r < KXP ? wab + r * 64 : wab + 64 * 64 + (r - KXP) * 64) + 8 * c;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = src[q] * wscale;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(img + off) = hi;
+    *reinterpret_cast<uint4*>(img + kW2Bytes + off) = lo;
+  }
+}
 
 // KXP / KYP = number of x / y functions padded to 16, 32 or 64 (UMMA N = 2 KXP, K extent KYP; weights beyond kx, ky are zero).
 // WPT walker sets per group (thread = one walker of each set; with WPT = 2 the two recursions of a thread run as one packed
@@ -187,9 +239,8 @@ __host__ __device__ constexpr uint32_t tmem_cols(int need) { return need <= 32 ?
 template <int KXP, int KYP, int G, int WPT, bool INJECT>
 __global__ void __launch_bounds__(kGT* G, 1)
 langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
-                     const Legendre2DSmemParams<float> BP, const RngKeys K) {
+                     const Legendre2DSmemParams<float> BP, const RngKeys K, const unsigned char* __restrict__ wimg) {
   using LY = TcLayout<KYP>;
-  static_assert(sizeof(TcSmem<KYP, G, WPT>::a) >= 2 * 64 * 64 * sizeof(float), "operand tiles double as the FP32 scratch of the weight transform");
   extern __shared__ unsigned char smem_raw[];
   TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -208,61 +259,17 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr MonicTab tab = make_monic_tab();
-  if (tid < 64) sm.kappa[tid] = monic_kappa(tid);
-  __syncthreads();
-  // ---- folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients, times kappa_row kappa_column), 64 x 64 FP32
-  //      each, in the tile area
-  float* const wa = reinterpret_cast<float*>(&sm.a[0][0][0][0]);
-  float* const wb = wa + 64 * 64;
-  float wmax = 0.f;
-  for (int item = tid; item < 2 * 64 * 64; item += blockDim.x) {
-    const int which = item >> 12, r = (item >> 6) & 63, c = item & 63;
-    double acc = 0.0;
-    if (which == 0) {
-      // WA[k = r][j = c]: sum over i = k + 1, k + 3, ... of w_ij
-      if (r < BP.kx && c < BP.ky)
-        for (int i = r + 1; i < BP.kx; i += 2) acc += (double)BP.w[i * BP.ky + c];
-      acc *= (double)(2 * r + 1);
-    } else {
-      // WB[i = r][k = c]: sum over j = k + 1, k + 3, ... of w_ij
-      if (r < BP.kx && c < BP.ky)
-        for (int j = c + 1; j < BP.ky; j += 2) acc += (double)BP.w[r * BP.ky + j];
-      acc *= (double)(2 * c + 1);
-    }
-    const float v = (float)(acc * sm.kappa[r] * sm.kappa[c]);
-    wa[item] = v;
-    wmax = fmaxf(wmax, fabsf(v));
+  // stacked B operand (WA rows over WB rows, hi and lo parts), prepared once per launch by tc_weight_prep_kernel in the final
+  // swizzled layout: a straight copy of 2 KXP rows of 128 bytes each
+  for (int item = tid; item < 2 * (2 * KXP * 8); item += blockDim.x) {
+    const int part = item / (2 * KXP * 8), off = (item % (2 * KXP * 8)) * 16;
+    const uint4 v = *reinterpret_cast<const uint4*>(wimg + part * kW2Bytes + off);
+    sts128(smem_u32(sm.w[part]) + (uint32_t)off, v);
   }
-  // scale: a power of two that brings max |W| into [2^12, 2^13) (FP16 range), found by every block itself so that
-  // coefficients handed over on the device need no host copy
-  float wscale;
-  {
-    float m = wmax;
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) sm.red[warp] = m;
-    __syncthreads();
-    m = 0.f;
-    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm.red[q]);
-    int ex = 0;
-    if (m > 0.f && m < 3e38f) frexpf(m, &ex);
-    wscale = ldexpf(1.f, 13 - ex);
-  }
-  // stacked B operand: row r < KXP = WA[r][.], row KXP + i = WB[i][.]; 64 j (K index) per 128-byte row, scaled by wscale
-  for (int item = tid; item < 2 * KXP * 8; item += blockDim.x) {
-    const int r = item >> 3, c = item & 7;
-    const float* src = (r < KXP ? wa + r * 64 : wb + (r - KXP) * 64) + 8 * c;
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = src[q] * wscale;
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    sts128(smem_u32(sm.w[0]) + off, hi);
-    sts128(smem_u32(sm.w[1]) + off, lo);
-  }
+  const float wscale = *reinterpret_cast<const float*>(wimg + 2 * kW2Bytes);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();                                                       // also: the scratch is free to become operand tiles
+  __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;           // this warp's TMEM lanes
   const uint32_t row_off = (uint32_t)(tl >> 3) * 1024u + (uint32_t)(tl & 7) * 128u;
@@ -523,7 +530,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 
 template <int KXP, int KYP, int G, int WPT>
 cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
-                      const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
+                      const Legendre2DSmemParams<float>& BP, const RngKeys& K, unsigned char* img, cudaStream_t st) {
   auto kern = A.noise != nullptr ? langevin2d_tc_kernel<KXP, KYP, G, WPT, true> : langevin2d_tc_kernel<KXP, KYP, G, WPT, false>;
   const size_t smem = sizeof(TcSmem<KYP, G, WPT>) + 1024;
   static_assert(sizeof(TcSmem<KYP, G, WPT>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
@@ -532,7 +539,8 @@ cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I
   if (e != cudaSuccess) return e;
   const int64_t per_block = (int64_t)kGT * G * WPT;
   const unsigned grid = (unsigned)((A.n + per_block - 1) / per_block);
-  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K);
+  tc_weight_prep_kernel<<<1, 1024, 0, st>>>(BP, KXP, img);
+  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K, img);
   return cudaGetLastError();
 }
 
@@ -963,7 +971,7 @@ cudaError_t launch_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float
 
 template <int KXP>
 cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
-                         const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
+                         const Legendre2DSmemParams<float>& BP, const RngKeys& K, unsigned char* img, cudaStream_t st) {
   // groups per CTA: 64 KB of operand tiles per group at KYP = 64 (three fit), 32 / 16 KB below (four: 512 threads at <= 128 registers)
   // groups per CTA x walker sets per group, measured on B200 (10^6 walkers, profiles/r02_tc_step_shapes.md): the kernels are bound by
   // instruction issue and dependent FP32 chains, so more resident warps (6 groups at <= 80 registers) beat two walker sets per thread
@@ -971,42 +979,45 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
   if (BP.ky <= 16) {
     if (KXP == 16) {
       switch (shape) {
-        case 41: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, st);
-        case 42: return launch_tc<16, 16, 4, 2>(A, I, PP, BP, K, st);
-        case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, st);
-        case 71: return launch_tc<16, 16, 7, 1>(A, I, PP, BP, K, st);
-        case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, st);
-        case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, st);
-        default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, st);
+        case 41: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, img, st);
+        case 42: return launch_tc<16, 16, 4, 2>(A, I, PP, BP, K, img, st);
+        case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, img, st);
+        case 71: return launch_tc<16, 16, 7, 1>(A, I, PP, BP, K, img, st);
+        case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, img, st);
+        case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, img, st);
+        default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, img, st);
       }
     }
-    return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+    return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
   }
   if (BP.ky <= 32) {
     if (KXP == 32) {
       switch (shape) {
-        case 41: return launch_tc<32, 32, 4, 1>(A, I, PP, BP, K, st);
-        case 51: return launch_tc<32, 32, 5, 1>(A, I, PP, BP, K, st);
-        case 71: return launch_tc<32, 32, 7, 1>(A, I, PP, BP, K, st);
-        case 81: return launch_tc<32, 32, 8, 1>(A, I, PP, BP, K, st);
-        case 42: return launch_tc<32, 32, 4, 2>(A, I, PP, BP, K, st);
-        default: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, st);
+        case 41: return launch_tc<32, 32, 4, 1>(A, I, PP, BP, K, img, st);
+        case 51: return launch_tc<32, 32, 5, 1>(A, I, PP, BP, K, img, st);
+        case 71: return launch_tc<32, 32, 7, 1>(A, I, PP, BP, K, img, st);
+        case 81: return launch_tc<32, 32, 8, 1>(A, I, PP, BP, K, img, st);
+        case 42: return launch_tc<32, 32, 4, 2>(A, I, PP, BP, K, img, st);
+        default: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, img, st);
       }
     }
-    return launch_tc<KXP, 32, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, st);
+    return launch_tc<KXP, 32, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
   }
-  if (KXP == 64 && shape == 31) return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, st);
-  return launch_tc<KXP, 64, 4, 1>(A, I, PP, BP, K, st);
+  if (KXP == 64 && shape == 31) return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, img, st);
+  return launch_tc<KXP, 64, 4, 1>(A, I, PP, BP, K, img, st);
 }
 
 }  // namespace
 
+size_t langevin2d_tc_scratch_bytes() { return 2 * kW2Bytes + 256; }
+
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
-                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, cudaStream_t st) {
-  if (BP.kx > 64 || BP.ky > 64 || BP.kx < 1 || BP.ky < 1 || A.traj != nullptr) return cudaErrorNotSupported;
-  if (BP.kx <= 16) return launch_tc_ky<16>(A, I, PP, BP, K, st);
-  if (BP.kx <= 32) return launch_tc_ky<32>(A, I, PP, BP, K, st);
-  return launch_tc_ky<64>(A, I, PP, BP, K, st);
+                                 const Legendre2DSmemParams<float>& BP, const RngKeys& K, void* scratch, cudaStream_t st) {
+  if (BP.kx > 64 || BP.ky > 64 || BP.kx < 1 || BP.ky < 1 || A.traj != nullptr || scratch == nullptr) return cudaErrorNotSupported;
+  unsigned char* img = static_cast<unsigned char*>(scratch);
+  if (BP.kx <= 16) return launch_tc_ky<16>(A, I, PP, BP, K, img, st);
+  if (BP.kx <= 32) return launch_tc_ky<32>(A, I, PP, BP, K, img, st);
+  return launch_tc_ky<64>(A, I, PP, BP, K, img, st);
 }
 
 // NN bias with three hidden layers packed at width H = 32 / 48 / 64 (MlpParams::packed of pyves_set_bias_mlp[_device])
