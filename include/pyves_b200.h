@@ -245,7 +245,8 @@ const char* pyves_comm_last_error(void);
 /* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel; 7 / 6 = the 2D Legendre
  * contraction of the step kernel on the tensor cores for every size <= 64 x 64 / on the CUDA cores for every size (default:
  * tensor cores for every FP32 2D Legendre basis up to 64 x 64 except the static 8 x 8 double-well kernel); 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed
- * again; 1000 + k = process-wide: rows the tensor-core covariance accumulates in TMEM between two drains = 2^k) */
+ * again; 96 / 95 = process-wide: first moments of 2D bases beyond 16 x 16 with the one-function-per-thread kernel / the register-tiled
+ * kernel again; 1000 + k = process-wide: rows the tensor-core covariance accumulates in TMEM between two drains = 2^k) */
 int pyves_set_tuning(pyves_t* h, int variant);
 
 /* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */

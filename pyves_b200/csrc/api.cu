@@ -795,6 +795,10 @@ int pyves_set_tuning(pyves_t* h, int variant) {
     set_no_tensor_cores(variant == 98);
     return PYVES_OK;
   }
+  if (variant == 96 || variant == 95) {   // 96: first moments of large 2D bases with the one-function-per-thread kernel; 95: register-tiled kernel again
+    set_tiled_first_moments(variant == 95);
+    return PYVES_OK;
+  }
   if (variant >= 1000 && variant <= 1030) {   // rows per CTA of the tensor-core covariance: 2^(variant - 1000)
     cov_tc_set_max_rows((int64_t)1 << (variant - 1000));
     return PYVES_OK;

@@ -147,6 +147,140 @@ __global__ void __launch_bounds__(kMomThreads) moments1_kernel(const RowSource<T
   }
 }
 
+// First moments of a LARGE 2D product basis (K > 256), register tiled.  moments1_kernel gives every thread one basis function
+// per pass and pays two shared-memory loads per FMA (K = 4096: 1.25 ms per 10^6 rows, LSU bound).  Here
+//   phase 1: ALL threads build the factor tables of a 128-row tile -- thread r < 128 the A (x) factors of row r, row weight
+//            folded in, thread 128 + r the B (y) factors -- four values per 128-bit store (row stride = k + 4 words: conflict free);
+//   phase 2: a thread owns a 4 x 4 tile of functions (a in 4 ta .., b in 4 tb ..) and, when the basis has fewer than 256 such
+//            tiles, one of RG row groups: per row two 128-bit loads feed 16 FMAs;
+// partial sums leave the tile loop in FP64 (one add per accumulator and tile), the row groups are summed through shared memory
+// at the end.  part_f[block][K], part_w[block] as for moments1_kernel.
+constexpr int kTileRows = 128;
+template <typename T>
+__global__ void __launch_bounds__(kMomThreads) moments1_tiled_kernel(const RowSource<T> S, const BasisParams<T> B,
+                                                                     double* __restrict__ part_f, double* __restrict__ part_w) {
+  constexpr int R = kTileRows;
+  constexpr int V = 16 / sizeof(T);
+  struct alignas(16) Vec { T v[V]; };
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int kap = ((B.ka + 3) & ~3) + 4, kbp = ((B.kb + 3) & ~3) + 4;
+  T* fa = reinterpret_cast<T*>(smem_raw);        // [R][kap]
+  T* fb = fa + R * kap;                          // [R][kbp]
+  __shared__ double wred[kMomThreads / 32];
+  const int ka4 = (B.ka + 3) >> 2, kb4 = (B.kb + 3) >> 2;
+  const int nt = ka4 * kb4, RG = kMomThreads / nt;
+  const int tile_id = threadIdx.x % nt, rg = threadIdx.x / nt;
+  const bool active = rg < RG;
+  const int ta = tile_id / kb4, tb = tile_id - ta * kb4;
+  double acc64[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc64[i][j] = 0.0;
+  double wsum = 0.0;
+  const int64_t ntiles = (S.n + R - 1) / R;
+  const int row = threadIdx.x & (R - 1), side = threadIdx.x >> 7;          // phase 1 role (R = 128, 256 threads)
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r = tile * R + row;
+    {
+      const int kf = side ? B.kb : B.ka, kfp = side ? kbp : kap;
+      T* dst = (side ? fb : fa) + row * kfp;
+      T wt = T(0), s = T(0);
+      if (r < S.n) {
+        const T x = S.pos[r * S.stride_row], y = S.pos[r * S.stride_row + S.stride_col];
+        bool inx, iny;
+        const T sx = scale_clamp(x, B.ca, B.iha, inx), sy = scale_clamp(y, B.cb, B.ihb, iny);
+        wt = S.w != nullptr ? S.w[r] : T(1);
+        if (B.inside_only && !(inx && iny)) wt = T(0);
+        s = side ? sy : sx;
+        if (side == 0) wsum += (double)wt;
+      }
+      const T scale = side ? (r < S.n ? T(1) : T(0)) : wt;                 // the row weight rides on factor A; rows past the end are zero
+      T pm = T(1), p = s;
+      for (int n0 = 0; n0 < kf; n0 += 4) {
+        Vec out[4 / V];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = n0 + q;
+          T val;
+          if (n == 0) {
+            val = T(1);
+          } else if (n == 1) {
+            val = s;
+          } else {
+            const T fn = T(n - 1);
+            const T pn = ((T(2) * fn + T(1)) * s * p - fn * pm) / (fn + T(1));   // the arithmetic of row_factors
+            pm = p;
+            p = pn;
+            val = pn;
+          }
+          out[q / V].v[q % V] = n < kf ? val * scale : T(0);
+        }
+#pragma unroll
+        for (int h = 0; h < 4 / V; ++h) *reinterpret_cast<Vec*>(dst + n0 + h * V) = out[h];
+      }
+    }
+    __syncthreads();
+    if (active) {
+      T acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+#pragma unroll 4
+      for (int rr = rg; rr < R; rr += RG) {
+        T a4[4], b4[4];
+#pragma unroll
+        for (int h = 0; h < 4 / V; ++h) {
+          const Vec av = *reinterpret_cast<const Vec*>(fa + rr * kap + ta * 4 + h * V);
+          const Vec bv = *reinterpret_cast<const Vec*>(fb + rr * kbp + tb * 4 + h * V);
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            a4[h * V + q] = av.v[q];
+            b4[h * V + q] = bv.v[q];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = Math<T>::fma(a4[i], b4[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc64[i][j] += (double)acc[i][j];
+    }
+    __syncthreads();
+  }
+  // row groups -> one vector per block, through shared memory: red[rg][tile][16]
+  double* red = reinterpret_cast<double*>(smem_raw);
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[((size_t)rg * nt + tile_id) * 16 + i * 4 + j] = acc64[i][j];
+  }
+  __syncthreads();
+  const int K = B.ka * B.kb;
+  for (int e = threadIdx.x; e < nt * 16; e += kMomThreads) {
+    const int tl = e >> 4, ij = e & 15;
+    const int a = (tl / kb4) * 4 + (ij >> 2), b = (tl % kb4) * 4 + (ij & 3);
+    if (a < B.ka && b < B.kb) {
+      double sum = 0.0;
+      for (int g = 0; g < RG; ++g) sum += red[((size_t)g * nt + tl) * 16 + ij];
+      part_f[(int64_t)blockIdx.x * K + a * B.kb + b] = sum;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sw = 0.0;
+    for (int i = 0; i < kMomThreads / 32; ++i) sw += wred[i];
+    part_w[blockIdx.x] = sw;
+  }
+}
+
 // out[m] = sum_g part[g][m] (m < M) and out_w[0] = sum_g part_w[g], in a fixed order (deterministic):
 // one warp per column, lane l adds the partials g = l, l + 32, ... (independent loads, all in flight
 // together), then a butterfly over the lanes.  A single thread walking the G = 592 partials of a column
@@ -471,6 +605,8 @@ template <> struct TcDispatch<float> {
 };
 
 static bool g_no_tc = false;
+static bool g_tiled_first = true;    // experiment knob (pyves_set_tuning 96 / 95): register-tiled first moments of large 2D bases
+void set_tiled_first_moments(bool v) { g_tiled_first = v; }
 bool no_tensor_cores() { return g_no_tc; }
 void set_no_tensor_cores(bool v) { g_no_tc = v; }
 
@@ -505,7 +641,27 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
       return cudaGetLastError();
     }
   }
-  {
+  if (B.kind == PYVES_BIAS_LEGENDRE_2D && B.kb > 1 && K > 256 && K <= 4096 && g_tiled_first) {   // large product bases: register-tiled
+    constexpr int R = kTileRows;
+    const int64_t tiles = (S.n + R - 1) / R;
+    const int G = (int)(tiles < kMaxBlocks ? tiles : kMaxBlocks);
+    double* part_f = scratch;
+    double* part_w = scratch + (size_t)kMaxBlocks * K;
+    const int kap = ((B.ka + 3) & ~3) + 4, kbp = ((B.kb + 3) & ~3) + 4;
+    size_t sm = (size_t)R * (kap + kbp) * sizeof(T);
+    const size_t red = (size_t)kMomThreads * 16 * sizeof(double);
+    if (sm < red) sm = red;
+    auto kern = moments1_tiled_kernel<T>;
+    if (sm + 1024 > 48 * 1024) {   // static shared memory counts against the default limit too
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<G, kMomThreads, sm, st>>>(S, B, part_f, part_w);
+    launch_reduce_partials(part_f, G, K, sum_wf, part_w, sum_w, st);
+    *launches += 2;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else {
     constexpr int R = Tile<T>::kRows1;
     const int64_t tiles = (S.n + R - 1) / R;
     const int G = (int)(tiles < kMaxBlocks ? tiles : kMaxBlocks);

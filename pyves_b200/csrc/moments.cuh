@@ -54,6 +54,7 @@ cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B
 void cov_tc_set_max_rows(int64_t rows);   // rows one CTA accumulates in FP32 before its partial goes to the FP64 sum (tuning)
 constexpr int kMaxSmForScratch = 160;
 bool no_tensor_cores();
+void set_tiled_first_moments(bool v);   // tuning / test switch: register-tiled first moments of large 2D bases (default on)
 void set_no_tensor_cores(bool v);   // tuning / test switch: force the CUDA-core covariance
 
 template <typename T>

@@ -516,6 +516,9 @@ MOMENT_CASES = [
     ("leg2d16", lambda r: rng_spec("leg2d", r, deg_x=15, deg_y=15), True),
     ("leg2d_5x9", lambda r: rng_spec("leg2d", r, deg_x=4, deg_y=8), True),
     ("leg2d32", lambda r: rng_spec("leg2d", r, deg_x=31, deg_y=31), False),
+    # K > 256: register-tiled first moments (4 x 4 functions per thread); ragged edges and the largest basis
+    ("leg2d_19x37", lambda r: rng_spec("leg2d", r, deg_x=18, deg_y=36), False),
+    ("leg2d64", lambda r: rng_spec("leg2d", r, deg_x=63, deg_y=63), False),
     ("pathcv", lambda r: dict(kind="pathcv", degree=6, x_i=np.linspace(-2, 2, 30), y_i=np.linspace(-1, 1.5, 30), lam=20.0, weights=r.standard_normal(7), phi=0.0), True),
     ("mlp48x3", lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), False),
     ("mlp128x2", lambda r: rng_spec("mlp", r, sizes=[128, 128]), False),          # the reference example's net (deepves...:102)
@@ -558,7 +561,7 @@ def test_moments_vs_oracle(case):
         e.close()
 
 
-@pytest.mark.parametrize("case", [c for c in MOMENT_CASES if c[0] in ("leg1d12y", "leg2d16", "leg2d_5x9", "leg2d32")],
+@pytest.mark.parametrize("case", [c for c in MOMENT_CASES if c[0] in ("leg1d12y", "leg2d16", "leg2d_5x9", "leg2d32", "leg2d_19x37", "leg2d64")],
                          ids=lambda c: c[0])
 def test_moments_inside_domain(case):
     """pyves_set_moment_domain(1): rows outside the basis interval get weight 0 (conditional averages on
