@@ -59,9 +59,11 @@ def parse_args():
     ap.add_argument("--update", default="device", choices=["device", "host"],
                     help="coefficient update of the resident-state loop: 'device' = optimiser, target refresh and coefficient "
                          "hand-over on the GPU (DeviceUpdater), 'host' = numpy optimiser + re-upload (VESBias_Ensemble)")
-    ap.add_argument("--e2e-chunks", type=int, default=4,
-                    help="e2e with --update device: the ensemble is cut into this many handles on their own streams so that the "
-                         "host<->device copies of one chunk overlap the step kernel of another (1 = one handle, serial copies)")
+    ap.add_argument("--e2e-chunks", type=int, default=8,
+                    help="e2e with --update device: the ensemble is cut into about this many handles on their own streams (at multiples "
+                         "of a wave of the step kernel, pyves_step_wave_walkers) so that the host<->device copies of one chunk overlap the "
+                         "step kernel of another (1 = one handle, serial copies).  Measured: 1 GPU 5 chunks 7.60e10 / 9 chunks 7.54e10; "
+                         "8 GPUs 5.30e11 / 5.56e11 -- the exposed head and tail copies cost more when eight processes share the host")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--comm", default="native", choices=["native", "torch"],
@@ -269,23 +271,34 @@ def run_ours(args):
         hmom = torch.empty(K + 1, dtype=torch.float64).pin_memory()
         ens.get_state(out=(hpos, hvel))
 
-        nch = args.e2e_chunks if (upd is not None and args.e2e_chunks > 1 and args.walkers % args.e2e_chunks == 0) else 1
+        # chunk boundaries: the tensor-core step kernel keeps one large CTA per SM, so a launch costs whole waves of
+        # wave_walkers() walkers; chunks are cut at multiples of a wave (a partial wave only in the last chunk)
+        bounds = [0, args.walkers]
+        if upd is not None and args.e2e_chunks > 1:
+            wave = ens.wave_walkers()
+            if wave > 0:
+                waves_total = -(-args.walkers // wave)
+                per_chunk = max(1, int(round(waves_total / args.e2e_chunks))) * wave
+            else:
+                per_chunk = -(-args.walkers // args.e2e_chunks)
+            bounds = list(range(0, args.walkers, per_chunk)) + [args.walkers]
+        nch = len(bounds) - 1
         if nch > 1:
             # chunked pipeline: walkers are independent between updates, so the ensemble is split into nch handles
             # (global walker ids preserved), each on its own stream; all copies are asynchronous from pinned memory
-            cn = args.walkers // nch
             subs, streams, hp, hv = [], [torch.cuda.Stream(device=dev) for _ in range(nch)], [], []
             for c in range(nch):
-                e = _lib.Ensemble(cn, dims=2, seed=args.seed, precision="fp32", device=local)
+                c0, c1 = bounds[c], bounds[c + 1]
+                e = _lib.Ensemble(c1 - c0, dims=2, seed=args.seed, precision="fp32", device=local)
                 e.set_integrator(1.0, KB * TEMP, 20.0, 0.01)
                 e.set_potential(_lib.POT_DOUBLE_WELL_2D)
-                e.set_walker_offset(rank * args.walkers + c * cn)
+                e.set_walker_offset(rank * args.walkers + c0)
                 e.set_tuning({"auto": -1, "cuda": 6, "tensor": 7}[args.step_kernel])
                 e.step_counter = ens.step_counter
                 upd.add_handle(e)
                 subs.append(e)
-                hp.append(torch.from_numpy(np.ascontiguousarray(hpos[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
-                hv.append(torch.from_numpy(np.ascontiguousarray(hvel[:, c * cn:(c + 1) * cn])).pin_memory().numpy())
+                hp.append(torch.from_numpy(np.ascontiguousarray(hpos[:, c0:c1])).pin_memory().numpy())
+                hv.append(torch.from_numpy(np.ascontiguousarray(hvel[:, c0:c1])).pin_memory().numpy())
             # per-chunk moment buffers allocated ONCE on the main stream and written through out=: no tensor allocated on a
             # side stream is consumed on the main stream (the caching allocator could hand such a block out again too early)
             mom = [(torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(K, dtype=torch.float64, device=dev), None) for _ in range(nch)]
@@ -340,7 +353,7 @@ def run_ours(args):
         state_bytes = 2 * 2 * args.walkers * 4
         e2e = {"value": n_total * args.stride * args.steps / float(w), "unit": "walker-steps/s",
                "h2d_bytes_per_step": state_bytes + (0 if upd is not None else K * 8), "d2h_bytes_per_step": state_bytes + (K + 1) * 8,
-               "chunks": nch, "numa_bound_cores": None if numa_cores is None else len(numa_cores)}
+               "chunks": nch, "chunk_walkers": [bounds[c + 1] - bounds[c] for c in range(nch)], "numa_bound_cores": None if numa_cores is None else len(numa_cores)}
         if nch > 1:
             for e in subs:
                 upd.handles.remove(e)

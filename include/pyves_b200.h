@@ -249,6 +249,13 @@ const char* pyves_comm_last_error(void);
  * kernel again; 1000 + k = process-wide: rows the tensor-core covariance accumulates in TMEM between two drains = 2^k) */
 int pyves_set_tuning(pyves_t* h, int variant);
 
+/* Walkers that ONE full wave of the handle's step kernel advances on its device (SMs x resident CTAs x walkers per CTA), or 0
+ * when the kernel has no such granularity worth respecting (light kernels with many small CTAs).  The tensor-core step kernels
+ * keep one large CTA per SM, so a launch costs whole waves: callers that split an ensemble into chunks (pipelined host <-> device
+ * copies; the reference has no counterpart, its one particle lives in an openmm.Context, ves/langevin_dynamics.py:60-76) should
+ * cut at multiples of this number. */
+int pyves_step_wave_walkers(pyves_t* h, int64_t* walkers);
+
 /* FP32 FMA throughput of `device` (TFLOP/s), the roofline denominator of the step kernel */
 int pyves_fp32_fma_peak(int device, double* tflops);
 /* the same probe issued as packed FP32x2 FMAs (FFMA2, sm_100) */

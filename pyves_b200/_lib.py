@@ -60,6 +60,7 @@ SIGNATURES = {
     "pyves_moments": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
+    "pyves_step_wave_walkers": (_i, [_vp, _c.POINTER(_i64)]),
     "pyves_set_moment_domain": (_i, [_vp, _i]),
     "pyves_averaged_sgd_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _i64, _vp, _vp, _vp]),
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
@@ -331,6 +332,13 @@ class Ensemble:
 
     def set_tuning(self, variant):
         self._ck(self.lib.pyves_set_tuning(self.h, variant))
+
+    def wave_walkers(self):
+        """Walkers one full wave of this handle's step kernel advances (0: no granularity worth respecting).  Chunked
+        pipelines should cut the ensemble at multiples of it: a partial wave costs a whole one."""
+        n = _i64(0)
+        self._ck(self.lib.pyves_step_wave_walkers(self.h, _c.byref(n)))
+        return int(n.value)
 
     def set_moment_domain(self, inside_only):
         """True: ``moments()`` averages over the rows inside the basis interval only (conditional

@@ -789,6 +789,27 @@ int pyves_averaged_sgd_step(int device, int K, const double* sum_w, const double
   return PYVES_OK;
 }
 
+int pyves_step_wave_walkers(pyves_t* h, int64_t* walkers) {
+  if (!h || !walkers) return PYVES_EINVAL;
+  *walkers = 0;
+  if (h->prec != PYVES_F32 || h->dims != 2 || h->scheme != PYVES_SCHEME_OPENMM_LANGEVIN) return PYVES_OK;
+  int per_cta = 0;
+  if (h->bias_kind == PYVES_BIAS_LEGENDRE_2D) {
+    const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
+    const bool tc = h->variant == 7 || (h->variant == -1 && !(kx == 8 && ky == 8 && h->pot.kind == PYVES_POT_DOUBLE_WELL_2D));
+    if (tc) per_cta = langevin2d_tc_walkers_per_cta(kx, ky);
+  } else if (h->bias_kind == PYVES_BIAS_MLP_1D && h->mlp_H > 0 && (h->variant == -1 || h->variant == 7)) {
+    per_cta = langevin2d_tc_mlp_walkers_per_cta(h->mlp_H, h->mlp_act);
+  }
+  if (per_cta > 0) {
+    int n_sm = 0;
+    DeviceGuard g(h->device);
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    *walkers = (int64_t)n_sm * per_cta;
+  }
+  return PYVES_OK;
+}
+
 int pyves_set_tuning(pyves_t* h, int variant) {
   if (!h) return PYVES_EINVAL;
   if (variant == 98 || variant == 97) {   // 98: covariance on CUDA cores only; 97: tensor cores allowed again

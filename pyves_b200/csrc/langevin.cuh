@@ -372,6 +372,8 @@ template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n,
 // `scratch`: device buffer of langevin2d_tc_scratch_bytes() bytes owned by the caller (the operand image of the folded coefficient
 // matrices, rebuilt by a one-block kernel on `st` at every launch, so coefficients updated on the device are picked up)
 size_t langevin2d_tc_scratch_bytes();
+int langevin2d_tc_walkers_per_cta(int kx, int ky);     // of the shape the launcher picks (one CTA per SM)
+int langevin2d_tc_mlp_walkers_per_cta(int H, int act);
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                                  const Legendre2DSmemParams<float>& BP, const RngKeys& K, void* scratch, cudaStream_t st);
 

@@ -1011,6 +1011,24 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
 
 size_t langevin2d_tc_scratch_bytes() { return 2 * kW2Bytes + 256; }
 
+// mirrors launch_tc_ky / launch_langevin2d_tc_mlp (default shapes)
+int langevin2d_tc_walkers_per_cta(int kx, int ky) {
+  if (kx > 64 || ky > 64 || kx < 1 || ky < 1) return 0;
+  if (ky > 32) return kGT * 4;
+  const bool square = (kx <= 16 && ky <= 16) || (kx > 16 && kx <= 32 && ky > 16);
+  if (square) return kGT * 6;
+  return kGT * 4 * (kx <= 32 ? 2 : 1);
+}
+int langevin2d_tc_mlp_walkers_per_cta(int H, int act) {
+  const bool relu = act == PYVES_ACT_RELU;
+  switch (H) {
+    case 32: return kGT * (relu ? 8 : 3);
+    case 48: return kGT * (relu ? 5 : 3);
+    case 64: return kGT * (relu ? 4 : 3);
+    default: return 0;
+  }
+}
+
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                                  const Legendre2DSmemParams<float>& BP, const RngKeys& K, void* scratch, cudaStream_t st) {
   if (BP.kx > 64 || BP.ky > 64 || BP.kx < 1 || BP.ky < 1 || A.traj != nullptr || scratch == nullptr) return cudaErrorNotSupported;
