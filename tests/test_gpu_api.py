@@ -409,6 +409,33 @@ def test_chunked_handles_async_copies_match_single_handle():
         h.close()
 
 
+def test_step_wave_walkers():
+    """pyves_step_wave_walkers: SMs x walkers per CTA for the tensor-core step kernels (one CTA per SM), 0 for the kernels with
+    many small CTAs and for FP64 handles."""
+    from pyves_b200 import _lib
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+
+    def wave(prec, setup, variant=-1):
+        e = _lib.Ensemble(1000, dims=2, seed=1, precision=prec)
+        e.set_integrator(1.0, 2.494, 20.0, 0.01)
+        e.set_potential(_lib.POT_DOUBLE_WELL_2D)
+        setup(e)
+        e.set_tuning(variant)
+        w = e.wave_walkers()
+        e.close()
+        return w
+
+    leg = lambda k: (lambda e: e.set_bias_legendre2d(k - 1, k - 1, (-2.5, 2.5, -2, 2), np.zeros(k * k)))
+    assert wave("fp32", leg(16)) == n_sm * 768 and wave("fp32", leg(32)) == n_sm * 768 and wave("fp32", leg(64)) == n_sm * 512
+    assert wave("fp32", leg(8)) == 0 and wave("fp32", leg(8), 7) == n_sm * 768      # static 8 x 8 double-well kernel unless forced
+    assert wave("fp32", leg(16), 6) == 0 and wave("fp64", leg(16)) == 0
+    assert wave("fp32", lambda e: e.set_bias_legendre1d(0, 5, -2.5, 2.5, np.zeros(6))) == 0
+    torch.manual_seed(0)
+    m = basis.NNBasis1D(min=-4, max=4, axis="x", hidden_layer_sizes=[48, 48, 48])
+    theta = np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
+    assert wave("fp32", lambda e: e.set_bias_mlp(0, -4.0, 4.0, [48, 48, 48], 0, theta)) == n_sm * 640
+
+
 def test_ensemble_ves_along_path_cv():
     """Ensemble VES with LegendreBasis2DPathCV (ves/basis.py:386-548) and a uniform target in the scaled path
     coordinate: the path runs along the x axis of the 2D double well through both minima, so the converged bias
