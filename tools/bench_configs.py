@@ -113,15 +113,16 @@ def cfg4(iters):
     b = bias.VESBias_Ensemble(model, target.Target_Uniform_HardSwitch_x(200), BETA, "Adam", {"lr": 1e-3}, target_update_every=0,
                               gradient_average='running')
     b.force.apply(e)
+    upd = bias.DeviceUpdater(b, e)                      # Adam kernel, fold + repack on the device: no host round trip
 
     def it():
         e.step(STRIDE)
         sw, sf, _ = e.moments()
-        b.update_from_moments(sw, sf)
-        b.force.apply(e)
+        upd.update(sw, sf)
     t = timed(it, iters)
     parts = dict(steps_ms=timed(lambda: e.step(STRIDE), 2) * 1e3, moments_ms=timed(lambda: e.moments(), 3) * 1e3)
-    emit(config="cfg4 Szabo-Berezhkovskii + NNBasis1D [48,48,48], Adam 1e-3, running-average gradients", walkers=n,
+    upd.close()
+    emit(config="cfg4 Szabo-Berezhkovskii + NNBasis1D [48,48,48], Adam 1e-3, running-average gradients (device-resident update)", walkers=n,
          md_steps_per_iteration=STRIDE, ms_per_iteration=t * 1e3, walker_steps_per_s=n * STRIDE / t, **parts)
     e.close()
 
