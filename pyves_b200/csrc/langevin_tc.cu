@@ -244,7 +244,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
   extern __shared__ unsigned char smem_raw[];
   TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int g = tid / kGT, tl = tid % kGT;
+  const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the compiler keeps it (and the descriptors built from it) in uniform registers
   constexpr uint32_t kCols = tmem_cols(G * WPT * 2 * KXP);
 
   if (warp == 0) {
@@ -567,7 +567,7 @@ langevin2d_tc_mlp_kernel(const StepArgs<float> A, const IntegratorParams<float> 
   extern __shared__ unsigned char smem_raw[];
   TcMlpSmem<H, G>& sm = *reinterpret_cast<TcMlpSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int g = tid / kGT, tl = tid % kGT;
+  const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the descriptors built from it stay in uniform registers
   constexpr uint32_t kCols = tmem_cols(G * 2 * H);
 
   if (warp == 0) {
@@ -770,7 +770,7 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
   extern __shared__ unsigned char smem_raw[];
   TcReluSmem<H, G>& sm = *reinterpret_cast<TcReluSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int g = tid / kGT, tl = tid % kGT;
+  const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the descriptors built from it stay in uniform registers
   constexpr uint32_t kCols = tmem_cols(G * 2 * H);
 
   if (warp == 0) {
