@@ -48,6 +48,11 @@ PV_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+PV_DEV bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 PV_DEV void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -245,6 +250,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
   TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the compiler keeps it (and the descriptors built from it) in uniform registers
+  const bool issuing_warp = __shfl_sync(0xffffffffu, (tid % kGT) >> 5, 0) == 0;
   constexpr uint32_t kCols = tmem_cols(G * WPT * 2 * KXP);
 
   if (warp == 0) {
@@ -384,18 +390,21 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
       const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // A'_k in [0, KXP), B_i in [KXP, 2 KXP)
-      if (tl == 0) {
+      if (issuing_warp) {                                            // warp-uniform branch; one elected lane issues
         mbar_wait(&sm.ready[g][k], parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dPhi = dsc[k][0], dPlo = dsc[k][1];
+        if (elect_one()) {
+          const uint64_t dPhi = dsc[k][0], dPlo = dsc[k][1];
 #pragma unroll
-        for (int kk = 0; kk < KYP / 16; ++kk) {                      // K = 16 per instruction: 32 bytes = +2 in 16-byte units
-          const uint64_t o = (uint64_t)(kk * 2);
-          umma_f16(tmem, dPhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
-          umma_f16(tmem, dPhi + o, dWlo + o, kIdesc, 1u);
-          umma_f16(tmem, dPlo + o, dWhi + o, kIdesc, 1u);
+          for (int kk = 0; kk < KYP / 16; ++kk) {                    // K = 16 per instruction: 32 bytes = +2 in 16-byte units
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_f16(tmem, dPhi + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+            umma_f16(tmem, dPhi + o, dWlo + o, kIdesc, 1u);
+            umma_f16(tmem, dPlo + o, dWhi + o, kIdesc, 1u);
+          }
+          umma_commit(&sm.bar[g][k]);
         }
-        umma_commit(&sm.bar[g][k]);
+        __syncwarp();
       }
       // ---- independent of the contraction: potential gradient and noise (overlaps the MMA round trip)
       float e = 0.f;
