@@ -183,6 +183,11 @@ template <int KYP, int G, int WPT> struct TcSmem {
 
 __host__ __device__ constexpr uint32_t tmem_cols(int need) { return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u; }
 
+// How the sets of 128 walkers are dealt to the CTAs of a launch (see the kernel and launch_tc)
+struct TcGrid {
+  int full, tail;
+};
+
 // Once per launch, one block: folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients, times kappa_row
 // kappa_column), their common power-of-two scale (max |W| into [2^12, 2^13): FP16 range; found on the device so that coefficients
 // handed over on the device need no host copy), and the stacked B operand image -- row r < KXP = WA[r][.], row KXP + i = WB[i][.],
@@ -242,9 +247,10 @@ __global__ void __launch_bounds__(1024, 1) tc_weight_prep_kernel(const Legendre2
 // FP32x2 chain).  The MMA round trip (store -> proxy fence -> barrier -> MMA -> commit -> TMEM load, ~1.3 us) is latency
 // that only independent groups can hide.
 template <int KXP, int KYP, int G, int WPT, bool INJECT>
-__global__ void __launch_bounds__(kGT* G, 1)
+__global__ void __launch_bounds__(kGT* G, (G <= 2 ? 3 : G == 3 ? 2 : 1))
 langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
-                     const Legendre2DSmemParams<float> BP, const RngKeys K, const unsigned char* __restrict__ wimg) {
+                     const Legendre2DSmemParams<float> BP, const RngKeys K, const unsigned char* __restrict__ wimg,
+                     const TcGrid GR) {
   using LY = TcLayout<KYP>;
   extern __shared__ unsigned char smem_raw[];
   TcSmem<KYP, G, WPT>& sm = *reinterpret_cast<TcSmem<KYP, G, WPT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -290,13 +296,20 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
     for (int q = 0; q < 2; ++q) dsc[k][q] = umma_desc_k_sw128(smem_u32(sm.a[g][k][0]) + LY::tile(q) * kTileBytes) + (uint64_t)LY::chunk0(q);
 
+  // sets of 128 walkers per CTA (TcGrid, filled by launch_tc): CTAs [0, full) advance G * WPT sets each -- whole rounds of the
+  // grid over the SMs --, CTAs [full, grid) `tail` sets: what is left over is spread evenly over the SMs, and the groups of such
+  // a CTA that have no set skip the time loop (a round of one-group CTAs is latency bound and costs about half a full round,
+  // instead of a whole round for a fraction of the SMs)
+  const int b = (int)blockIdx.x;
+  const int nsets = b < GR.full ? G * WPT : GR.tail;
+  const int64_t set0 = b < GR.full ? (int64_t)b * (G * WPT) : (int64_t)GR.full * (G * WPT) + (int64_t)(b - GR.full) * GR.tail;
   int64_t wk[WPT];
   bool live[WPT];
   float x[WPT], y[WPT], vx[WPT], vy[WPT], zodd_x[WPT], zodd_y[WPT];
 #pragma unroll
   for (int k = 0; k < WPT; ++k) {
-    const int64_t idx = (((int64_t)blockIdx.x * G + g) * WPT + k) * kGT + tl;
-    live[k] = idx < A.n;
+    const int64_t idx = (set0 + g * WPT + k) * kGT + tl;
+    live[k] = g * WPT + k < nsets && idx < A.n;
     wk[k] = live[k] ? idx : A.n - 1;
     x[k] = A.pos[wk[k]];
     y[k] = A.pos[A.n + wk[k]];
@@ -309,7 +322,8 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
   };
 
   uint32_t parity = 0;
-  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+  const int64_t nsteps = g * WPT < nsets ? A.nsteps : 0;           // a group without a set idles until the end of the kernel
+  for (int64_t ts = 0; ts < nsteps; ++ts) {
     const int64_t t = A.step0 + ts;
     float sx[WPT], gx[WPT], gy[WPT], zx[WPT], zy[WPT];
     bool inx[WPT], iny[WPT];
@@ -475,11 +489,44 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 #pragma unroll
       for (int k = 0; k < WPT; ++k) {
         const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
-        mbar_wait(&sm.bar[g][k], parity);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
         const float sx2 = sx[k] + sx[k];
         float pxm = 1.f, px = sx[k];
+        if constexpr (KXP <= 16) {
+          // the x recursion does not need the contraction: it runs in the shadow of the MMA round trip (16 registers), so that
+          // only the loads, the two row sums and the integrator are left on the group's critical path after the commit
+          float qx[KXP];
+#pragma unroll
+          for (int i = 0; i < KXP; ++i) {
+            if (i == 0) {
+              qx[i] = 1.f;
+            } else if (i == 1) {
+              qx[i] = px;
+            } else {
+              const float pn = fmaf(tab.d[i - 1] ? sx2 : sx[k], px, -(tab.cc[i - 1] * pxm));
+              pxm = px; px = pn;
+              qx[i] = pn;
+            }
+          }
+          mbar_wait(&sm.bar[g][k], parity);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          float av[16], bv[16];
+          tmem_ld16(tmem + tlane, av);
+          tmem_ld16(tmem + tlane + (uint32_t)KXP, bv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (q & 1) {
+              Gx1 = fmaf(qx[q], av[q], Gx1);
+              Gy1 = fmaf(qx[q], bv[q], Gy1);
+            } else {
+              Gx0 = fmaf(qx[q], av[q], Gx0);
+              Gy0 = fmaf(qx[q], bv[q], Gy0);
+            }
+          }
+        } else {
+        mbar_wait(&sm.bar[g][k], parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int i0 = 0; i0 < KXP; i0 += 16) {
           float av[16], bv[16];
@@ -507,6 +554,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
               Gy0 = fmaf(pi, bv[q], Gy0);
             }
           }
+        }
         }
         Gx[k] = Gx0 + Gx1;
         Gy[k] = Gy0 + Gy1;
@@ -546,10 +594,33 @@ cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I
   static_assert(G * WPT * 2 * KXP <= 512, "accumulators do not fit the TMEM columns of an SM");
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int64_t per_block = (int64_t)kGT * G * WPT;
-  const unsigned grid = (unsigned)((A.n + per_block - 1) / per_block);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  // One CTA (or `resident` CTAs) per SM and every CTA of a round takes the same time, so a launch costs whole rounds: full CTAs
+  // are dealt in whole rounds, the remainder goes into a last round of small CTAs spread evenly over the SMs.  (Letting the
+  // remainder ride as a fifth group on four-group CTAs was measured too: 5.27 against 5.09 ms, the larger block lowers the register cap.)
+  int resident = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kGT * G, smem);
+  if (resident < 1) resident = 1;
+  const int64_t sets = (A.n + kGT - 1) / kGT, cap = (int64_t)G * WPT, slots = (int64_t)n_sm * resident;
+  const int64_t full = (sets / (cap * slots)) * slots, rem = sets - full * cap;
+  int64_t tail_sets = 1, tail_ctas = 0;
+  if (rem > 0) {
+    tail_sets = (rem + slots - 1) / slots;
+    if (WPT > 1) tail_sets = (tail_sets + WPT - 1) / WPT * WPT;     // whole groups
+    if (tail_sets > cap) tail_sets = cap;
+    tail_ctas = (rem + tail_sets - 1) / tail_sets;
+  }
+  TcGrid GR;
+  GR.full = (int)full;
+  GR.tail = (int)tail_sets;
   tc_weight_prep_kernel<<<1, 1024, 0, st>>>(BP, KXP, img);
-  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K, img);
+  kern<<<(unsigned)(full + tail_ctas), kGT * G, smem, st>>>(A, I, PP, BP, K, img, GR);
   return cudaGetLastError();
 }
 
@@ -577,6 +648,7 @@ langevin2d_tc_mlp_kernel(const StepArgs<float> A, const IntegratorParams<float> 
   TcMlpSmem<H, G>& sm = *reinterpret_cast<TcMlpSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the descriptors built from it stay in uniform registers
+  const bool issuing_warp = __shfl_sync(0xffffffffu, (tid % kGT) >> 5, 0) == 0;
   constexpr uint32_t kCols = tmem_cols(G * 2 * H);
 
   if (warp == 0) {
@@ -673,20 +745,23 @@ langevin2d_tc_mlp_kernel(const StepArgs<float> A, const IntegratorParams<float> 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     mbar_arrive(&sm.ready[g]);
-    if (tl == 0) {
+    if (issuing_warp) {                                              // warp-uniform branch; one elected lane issues
       mbar_wait(&sm.ready[g], parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < H / 16; ++kk) {
-        const uint64_t o = (uint64_t)(kk * 2);
-        umma_f16(tmem, dsc[0] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
-        umma_f16(tmem, dsc[0] + o, dWlo + o, kIdesc, 1u);
-        umma_f16(tmem, dsc[1] + o, dWhi + o, kIdesc, 1u);
-        umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
-        umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWlo + o, kIdesc, 1u);
-        umma_f16(tmem + (uint32_t)H, dsc[3] + o, dWhi + o, kIdesc, 1u);
+        for (int kk = 0; kk < H / 16; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);
+          umma_f16(tmem, dsc[0] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+          umma_f16(tmem, dsc[0] + o, dWlo + o, kIdesc, 1u);
+          umma_f16(tmem, dsc[1] + o, dWhi + o, kIdesc, 1u);
+          umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+          umma_f16(tmem + (uint32_t)H, dsc[2] + o, dWlo + o, kIdesc, 1u);
+          umma_f16(tmem + (uint32_t)H, dsc[3] + o, dWhi + o, kIdesc, 1u);
+        }
+        umma_commit(&sm.bar[g]);
       }
-      umma_commit(&sm.bar[g]);
+      __syncwarp();
     }
     float gx = 0.f, gy = 0.f, e = 0.f;
     PotGeneric<float>::template grad<false>(PP, x, y, e, gx, gy);
@@ -780,6 +855,7 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
   TcReluSmem<H, G>& sm = *reinterpret_cast<TcReluSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = __shfl_sync(0xffffffffu, tid / kGT, 0), tl = tid % kGT;   // g through a shuffle: the descriptors built from it stay in uniform registers
+  const bool issuing_warp = __shfl_sync(0xffffffffu, (tid % kGT) >> 5, 0) == 0;
   constexpr uint32_t kCols = tmem_cols(G * 2 * H);
 
   if (warp == 0) {
@@ -871,16 +947,19 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     mbar_arrive(&sm.ready[g]);
-    if (tl == 0) {
+    if (issuing_warp) {                                              // warp-uniform branch; one elected lane issues
       mbar_wait(&sm.ready[g], parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < H / 16; ++kk) {
-        const uint64_t o = (uint64_t)(kk * 2);
-        umma_f16(tmem, dM + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
-        umma_f16(tmem, dM + o, dWlo + o, kIdesc, 1u);
+        for (int kk = 0; kk < H / 16; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);
+          umma_f16(tmem, dM + o, dWhi + o, kIdesc, kk > 0 ? 1u : 0u);
+          umma_f16(tmem, dM + o, dWlo + o, kIdesc, 1u);
+        }
+        umma_commit(&sm.bar[g]);
       }
-      umma_commit(&sm.bar[g]);
+      __syncwarp();
     }
     float gx = 0.f, gy = 0.f, e = 0.f;
     PotGeneric<float>::template grad<false>(PP, x, y, e, gx, gy);
@@ -981,20 +1060,24 @@ cudaError_t launch_tc_mlp(const StepArgs<float>& A, const IntegratorParams<float
 template <int KXP>
 cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                          const Legendre2DSmemParams<float>& BP, const RngKeys& K, unsigned char* img, cudaStream_t st) {
-  // groups per CTA: 64 KB of operand tiles per group at KYP = 64 (three fit), 32 / 16 KB below (four: 512 threads at <= 128 registers)
-  // groups per CTA x walker sets per group, measured on B200 (10^6 walkers, profiles/r02_tc_step_shapes.md): the kernels are bound by
-  // instruction issue and dependent FP32 chains, so more resident warps (6 groups at <= 80 registers) beat two walker sets per thread
+  // groups per CTA x walker sets per group, measured on B200 (10^6 walkers, profiles/r02_tc_step_shapes.md).  Since the MMA issue
+  // path became short (descriptors in uniform registers, one elected lane) four groups at <= 128 registers step fastest per walker
+  // at 16 x 16 (5.09 ms per 10^6 x 500 against 5.19 / 5.42 ms for five / six groups), three CTAs of two groups at 32 x 32; one
+  // walker set per thread beats two (packed FP32x2 recursions do not pay: FFMA2 holds the FMA pipe two cycles)
   static const int shape = getenv("PYVES_TC_SHAPE") ? atoi(getenv("PYVES_TC_SHAPE")) : 0;     // experiment knob: G * 10 + WPT
   if (BP.ky <= 16) {
     if (KXP == 16) {
       switch (shape) {
+        case 21: return launch_tc<16, 16, 2, 1>(A, I, PP, BP, K, img, st);
+        case 31: return launch_tc<16, 16, 3, 1>(A, I, PP, BP, K, img, st);
         case 41: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, img, st);
         case 42: return launch_tc<16, 16, 4, 2>(A, I, PP, BP, K, img, st);
         case 51: return launch_tc<16, 16, 5, 1>(A, I, PP, BP, K, img, st);
         case 71: return launch_tc<16, 16, 7, 1>(A, I, PP, BP, K, img, st);
         case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, img, st);
         case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, img, st);
-        default: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, img, st);
+        case 61: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, img, st);
+        default: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, img, st);
       }
     }
     return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
@@ -1002,17 +1085,21 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
   if (BP.ky <= 32) {
     if (KXP == 32) {
       switch (shape) {
+        case 21: return launch_tc<32, 32, 2, 1>(A, I, PP, BP, K, img, st);
+        case 31: return launch_tc<32, 32, 3, 1>(A, I, PP, BP, K, img, st);
         case 41: return launch_tc<32, 32, 4, 1>(A, I, PP, BP, K, img, st);
         case 51: return launch_tc<32, 32, 5, 1>(A, I, PP, BP, K, img, st);
         case 71: return launch_tc<32, 32, 7, 1>(A, I, PP, BP, K, img, st);
         case 81: return launch_tc<32, 32, 8, 1>(A, I, PP, BP, K, img, st);
         case 42: return launch_tc<32, 32, 4, 2>(A, I, PP, BP, K, img, st);
-        default: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, img, st);
+        case 61: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, img, st);
+        default: return launch_tc<32, 32, 2, 1>(A, I, PP, BP, K, img, st);
       }
     }
     return launch_tc<KXP, 32, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
   }
   if (KXP == 64 && shape == 31) return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, img, st);
+  if (KXP == 64 && shape == 21) return launch_tc<KXP, 64, 2, 1>(A, I, PP, BP, K, img, st);
   return launch_tc<KXP, 64, 4, 1>(A, I, PP, BP, K, img, st);
 }
 
@@ -1021,11 +1108,11 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
 size_t langevin2d_tc_scratch_bytes() { return 2 * kW2Bytes + 256; }
 
 // mirrors launch_tc_ky / launch_langevin2d_tc_mlp (default shapes)
-int langevin2d_tc_walkers_per_cta(int kx, int ky) {
+int langevin2d_tc_walkers_per_cta(int kx, int ky) {       // per SM: walkers per CTA x resident CTAs of the default shapes
   if (kx > 64 || ky > 64 || kx < 1 || ky < 1) return 0;
   if (ky > 32) return kGT * 4;
-  const bool square = (kx <= 16 && ky <= 16) || (kx > 16 && kx <= 32 && ky > 16);
-  if (square) return kGT * 6;
+  if (kx <= 16 && ky <= 16) return kGT * 4;               // <16,16,4,1>, one CTA per SM
+  if (kx > 16 && kx <= 32 && ky > 16) return kGT * 2 * 3; // <32,32,2,1>, three CTAs per SM
   return kGT * 4 * (kx <= 32 ? 2 : 1);
 }
 int langevin2d_tc_mlp_walkers_per_cta(int H, int act) {

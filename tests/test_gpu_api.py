@@ -426,8 +426,8 @@ def test_step_wave_walkers():
         return w
 
     leg = lambda k: (lambda e: e.set_bias_legendre2d(k - 1, k - 1, (-2.5, 2.5, -2, 2), np.zeros(k * k)))
-    assert wave("fp32", leg(16)) == n_sm * 768 and wave("fp32", leg(32)) == n_sm * 768 and wave("fp32", leg(64)) == n_sm * 512
-    assert wave("fp32", leg(8)) == 0 and wave("fp32", leg(8), 7) == n_sm * 768      # static 8 x 8 double-well kernel unless forced
+    assert wave("fp32", leg(16)) == n_sm * 512 and wave("fp32", leg(32)) == n_sm * 768 and wave("fp32", leg(64)) == n_sm * 512
+    assert wave("fp32", leg(8)) == 0 and wave("fp32", leg(8), 7) == n_sm * 512      # static 8 x 8 double-well kernel unless forced
     assert wave("fp32", leg(16), 6) == 0 and wave("fp64", leg(16)) == 0
     assert wave("fp32", lambda e: e.set_bias_legendre1d(0, 5, -2.5, 2.5, np.zeros(6))) == 0
     torch.manual_seed(0)
