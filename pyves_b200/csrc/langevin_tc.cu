@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) tc_weight_prep_kernel(const Legendre2
 // WPT walker sets per group (thread = one walker of each set; with WPT = 2 the two recursions of a thread run as one packed
 // FP32x2 chain).  The MMA round trip (store -> proxy fence -> barrier -> MMA -> commit -> TMEM load, ~1.3 us) is latency
 // that only independent groups can hide.
-template <int KXP, int KYP, int G, int WPT, bool INJECT>
+template <int KXP, int KYP, int G, int WPT, bool INJECT, class POT>
 __global__ void __launch_bounds__(kGT* G, (G <= 2 ? 3 : G == 3 ? 2 : 1))
 langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
                      const Legendre2DSmemParams<float> BP, const RngKeys K, const unsigned char* __restrict__ wimg,
@@ -322,6 +322,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
   };
 
   uint32_t parity = 0;
+  const uint32_t tmem_base = sm.tmem_base;                         // once: inside the loop it would be a generic load per step
   const int64_t nsteps = g * WPT < nsets ? A.nsteps : 0;           // a group without a set idles until the end of the kernel
   for (int64_t ts = 0; ts < nsteps; ++ts) {
     const int64_t t = A.step0 + ts;
@@ -403,7 +404,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     for (int k = 0; k < WPT; ++k) mbar_arrive(&sm.ready[g][k]);
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
-      const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // A'_k in [0, KXP), B_i in [KXP, 2 KXP)
+      const uint32_t tmem = tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);   // A'_k in [0, KXP), B_i in [KXP, 2 KXP)
       if (issuing_warp) {                                            // warp-uniform branch; one elected lane issues
         mbar_wait(&sm.ready[g][k], parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -423,7 +424,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
       // ---- independent of the contraction: potential gradient and noise (overlaps the MMA round trip)
       float e = 0.f;
       gx[k] = gy[k] = 0.f;
-      PotGeneric<float>::template grad<false>(PP, x[k], y[k], e, gx[k], gy[k]);
+      POT::template grad<false>(PP, x[k], y[k], e, gx[k], gy[k]);
       if (INJECT) {
         zx[k] = A.noise[(ts * 2) * A.n + wk[k]];
         zy[k] = A.noise[(ts * 2 + 1) * A.n + wk[k]];
@@ -450,7 +451,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     float Gx[WPT], Gy[WPT];
     if constexpr (WPT == 2) {
       using Q = Pair<float>;
-      const uint32_t tmem0 = sm.tmem_base + (uint32_t)((g * 2) * 2 * KXP) + tlane, tmem1 = tmem0 + (uint32_t)(2 * KXP);
+      const uint32_t tmem0 = tmem_base + (uint32_t)((g * 2) * 2 * KXP) + tlane, tmem1 = tmem0 + (uint32_t)(2 * KXP);
       mbar_wait(&sm.bar[g][0], parity);
       mbar_wait(&sm.bar[g][1], parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -488,7 +489,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
     } else {
 #pragma unroll
       for (int k = 0; k < WPT; ++k) {
-        const uint32_t tmem = sm.tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
+        const uint32_t tmem = tmem_base + (uint32_t)((g * WPT + k) * 2 * KXP);
         float Gx0 = 0.f, Gx1 = 0.f, Gy0 = 0.f, Gy1 = 0.f;
         const float sx2 = sx[k] + sx[k];
         float pxm = 1.f, px = sx[k];
@@ -514,8 +515,10 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
           tmem_ld16(tmem + tlane, av);
           tmem_ld16(tmem + tlane + (uint32_t)KXP, bv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          Gx0 = av[0];                                               // q_0 = 1
+          Gy0 = bv[0];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
+          for (int q = 1; q < 16; ++q) {
             if (q & 1) {
               Gx1 = fmaf(qx[q], av[q], Gx1);
               Gy1 = fmaf(qx[q], bv[q], Gy1);
@@ -585,10 +588,10 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
 }
 
-template <int KXP, int KYP, int G, int WPT>
+template <int KXP, int KYP, int G, int WPT, class POT = PotGeneric<float>>
 cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                       const Legendre2DSmemParams<float>& BP, const RngKeys& K, unsigned char* img, cudaStream_t st) {
-  auto kern = A.noise != nullptr ? langevin2d_tc_kernel<KXP, KYP, G, WPT, true> : langevin2d_tc_kernel<KXP, KYP, G, WPT, false>;
+  auto kern = A.noise != nullptr ? langevin2d_tc_kernel<KXP, KYP, G, WPT, true, POT> : langevin2d_tc_kernel<KXP, KYP, G, WPT, false, POT>;
   const size_t smem = sizeof(TcSmem<KYP, G, WPT>) + 1024;
   static_assert(sizeof(TcSmem<KYP, G, WPT>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
   static_assert(G * WPT * 2 * KXP <= 512, "accumulators do not fit the TMEM columns of an SM");
@@ -1077,7 +1080,10 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
         case 81: return launch_tc<16, 16, 8, 1>(A, I, PP, BP, K, img, st);
         case 62: return launch_tc<16, 16, 6, 2>(A, I, PP, BP, K, img, st);
         case 61: return launch_tc<16, 16, 6, 1>(A, I, PP, BP, K, img, st);
-        default: return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, img, st);
+        default:
+          // the double well (every BASELINE 2D configuration) without the runtime switch over the potentials
+          if (PP.kind == PYVES_POT_DOUBLE_WELL_2D) return launch_tc<16, 16, 4, 1, PotDoubleWell2D<float>>(A, I, PP, BP, K, img, st);
+          return launch_tc<16, 16, 4, 1>(A, I, PP, BP, K, img, st);
       }
     }
     return launch_tc<KXP, 16, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
@@ -1093,13 +1099,16 @@ cudaError_t launch_tc_ky(const StepArgs<float>& A, const IntegratorParams<float>
         case 81: return launch_tc<32, 32, 8, 1>(A, I, PP, BP, K, img, st);
         case 42: return launch_tc<32, 32, 4, 2>(A, I, PP, BP, K, img, st);
         case 61: return launch_tc<32, 32, 6, 1>(A, I, PP, BP, K, img, st);
-        default: return launch_tc<32, 32, 2, 1>(A, I, PP, BP, K, img, st);
+        default:
+          if (PP.kind == PYVES_POT_DOUBLE_WELL_2D) return launch_tc<32, 32, 2, 1, PotDoubleWell2D<float>>(A, I, PP, BP, K, img, st);
+          return launch_tc<32, 32, 2, 1>(A, I, PP, BP, K, img, st);
       }
     }
     return launch_tc<KXP, 32, 4, (KXP <= 32 ? 2 : 1)>(A, I, PP, BP, K, img, st);
   }
   if (KXP == 64 && shape == 31) return launch_tc<KXP, 64, 3, 1>(A, I, PP, BP, K, img, st);
   if (KXP == 64 && shape == 21) return launch_tc<KXP, 64, 2, 1>(A, I, PP, BP, K, img, st);
+  if (KXP == 64 && PP.kind == PYVES_POT_DOUBLE_WELL_2D) return launch_tc<KXP, 64, 4, 1, PotDoubleWell2D<float>>(A, I, PP, BP, K, img, st);
   return launch_tc<KXP, 64, 4, 1>(A, I, PP, BP, K, img, st);
 }
 
