@@ -188,6 +188,32 @@ struct TcGrid {
   int full, tail;
 };
 
+// One CTA (or `resident` CTAs) per SM and every CTA of a round takes the same time, so a launch costs whole rounds: full CTAs
+// (cap sets each) are dealt in whole rounds, the remainder goes into a last round of small CTAs spread evenly over the SMs.
+// Returns the grid size.
+inline unsigned tc_deal_sets(int64_t n, int cap, int wpt, int resident, TcGrid& GR) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  if (resident < 1) resident = 1;
+  const int64_t sets = (n + kGT - 1) / kGT, slots = (int64_t)n_sm * resident;
+  const int64_t full = (sets / (cap * slots)) * slots, rem = sets - full * cap;
+  int64_t tail_sets = 1, tail_ctas = 0;
+  if (rem > 0) {
+    tail_sets = (rem + slots - 1) / slots;
+    if (wpt > 1) tail_sets = (tail_sets + wpt - 1) / wpt * wpt;     // whole groups
+    if (tail_sets > cap) tail_sets = cap;
+    tail_ctas = (rem + tail_sets - 1) / tail_sets;
+  }
+  GR.full = (int)full;
+  GR.tail = (int)tail_sets;
+  return (unsigned)(full + tail_ctas);
+}
+
 // Once per launch, one block: folded matrices WA[k][j], WB[i][k] (FP64 sums of the FP32 coefficients, times kappa_row
 // kappa_column), their common power-of-two scale (max |W| into [2^12, 2^13): FP16 range; found on the device so that coefficients
 // handed over on the device need no host copy), and the stacked B operand image -- row r < KXP = WA[r][.], row KXP + i = WB[i][.],
@@ -597,33 +623,14 @@ cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I
   static_assert(G * WPT * 2 * KXP <= 512, "accumulators do not fit the TMEM columns of an SM");
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
-  // One CTA (or `resident` CTAs) per SM and every CTA of a round takes the same time, so a launch costs whole rounds: full CTAs
-  // are dealt in whole rounds, the remainder goes into a last round of small CTAs spread evenly over the SMs.  (Letting the
-  // remainder ride as a fifth group on four-group CTAs was measured too: 5.27 against 5.09 ms, the larger block lowers the register cap.)
+  // (letting the remainder ride as a fifth group on four-group CTAs was measured too: 5.27 against 5.09 ms, the larger block
+  // lowers the register cap)
   int resident = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kGT * G, smem);
-  if (resident < 1) resident = 1;
-  const int64_t sets = (A.n + kGT - 1) / kGT, cap = (int64_t)G * WPT, slots = (int64_t)n_sm * resident;
-  const int64_t full = (sets / (cap * slots)) * slots, rem = sets - full * cap;
-  int64_t tail_sets = 1, tail_ctas = 0;
-  if (rem > 0) {
-    tail_sets = (rem + slots - 1) / slots;
-    if (WPT > 1) tail_sets = (tail_sets + WPT - 1) / WPT * WPT;     // whole groups
-    if (tail_sets > cap) tail_sets = cap;
-    tail_ctas = (rem + tail_sets - 1) / tail_sets;
-  }
   TcGrid GR;
-  GR.full = (int)full;
-  GR.tail = (int)tail_sets;
+  const unsigned grid = tc_deal_sets(A.n, G * WPT, WPT, resident, GR);
   tc_weight_prep_kernel<<<1, 1024, 0, st>>>(BP, KXP, img);
-  kern<<<(unsigned)(full + tail_ctas), kGT * G, smem, st>>>(A, I, PP, BP, K, img, GR);
+  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K, img, GR);
   return cudaGetLastError();
 }
 
@@ -850,10 +857,10 @@ template <int H, int G> struct TcReluSmem {
   uint32_t tmem_base;
 };
 
-template <int H, int G, bool INJECT>
+template <int H, int G, bool INJECT, class POT>
 __global__ void __launch_bounds__(kGT* G, 1)
 langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float> I, const PotParams<float> PP,
-                          const MlpParams<float> BP, const RngKeys K) {
+                          const MlpParams<float> BP, const RngKeys K, const TcGrid GR) {
   extern __shared__ unsigned char smem_raw[];
   TcReluSmem<H, G>& sm = *reinterpret_cast<TcReluSmem<H, G>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -921,13 +928,18 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
   const float* wout = sm.vec + 2 * H;
   const float* b2 = sm.vec + 3 * H;
 
-  const int64_t idx = ((int64_t)blockIdx.x * G + g) * kGT + tl;
-  const bool live = idx < A.n;
+  // sets of 128 walkers per CTA as in langevin2d_tc_kernel: full CTAs in whole rounds, the remainder in small CTAs
+  const int bI = (int)blockIdx.x;
+  const int nsets = bI < GR.full ? G : GR.tail;
+  const int64_t set0 = bI < GR.full ? (int64_t)bI * G : (int64_t)GR.full * G + (int64_t)(bI - GR.full) * GR.tail;
+  const int64_t idx = (set0 + g) * kGT + tl;
+  const bool live = g < nsets && idx < A.n;
   const int64_t w = live ? idx : A.n - 1;
   float x = A.pos[w], y = A.pos[A.n + w], vx = A.vel[w], vy = A.vel[A.n + w];
   float zodd_x = 0.f, zodd_y = 0.f;
   uint32_t parity = 0;
-  for (int64_t ts = 0; ts < A.nsteps; ++ts) {
+  const int64_t nsteps = g < nsets ? A.nsteps : 0;             // a group without a set idles until the end of the kernel
+  for (int64_t ts = 0; ts < nsteps; ++ts) {
     const int64_t t = A.step0 + ts;
     const float sc = ((BP.axis ? y : x) - BP.lo) * BP.inv_range;
     // ---- mask row m_i = [u_i s + c_i > 0], i < H, as FP16 0 / 1
@@ -965,7 +977,7 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
       __syncwarp();
     }
     float gx = 0.f, gy = 0.f, e = 0.f;
-    PotGeneric<float>::template grad<false>(PP, x, y, e, gx, gy);
+    POT::template grad<false>(PP, x, y, e, gx, gy);
     float zx, zy;
     if (INJECT) {
       zx = A.noise[(ts * 2) * A.n + w];
@@ -1032,18 +1044,28 @@ langevin2d_tc_relu_kernel(const StepArgs<float> A, const IntegratorParams<float>
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kCols));
 }
 
-template <int H, int G>
-cudaError_t launch_tc_relu(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
-                           const RngKeys& K, cudaStream_t st) {
-  auto kern = A.noise != nullptr ? langevin2d_tc_relu_kernel<H, G, true> : langevin2d_tc_relu_kernel<H, G, false>;
+template <int H, int G, class POT>
+cudaError_t launch_tc_relu_pot(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
+                               const RngKeys& K, cudaStream_t st) {
+  auto kern = A.noise != nullptr ? langevin2d_tc_relu_kernel<H, G, true, POT> : langevin2d_tc_relu_kernel<H, G, false, POT>;
   const size_t smem = sizeof(TcReluSmem<H, G>) + 1024;
   static_assert(sizeof(TcReluSmem<H, G>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
   static_assert(G * 2 * H <= 512, "accumulators do not fit the TMEM columns of an SM");
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int64_t per_block = (int64_t)kGT * G;
-  kern<<<(unsigned)((A.n + per_block - 1) / per_block), kGT * G, smem, st>>>(A, I, PP, BP, K);
+  int resident = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kGT * G, smem);
+  TcGrid GR;
+  const unsigned grid = tc_deal_sets(A.n, G, 1, resident, GR);
+  kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K, GR);
   return cudaGetLastError();
+}
+template <int H, int G>
+cudaError_t launch_tc_relu(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP, const MlpParams<float>& BP,
+                           const RngKeys& K, cudaStream_t st) {
+  // the reference's NN example (examples/szabo_berezhkovskii) without the runtime switch over the potentials
+  if (PP.kind == PYVES_POT_SZABO_BEREZHKOVSKII) return launch_tc_relu_pot<H, G, PotSzaboBerezhkovskii<float>>(A, I, PP, BP, K, st);
+  return launch_tc_relu_pot<H, G, PotGeneric<float>>(A, I, PP, BP, K, st);
 }
 
 template <int H, int ACT>
