@@ -59,11 +59,12 @@ def parse_args():
     ap.add_argument("--update", default="device", choices=["device", "host"],
                     help="coefficient update of the resident-state loop: 'device' = optimiser, target refresh and coefficient "
                          "hand-over on the GPU (DeviceUpdater), 'host' = numpy optimiser + re-upload (VESBias_Ensemble)")
-    ap.add_argument("--e2e-chunks", type=int, default=8,
+    ap.add_argument("--e2e-chunks", type=int, default=16,
                     help="e2e with --update device: the ensemble is cut into about this many handles on their own streams (at multiples "
                          "of a wave of the step kernel, pyves_step_wave_walkers) so that the host<->device copies of one chunk overlap the "
-                         "step kernel of another (1 = one handle, serial copies).  Measured: 1 GPU 5 chunks 7.60e10 / 9 chunks 7.54e10; "
-                         "8 GPUs 5.30e11 / 5.56e11 -- the exposed head and tail copies cost more when eight processes share the host")
+                         "step kernel of another (1 = one handle, serial copies).  Measured at 1 GPU with the 4.8 ms step kernel: 3 / 5 / 7 / 14 "
+                         "chunks 9.29 / 9.28 / 9.24 / 9.47e10; at 8 GPUs more chunks help more (the exposed head and tail copies cost more "
+                         "when eight processes share the host)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--comm", default="native", choices=["native", "torch"],
