@@ -167,6 +167,12 @@ __global__ void __launch_bounds__(kMomThreads) moments1_tiled_kernel(const RowSo
   T* fa = reinterpret_cast<T*>(smem_raw);        // [R][kap]
   T* fb = fa + R * kap;                          // [R][kbp]
   __shared__ double wred[kMomThreads / 32];
+  __shared__ T rec_a[64], rec_b[64];                 // P_{n+1} = a_n s P_n - b_n P_{n-1}
+  if (threadIdx.x < 64) {
+    rec_a[threadIdx.x] = T(2 * threadIdx.x + 1) / T(threadIdx.x + 1);
+    rec_b[threadIdx.x] = T(threadIdx.x) / T(threadIdx.x + 1);
+  }
+  __syncthreads();
   const int ka4 = (B.ka + 3) >> 2, kb4 = (B.kb + 3) >> 2;
   const int nt = ka4 * kb4, RG = kMomThreads / nt;
   const int tile_id = threadIdx.x % nt, rg = threadIdx.x / nt;
@@ -208,8 +214,13 @@ __global__ void __launch_bounds__(kMomThreads) moments1_tiled_kernel(const RowSo
           } else if (n == 1) {
             val = s;
           } else {
-            const T fn = T(n - 1);
-            const T pn = ((T(2) * fn + T(1)) * s * p - fn * pm) / (fn + T(1));   // the arithmetic of row_factors
+            T pn;
+            if (sizeof(T) == 8) {
+              const T fn = T(n - 1);
+              pn = ((T(2) * fn + T(1)) * s * p - fn * pm) / (fn + T(1));         // the arithmetic of row_factors (FP64 parity)
+            } else {
+              pn = rec_a[n - 1] * s * p - rec_b[n - 1] * pm;                     // FP32: tabulated coefficients, no division
+            }
             pm = p;
             p = pn;
             val = pn;
@@ -605,6 +616,7 @@ template <> struct TcDispatch<float> {
 };
 
 static bool g_no_tc = false;
+static int g_tiled_min_k = 64;       // below: moments1_kernel (few 4 x 4 tiles per block)
 static bool g_tiled_first = true;    // experiment knob (pyves_set_tuning 96 / 95): register-tiled first moments of large 2D bases
 void set_tiled_first_moments(bool v) { g_tiled_first = v; }
 bool no_tensor_cores() { return g_no_tc; }
@@ -641,7 +653,7 @@ cudaError_t launch_moments_basis(const RowSource<T>& S, const BasisParams<T>& B,
       return cudaGetLastError();
     }
   }
-  if (B.kind == PYVES_BIAS_LEGENDRE_2D && B.kb > 1 && K > 256 && K <= 4096 && g_tiled_first) {   // large product bases: register-tiled
+  if (B.kind == PYVES_BIAS_LEGENDRE_2D && B.kb > 1 && B.ka <= 64 && B.kb <= 64 && K >= g_tiled_min_k && K <= 4096 && g_tiled_first) {   // product bases: register-tiled
     constexpr int R = kTileRows;
     const int64_t tiles = (S.n + R - 1) / R;
     const int G = (int)(tiles < kMaxBlocks ? tiles : kMaxBlocks);

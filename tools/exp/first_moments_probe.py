@@ -28,7 +28,7 @@ def t_ms(fn, reps=5):
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 for prec in ("fp32", "fp64"):
-    for k in (16, 20, 32, 48, 64):
+    for k in (8, 12, 16, 20, 32, 48, 64):
         e = _lib.Ensemble(n, dims=2, seed=1, precision=prec)
         e.set_integrator(1.0, 2.494, 20.0, 0.01)
         e.set_potential(_lib.POT_DOUBLE_WELL_2D)
