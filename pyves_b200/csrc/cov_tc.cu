@@ -68,6 +68,11 @@ PV_DEV void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+PV_DEV bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 PV_DEV void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -200,6 +205,7 @@ cov_f16_kernel(const RowSource<float> S, const BasisParams<float> B, int T256, i
   // table is double buffered (no third barrier), so the tensor core works on stage s while the warps already build the
   // next tables and generate stage s ^ 1.
   constexpr int kIssuer = 192;
+  const bool issuing_warp = __shfl_sync(0xffffffffu, tid >> 5, 0) == (kIssuer >> 5);
   const int rr = tid & (kSuperRows - 1), ax = tid >> 7;
   float px = 0.f, py = 0.f, pw = 1.f;
   bool plive = false;
@@ -289,7 +295,7 @@ cov_f16_kernel(const RowSource<float> S, const BasisParams<float> B, int T256, i
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncthreads();
-      if (tid == kIssuer) {
+      if (issuing_warp && elect_one()) {                            // warp-uniform branch, one elected lane: descriptors stay in uniform registers
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_u32(sm.tile[s]);
         const int nsub = diag ? 2 : 1;
@@ -316,7 +322,7 @@ cov_f16_kernel(const RowSource<float> S, const BasisParams<float> B, int T256, i
   }
   // ---- drain: all MMAs of the segment done?  (the issuer's commit covers every MMA it queued before)
   if (seg_trip > 0) {
-    if (tid == kIssuer) umma_commit(&sm.done_bar);
+    if (issuing_warp && elect_one()) umma_commit(&sm.done_bar);
     mbar_wait(&sm.done_bar, (uint32_t)(seg & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
