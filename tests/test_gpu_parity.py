@@ -299,6 +299,40 @@ def test_tensor_core_step_force_vs_oracle():
             e.close()
 
 
+@pytest.mark.parametrize("shape", [(15, 15), (31, 31), (63, 63), (16, 2), "mlp48"], ids=["16x16", "32x32", "64x64", "17x3_two_sets_per_thread", "relu_mlp48"])
+def test_tensor_core_step_every_walker_once(shape):
+    """How the tensor-core launch deals the sets of 128 walkers to its CTAs (whole rounds of full CTAs, the remainder in small CTAs
+    spread over the SMs, the MLP kernel likewise): for ensemble sizes around one and two rounds of the grid, with ragged ends, a few
+    RNG-driven steps (Philox keyed on the global walker id) must move EVERY walker exactly as the CUDA-core kernel does -- a set
+    skipped, done twice or mapped to the wrong ids would show as walkers that did not move or moved with another walker's noise."""
+    rng = np.random.default_rng(5)
+    if shape == "mlp48":
+        spec = rng_spec("mlp", rng, sizes=[48, 48, 48])
+    else:
+        spec = rng_spec("leg2d", rng, deg_x=shape[0], deg_y=shape[1], scale=1.0)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    probe = biasspec.make_ensemble(128, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+    wave = probe.wave_walkers()
+    probe.close()
+    assert wave > 0 and wave % (128 * n_sm) == 0
+    for n in (1, 127, 129, wave - 128 - 1, wave, wave + 1, wave + 300, 2 * wave + 128 * n_sm + 77):
+        x0 = np.stack([rng.uniform(-1.6, 1.6, n), rng.uniform(-1.0, 1.0, n)], 1)
+        v0 = np.zeros((n, 2))
+        out = []
+        for variant in (-1, 6):
+            e = biasspec.make_ensemble(n, 2, 123, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+            e.set_walker_offset(10 ** 9)
+            e.set_tuning(variant)
+            e.set_state(torch.tensor(x0.T.copy(), dtype=torch.float32, device=DEV), torch.tensor(v0.T.copy(), dtype=torch.float32, device=DEV))
+            e.step(3)
+            e.step(2)
+            out.append(e.get_state(host=True))
+            e.close()
+        (xa, va), (xb, vb) = out
+        assert np.all(np.abs(xa.T - x0) > 0), (shape, n)                # every walker moved
+        assert np.max(np.abs(xa - xb)) < 2e-5 and np.max(np.abs(va - vb)) < 2e-3, (shape, n, np.max(np.abs(xa - xb)))
+
+
 @pytest.mark.parametrize("deg", [7, 15, 31, 63], ids=["8x8_cuda_cores", "16x16_tensor_cores", "32x32_tensor_cores", "64x64_tensor_cores"])
 def test_trajectory_parity_philox_and_chunking(deg):
     """RNG-driven run against the oracle's Philox stream; launches of any length give identical bits."""
