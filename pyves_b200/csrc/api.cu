@@ -63,6 +63,11 @@ struct pyves_ctx {
   size_t mlp_np = 0;                // number of parameters (torch parameters() order)
   void* mlp_theta_dev = nullptr;
   void* mlp_packed_dev = nullptr;
+  void* pwl_brk = nullptr;         // ReLU NNBasis1D compiled to a piecewise-constant dV/ds (BiasPwl1D): breakpoints, slopes, count
+  void* pwl_slope = nullptr;
+  int* pwl_count = nullptr;
+  int pwl_cap = 0;
+  bool pwl_valid = false;
   void* tc_img = nullptr;          // operand image of the tensor-core Legendre step kernel (langevin2d_tc_scratch_bytes())
   int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
   int mlp_width = 0, mlp_linear = 0;
@@ -239,6 +244,47 @@ template <typename T, int KX, int KY> Legendre2DStaticTCParams<T, KX, KY> l2_sta
   P.ihx = S.ihx;
   P.cy = S.cy;
   P.ihy = S.ihy;
+  return P;
+}
+
+// ReLU nets with two or three hidden layers: compile the packed parameters into the piecewise-constant dV/ds of BiasPwl1D
+// (stream ordered after the pack / upload that precedes it).  Anything else leaves pwl_valid false.
+int refresh_pwl(pyves_ctx* h, cudaStream_t st) {
+  h->pwl_valid = false;
+  if (h->mlp_act != PYVES_ACT_RELU || h->mlp_linear || h->mlp_H < 0) return PYVES_OK;
+  const int n1 = h->mlp_H > 0 ? h->mlp_H : h->mlp_width;
+  if (n1 < 1 || n1 > 128) return PYVES_OK;
+  const int cap = mlp_pwl_capacity(h->mlp_H, h->mlp_width);
+  if (cap > h->pwl_cap) {
+    if (h->pwl_brk) cudaFree(h->pwl_brk);
+    if (h->pwl_slope) cudaFree(h->pwl_slope);
+    h->pwl_brk = h->pwl_slope = nullptr;
+    CU(cudaMalloc(&h->pwl_brk, (size_t)cap * h->esz));
+    CU(cudaMalloc(&h->pwl_slope, (size_t)(cap + 1) * h->esz));
+    h->pwl_cap = cap;
+  }
+  if (!h->pwl_count) CU(cudaMalloc(reinterpret_cast<void**>(&h->pwl_count), sizeof(int)));
+  if (h->prec == PYVES_F64) {
+    CU(launch_mlp_pwl_build<double>(static_cast<const double*>(h->mlp_packed_dev), h->mlp_H, h->mlp_width, static_cast<double*>(h->pwl_brk),
+                                    static_cast<double*>(h->pwl_slope), h->pwl_count, st));
+  } else {
+    CU(launch_mlp_pwl_build<float>(static_cast<const float*>(h->mlp_packed_dev), h->mlp_H, h->mlp_width, static_cast<float*>(h->pwl_brk),
+                                   static_cast<float*>(h->pwl_slope), h->pwl_count, st));
+  }
+  g_launches++;
+  h->pwl_valid = true;
+  return PYVES_OK;
+}
+
+template <typename T> PwlParams<T> pwl_params(const pyves_ctx* h) {
+  PwlParams<T> P;
+  P.axis = h->mlp_axis;
+  P.lo = (T)h->mlp_lo;
+  P.inv_range = (T)(1.0 / (h->mlp_hi - h->mlp_lo));
+  P.cap = h->pwl_cap;
+  P.brk = static_cast<const T*>(h->pwl_brk);
+  P.slope = static_cast<const T*>(h->pwl_slope);
+  P.count = h->pwl_count;
   return P;
 }
 
@@ -527,6 +573,12 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       const MlpParams<T> BP = mlp_params<T>(h);
       const bool relu = h->mlp_act == PYVES_ACT_RELU;
       const bool sb = pk == PYVES_POT_SZABO_BEREZHKOVSKII && relu;
+      // ReLU nets with two / three hidden layers, FP32 default: dV/ds is piecewise constant in the one input -- a binary search
+      // (variant 8 forces it for FP64 handles too; 6 / 7 keep the CUDA-core / tensor-core evaluation of the network)
+      if (h->pwl_valid && ((h->variant == -1 && sizeof(T) == 4) || h->variant == 8)) {
+        if (pk == PYVES_POT_SZABO_BEREZHKOVSKII) return run_fast<T, SB, BiasPwl1D<T>, 2, 1>(h, A, pwl_params<T>(h), st);
+        return run_fast<T, GP, BiasPwl1D<T>, 2, 1>(h, A, pwl_params<T>(h), st);
+      }
       if (h->mlp_H > 0 && (h->variant == -1 || h->variant == 7)) {      // one H x H layer: on the tensor cores (variant 6: CUDA cores)
         const int rc = run_tc_mlp<T>(h, A, st);
         if (rc <= 0) return rc;
@@ -690,7 +742,7 @@ int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
   void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->l1_wt_dev, h->l1_w64_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
-                  h->scratch, h->stage, h->fail_dev, h->tc_img};
+                  h->scratch, h->stage, h->fail_dev, h->tc_img, h->pwl_brk, h->pwl_slope, h->pwl_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;
@@ -798,7 +850,7 @@ int pyves_step_wave_walkers(pyves_t* h, int64_t* walkers) {
     const int kx = h->l2_dx + 1, ky = h->l2_dy + 1;
     const bool tc = h->variant == 7 || (h->variant == -1 && !(kx == 8 && ky == 8 && h->pot.kind == PYVES_POT_DOUBLE_WELL_2D));
     if (tc) per_cta = langevin2d_tc_walkers_per_cta(kx, ky);
-  } else if (h->bias_kind == PYVES_BIAS_MLP_1D && h->mlp_H > 0 && (h->variant == -1 || h->variant == 7)) {
+  } else if (h->bias_kind == PYVES_BIAS_MLP_1D && h->mlp_H > 0 && (h->variant == 7 || (h->variant == -1 && !h->pwl_valid))) {
     per_cta = langevin2d_tc_mlp_walkers_per_cta(h->mlp_H, h->mlp_act);
   }
   if (per_cta > 0) {
@@ -1076,7 +1128,7 @@ int pyves_set_bias_mlp(pyves_t* h, int axis, double lo, double hi, int n_hidden,
   rc = upload(h, &h->mlp_packed_dev, packed.data(), packed.size(), st);
   if (rc) return rc;
   h->bias_kind = PYVES_BIAS_MLP_1D;
-  return PYVES_OK;
+  return refresh_pwl(h, st);
 }
 
 int pyves_set_bias_mlp_device(pyves_t* h, int axis, double lo, double hi, int n_hidden, const int* sizes, int act, const double* theta_dev,
@@ -1153,7 +1205,7 @@ int pyves_set_bias_mlp_device(pyves_t* h, int axis, double lo, double hi, int n_
   h->mlp_bout = 0;
   h->mlp_u0 = 0;
   h->bias_kind = PYVES_BIAS_MLP_1D;
-  return PYVES_OK;
+  return refresh_pwl(h, st);
 }
 
 int pyves_optimizer_step(int device, int kind, int64_t P, const double* sum_w, const double* sum_wf, const double* f_target, int grad_average,

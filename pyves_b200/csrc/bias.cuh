@@ -552,6 +552,47 @@ template <typename T, int H, int ACT> struct BiasMlp {
 };
 
 // ------------------------------------------------------------------------------------------------
+// ReLU NNBasis1D as what it is: a piecewise-LINEAR function of its one input.  Every unit of the folded first layer switches at
+// s = -c_i / u_i; between two such points the second layer's pre-activations are linear in s and switch at most once each; so
+// dV/ds is piecewise constant on at most (H + 1)^2 pieces.  mlp_pwl_build_kernel (misc_kernels.cu) compiles the parameters into
+// the sorted breakpoints and the slope of every piece (FP64 sums, exact up to the rounding of the breakpoints) whenever they
+// change; the step kernel's bias force is then ONE binary search in shared memory -- no matmul, no activations, no tensor core.
+// Step kernels only (forces); energies and parameter gradients go through the network itself (BiasMlp, moments_mlp2_kernel).
+template <typename T> struct PwlParams {
+  int axis;
+  T lo, inv_range;
+  int cap;             // capacity of brk (slope has cap + 1 entries)
+  const T* brk;        // device: breakpoints in the scaled coordinate, ascending
+  const T* slope;      // device: dV/ds on the pieces: slope[k] for brk[k-1] < s <= brk[k]
+  const int* count;    // device: number of breakpoints
+};
+
+template <typename T> struct BiasPwl1D {
+  using Params = PwlParams<T>;
+  static size_t smem_bytes(const Params& P) { return (size_t)(2 * P.cap + 1) * sizeof(T) + 16; }
+  static PV_DEV void stage(const Params& P, void* smem) {
+    T* d = reinterpret_cast<T*>(smem);
+    const int n = *P.count;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = P.brk[i];
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) d[P.cap + i] = P.slope[i];
+  }
+  template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
+    const T s = ((P.axis ? y : x) - P.lo) * P.inv_range;
+    const T* brk = reinterpret_cast<const T*>(smem);
+    int lo = 0, len = *P.count;                     // number of breakpoints below s (branch-free halving)
+    while (len > 0) {
+      const int half = len >> 1;
+      const bool right = brk[lo + half] < s;
+      lo = right ? lo + half + 1 : lo;
+      len = right ? len - half - 1 : half;
+    }
+    const T g = brk[P.cap + lo] * P.inv_range;
+    gx += P.axis ? T(0) : g;
+    gy += P.axis ? g : T(0);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Everything else behind one runtime switch: LegendreBasis2DPathCV (ves/basis.py:509-548),
 // HarmonicBias (ves/bias.py:133), and MLPs of any depth/width up to kGenH (unfolded, layer by
 // layer, activations in local memory).

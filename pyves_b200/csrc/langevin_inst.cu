@@ -59,6 +59,7 @@ PV_PAIR(PotSzaboBerezhkovskii<T>, BiasNone<T>, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)
 PV_FAST(PotSzaboBerezhkovskii<T>, BiasMlp<T PV_COMMA 48 PV_COMMA PYVES_ACT_RELU>, 1, 1)
+PV_FAST(PotSzaboBerezhkovskii<T>, BiasPwl1D<T>, 2, 1)
 #elif PV_GROUP == 2  // any potential x each bias family
 PV_FAST(PotGeneric<T>, BiasNone<T>, 2, 1)
 PV_FAST(PotGeneric<T>, BiasLegendre1D<T PV_COMMA 0>, 2, 1)
@@ -69,6 +70,7 @@ PV_FAST(PotGeneric<T>, BiasLegendre2DStaticT<T PV_COMMA 16 PV_COMMA 16 PV_COMMA 
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 1 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasLegendre2DSmem<T PV_COMMA 32 PV_COMMA 2 PV_COMMA 5>, 1, 2)
 PV_FAST(PotGeneric<T>, BiasOther<T>, 1, 1)
+PV_FAST(PotGeneric<T>, BiasPwl1D<T>, 2, 1)
 #elif PV_GROUP == 3  // any potential x MLP widths; the general kernel
 PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_RELU>, 2, 1)
 PV_FAST(PotGeneric<T>, BiasMlp<T PV_COMMA 0 PV_COMMA PYVES_ACT_TANH>, 2, 1)

@@ -474,4 +474,177 @@ cudaError_t launch_mlp_pack(const double* theta64, const MlpPackPlan& Q, T* thet
 PV_INST(float)
 PV_INST(double)
 
+// ------------------------------------------------------------------------------------------------
+// ReLU NNBasis1D -> piecewise-constant dV/ds (see BiasPwl1D in bias.cuh).  One block; all sums in FP64.
+//   first layer (folded): unit i is active where u_i s + c_i > 0, i.e. on one side of tau_i = -c_i / u_i; the sorted tau cut the
+//   line into intervals r = 0 .. M on which the active set is constant;
+//   H == 0 (two hidden layers): V = bout + sum_i wout_i relu(u_i s + c_i), slope_r = sum over the active i of wout_i u_i;
+//   H  > 0 (three hidden layers): on interval r, z2_j = alpha_rj s + beta_rj with alpha_rj = sum_active W2[j][i] u_i,
+//   beta_rj = b2_j + sum_active W2[j][i] c_i; unit j of the second layer switches at kappa_rj = -beta_rj / alpha_rj if that lies
+//   inside the interval; between two consecutive switch points slope = sum over the active j of wout_j alpha_rj.
+// Active sets are evaluated at the midpoint of every piece (robust against ties), never inferred from the order of the switches.
+constexpr int kPwlMaxUnits = 128;     // first-layer units (H <= 64, streamed width <= 128)
+constexpr int kPwlThreads = 1024;
+
+int mlp_pwl_capacity(int H, int width) {
+  if (H > 0) return (H + 1) * (H + 1);
+  return width + 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPwlThreads) mlp_pwl_build_kernel(const T* __restrict__ packed, const int H, const int width,
+                                                                   T* __restrict__ brk, T* __restrict__ slope, int* __restrict__ count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n1 = H > 0 ? H : width;                   // first-layer units
+  const int n2 = H > 0 ? H : 0;                       // second-layer units
+  double* tau = reinterpret_cast<double*>(smem_raw);  // [n1] sorted thresholds
+  double* alpha = tau + kPwlMaxUnits;                 // [(n1 + 1) * n2]
+  double* beta = alpha + (size_t)(n1 + 1) * n2;       // [(n1 + 1) * n2]
+  double* kink = beta + (size_t)(n1 + 1) * n2;        // [(n1 + 1) * n2] sorted switch points of the second layer inside interval r
+  int* kcount = reinterpret_cast<int*>(kink + (size_t)(n1 + 1) * n2);   // [n1 + 1]
+  int* base = kcount + (n1 + 2);                      // [n1 + 2] first piece of interval r
+  __shared__ int M_sh;
+  const T* u = packed;
+  const T* c = packed + n1;
+  const T* wout = packed + 2 * n1;
+  const T* b2 = packed + 3 * n1;                      // H > 0 only
+  const T* W2T = packed + 4 * n1;                     // H > 0 only: W2T[i][j] = W2[j][i]
+  const int tid = threadIdx.x;
+  if (tid == 0) M_sh = 0;
+  __syncthreads();
+  // ---- thresholds of the first layer, rank sort
+  if (tid < n1) {
+    const double ui = (double)u[tid], ci = (double)c[tid];
+    if (ui != 0.0) {
+      const double t = -ci / ui;
+      int rank = 0;
+      for (int k = 0; k < n1; ++k) {
+        const double uk = (double)u[k];
+        if (uk == 0.0) continue;
+        const double tk = -(double)c[k] / uk;
+        rank += (tk < t || (tk == t && k < tid)) ? 1 : 0;
+      }
+      tau[rank] = t;
+      atomicAdd(&M_sh, 1);
+    }
+  }
+  __syncthreads();
+  const int M = M_sh;
+  auto mid = [&](double lo, bool has_lo, double hi, bool has_hi) {   // a point strictly inside (lo, hi) where possible
+    if (has_lo && has_hi) return 0.5 * (lo + hi);
+    if (has_lo) return lo + 1.0;
+    if (has_hi) return hi - 1.0;
+    return 0.0;
+  };
+  if (n2 == 0) {
+    for (int r = tid; r <= M; r += blockDim.x) {
+      const double sp = mid(r > 0 ? tau[r - 1] : 0.0, r > 0, r < M ? tau[r] : 0.0, r < M);
+      double g = 0.0;
+      for (int i = 0; i < n1; ++i) {
+        const double ui = (double)u[i];
+        if (ui * sp + (double)c[i] > 0.0) g += (double)wout[i] * ui;
+      }
+      slope[r] = (T)g;
+      if (r < M) brk[r] = (T)tau[r];
+    }
+    if (tid == 0) *count = M;
+    return;
+  }
+  // ---- second layer on every interval of the first
+  for (int item = tid; item < (M + 1) * n2; item += blockDim.x) {
+    const int r = item / n2, j = item - r * n2;
+    const double sp = mid(r > 0 ? tau[r - 1] : 0.0, r > 0, r < M ? tau[r] : 0.0, r < M);
+    double a = 0.0, b = (double)b2[j];
+    for (int i = 0; i < n1; ++i) {
+      const double ui = (double)u[i], ci = (double)c[i];
+      if (ui * sp + ci > 0.0) {
+        const double w = (double)W2T[i * n2 + j];
+        a += w * ui;
+        b += w * ci;
+      }
+    }
+    alpha[item] = a;
+    beta[item] = b;
+  }
+  __syncthreads();
+  // ---- switch points of the second layer inside each interval, rank sort per interval
+  for (int item = tid; item < (M + 1) * n2; item += blockDim.x) {
+    const int r = item / n2, j = item - r * n2;
+    const bool has_lo = r > 0, has_hi = r < M;
+    const double lo = has_lo ? tau[r - 1] : 0.0, hi = has_hi ? tau[r] : 0.0;
+    auto inside = [&](int jj, double& kap) {
+      const double a = alpha[r * n2 + jj];
+      if (a == 0.0) return false;
+      kap = -beta[r * n2 + jj] / a;
+      return (!has_lo || kap > lo) && (!has_hi || kap < hi);
+    };
+    double kap;
+    if (inside(j, kap)) {
+      int rank = 0;
+      for (int jj = 0; jj < n2; ++jj) {
+        double kk;
+        if (jj != j && inside(jj, kk)) rank += (kk < kap || (kk == kap && jj < j)) ? 1 : 0;
+      }
+      kink[r * n2 + rank] = kap;
+    }
+  }
+  for (int r = tid; r <= M; r += blockDim.x) {
+    const bool has_lo = r > 0, has_hi = r < M;
+    const double lo = has_lo ? tau[r - 1] : 0.0, hi = has_hi ? tau[r] : 0.0;
+    int cnt = 0;
+    for (int jj = 0; jj < n2; ++jj) {
+      const double a = alpha[r * n2 + jj];
+      if (a == 0.0) continue;
+      const double kap = -beta[r * n2 + jj] / a;
+      cnt += ((!has_lo || kap > lo) && (!has_hi || kap < hi)) ? 1 : 0;
+    }
+    kcount[r] = cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int r = 0; r <= M; ++r) {
+      base[r] = acc;
+      acc += kcount[r] + 1;
+    }
+    base[M + 1] = acc;                                // pieces in total
+    *count = acc - 1;                                 // breakpoints
+  }
+  __syncthreads();
+  // ---- pieces: (r, q), q = 0 .. kcount[r]; its upper end is breakpoint base[r] + q (the last piece has none)
+  const int pieces = base[M + 1];
+  for (int pidx = tid; pidx < pieces; pidx += blockDim.x) {
+    int r = 0;
+    while (base[r + 1] <= pidx) ++r;                  // <= 129 intervals
+    const int q = pidx - base[r], kc = kcount[r];
+    const bool has_lo = q > 0 || r > 0, has_hi = q < kc || r < M;
+    const double lo = q > 0 ? kink[r * n2 + q - 1] : (r > 0 ? tau[r - 1] : 0.0);
+    const double hi = q < kc ? kink[r * n2 + q] : (r < M ? tau[r] : 0.0);
+    const double sp = mid(lo, has_lo, hi, has_hi);
+    double g = 0.0;
+    for (int j = 0; j < n2; ++j) {
+      const double a = alpha[r * n2 + j];
+      if (a * sp + beta[r * n2 + j] > 0.0) g += (double)wout[j] * a;
+    }
+    slope[pidx] = (T)g;
+    if (has_hi) brk[pidx] = (T)hi;
+  }
+}
+
+template <typename T>
+cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, cudaStream_t st) {
+  const int n1 = H > 0 ? H : width, n2 = H > 0 ? H : 0;
+  if (n1 < 1 || n1 > kPwlMaxUnits) return cudaErrorInvalidValue;
+  const size_t sm = sizeof(double) * (kPwlMaxUnits + 3 * (size_t)(n1 + 1) * n2) + sizeof(int) * (2 * (size_t)n1 + 8);
+  auto kern = mlp_pwl_build_kernel<T>;
+  if (sm > 48 * 1024 - 64) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<1, kPwlThreads, sm, st>>>(packed, H, width, brk, slope, count);
+  return cudaGetLastError();
+}
+template cudaError_t launch_mlp_pwl_build<float>(const float*, int, int, float*, float*, int*, cudaStream_t);
+template cudaError_t launch_mlp_pwl_build<double>(const double*, int, int, double*, double*, int*, cudaStream_t);
+
 }  // namespace pv

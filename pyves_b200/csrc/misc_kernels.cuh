@@ -48,6 +48,12 @@ struct MlpPackPlan {
 template <typename T>
 cudaError_t launch_mlp_pack(const double* theta64, const MlpPackPlan& Q, T* theta_t, T* packed, cudaStream_t st);
 
+// Compiles the packed ReLU NNBasis1D parameters (BiasMlp layout: H > 0 one H x H layer, H == 0 streamed with `width` units) into
+// the piecewise-constant derivative dV/ds that BiasPwl1D evaluates: brk[count] ascending, slope[count + 1], count <= mlp_pwl_capacity.
+int mlp_pwl_capacity(int H, int width);
+template <typename T>
+cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, cudaStream_t st);
+
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>
 cudaError_t launch_energies(const T* pos, const T* vel, int64_t n, int dims, T* PE, T* KE, T mass, T dt,

@@ -433,7 +433,8 @@ def test_step_wave_walkers():
     torch.manual_seed(0)
     m = basis.NNBasis1D(min=-4, max=4, axis="x", hidden_layer_sizes=[48, 48, 48])
     theta = np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
-    assert wave("fp32", lambda e: e.set_bias_mlp(0, -4.0, 4.0, [48, 48, 48], 0, theta)) == n_sm * 640
+    nn = lambda e: e.set_bias_mlp(0, -4.0, 4.0, [48, 48, 48], 0, theta)
+    assert wave("fp32", nn) == 0 and wave("fp32", nn, 7) == n_sm * 640           # default: the piecewise-constant table, many small CTAs
 
 
 def test_ensemble_ves_along_path_cv():

@@ -217,11 +217,13 @@ TRAJ_CASES = [
     ("slip_leg1d12", potentials.SLIP_BOND_2D, None, lambda r: rng_spec("leg1d", r, degree=12, min=-3.0, max=6.0, scale=1.0), (-3.7, -3.2, -3.7, -3.2), [-1]),
     ("slip_forced_leg1d7y", potentials.SLIP_BOND_2D, (1.5, -0.5, 0.8, 4.0, 3.0, 0.2, 2.5), lambda r: rng_spec("leg1d", r, degree=7, axis='y', min=-4.0, max=6.0, scale=1.0), (-3.0, -2.5, -3.0, -2.5), [-1]),
     ("sb_none", potentials.SZABO_BEREZHKOVSKII, None, lambda r: dict(kind="none"), (2.0, 2.4, 2.0, 2.4), [-1]),
-    ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
+    # ReLU nets, variants: -1 = FP32 default, the piecewise-constant dV/ds table (BiasPwl1D; FP64 handles: the network itself), 8 = the table
+    # forced (FP64 too), 7 = the H x H layer on the tensor cores, 6 = CUDA cores
+    ("sb_mlp48x3", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[48, 48, 48]), (2.0, 2.4, 2.0, 2.4), [-1, 6, 7, 8]),
     # ReLU nets with one H x H layer run the mask-operand tensor-core kernel (H padded to 32 / 48 / 64)
-    ("sb_mlp_relu_32", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[30, 32, 28]), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
-    ("catch_mlp_relu_64", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[64, 60, 64], scale=0.25), (-3.7, -3.2, -3.7, -3.2), [-1, 6]),
-    ("sb_mlp128x2", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[128, 128]), (2.0, 2.4, 2.0, 2.4), [-1]),
+    ("sb_mlp_relu_32", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[30, 32, 28]), (2.0, 2.4, 2.0, 2.4), [-1, 6, 7, 8]),
+    ("catch_mlp_relu_64", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[64, 60, 64], scale=0.25), (-3.7, -3.2, -3.7, -3.2), [-1, 6, 7, 8]),
+    ("sb_mlp128x2", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[128, 128]), (2.0, 2.4, 2.0, 2.4), [-1, 6, 8]),
     ("sb_mlp16", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[16]), (2.0, 2.4, 2.0, 2.4), [-1]),
     ("catch_mlp_tanh", potentials.CATCH_BOND_2D, None, lambda r: rng_spec("mlp", r, sizes=[20, 30, 24], act=1), (-3.7, -3.2, -3.7, -3.2), [-1, 6]),
     ("sb_mlp_64_tanh", potentials.SZABO_BEREZHKOVSKII, None, lambda r: rng_spec("mlp", r, sizes=[64, 64, 56], act=1, scale=0.25), (2.0, 2.4, 2.0, 2.4), [-1, 6]),
@@ -312,6 +314,8 @@ def test_tensor_core_step_every_walker_once(shape):
         spec = rng_spec("leg2d", rng, deg_x=shape[0], deg_y=shape[1], scale=1.0)
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
     probe = biasspec.make_ensemble(128, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
+    if shape == "mlp48":
+        probe.set_tuning(7)
     wave = probe.wave_walkers()
     probe.close()
     assert wave > 0 and wave % (128 * n_sm) == 0
@@ -319,7 +323,7 @@ def test_tensor_core_step_every_walker_once(shape):
         x0 = np.stack([rng.uniform(-1.6, 1.6, n), rng.uniform(-1.0, 1.0, n)], 1)
         v0 = np.zeros((n, 2))
         out = []
-        for variant in (-1, 6):
+        for variant in ((7, 6) if shape == "mlp48" else (-1, 6)):
             e = biasspec.make_ensemble(n, 2, 123, "fp32", potentials.DOUBLE_WELL_2D, None, spec)
             e.set_walker_offset(10 ** 9)
             e.set_tuning(variant)
