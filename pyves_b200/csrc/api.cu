@@ -68,6 +68,10 @@ struct pyves_ctx {
   int* pwl_count = nullptr;
   int pwl_cap = 0;
   bool pwl_valid = false;
+  double* pwl_hist = nullptr;      // moments through the pieces: histogram, pseudo rows, their weights
+  void* pwl_rows = nullptr;
+  void* pwl_row_w = nullptr;
+  int pwl_hist_cap = 0;
   void* tc_img = nullptr;          // operand image of the tensor-core Legendre step kernel (langevin2d_tc_scratch_bytes())
   int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
   int mlp_width = 0, mlp_linear = 0;
@@ -644,7 +648,35 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
     M.theta = static_cast<const T*>(h->mlp_theta_dev);
     M.n_params = (int)K;
     M.inside_only = h->mom_inside;
-    CU(launch_moments_mlp<T>(S, M, sum_w, sum_wf, h->scratch, st, &launches));
+    // ReLU nets: rows binned into the pieces of the piecewise-linear network, gradients on one pseudo row per piece (moments.cuh);
+    // FP32 default for ensembles much larger than the table, variant 8 always
+    const int cap = h->pwl_cap;
+    if (h->pwl_valid && S.ncols <= 2 && (h->variant == 8 || (h->variant == -1 && sizeof(T) == 4 && S.n >= 8 * (int64_t)(cap + 1)))) {
+      if (h->pwl_hist_cap < cap) {
+        if (h->pwl_hist) cudaFree(h->pwl_hist);
+        if (h->pwl_rows) cudaFree(h->pwl_rows);
+        if (h->pwl_row_w) cudaFree(h->pwl_row_w);
+        h->pwl_hist = nullptr;
+        h->pwl_rows = h->pwl_row_w = nullptr;
+        CU(cudaMalloc(reinterpret_cast<void**>(&h->pwl_hist), sizeof(double) * 2 * (size_t)(cap + 1)));
+        CU(cudaMalloc(&h->pwl_rows, sizeof(T) * 2 * (size_t)(cap + 1)));
+        CU(cudaMalloc(&h->pwl_row_w, sizeof(T) * (size_t)(cap + 1)));
+        h->pwl_hist_cap = cap;
+      }
+      CU(launch_pwl_compress<T>(S, M.axis, M.lo, M.inv_range, M.inside_only, static_cast<const T*>(h->pwl_brk), h->pwl_count, cap, h->pwl_hist,
+                                static_cast<T*>(h->pwl_rows), static_cast<T*>(h->pwl_row_w), st, &launches));
+      RowSource<T> S2;
+      S2.pos = static_cast<const T*>(h->pwl_rows);
+      S2.n = cap + 1;
+      S2.stride_row = 2;
+      S2.stride_col = 1;
+      S2.ncols = 2;
+      S2.w = static_cast<const T*>(h->pwl_row_w);
+      M.inside_only = 0;                           // already applied to the rows; the pseudo rows are means of admitted rows
+      CU(launch_moments_mlp<T>(S2, M, sum_w, sum_wf, h->scratch, st, &launches));
+    } else {
+      CU(launch_moments_mlp<T>(S, M, sum_w, sum_wf, h->scratch, st, &launches));
+    }
   } else {
     BasisParams<T> B;
     std::memset(&B, 0, sizeof(B));
@@ -742,7 +774,7 @@ int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
   void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->l1_wt_dev, h->l1_w64_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
-                  h->scratch, h->stage, h->fail_dev, h->tc_img, h->pwl_brk, h->pwl_slope, h->pwl_count};
+                  h->scratch, h->stage, h->fail_dev, h->tc_img, h->pwl_brk, h->pwl_slope, h->pwl_count, h->pwl_hist, h->pwl_rows, h->pwl_row_w};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;

@@ -1219,6 +1219,83 @@ cudaError_t launch_moments_mlp(const RowSource<T>& S, const MlpGradParams<T>& M,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rows -> pieces of the piecewise-linear ReLU network (see moments.cuh).  Block-private histograms in shared memory (FP64), flushed
+// with one global atomic per non-empty bin.
+template <typename T>
+__global__ void __launch_bounds__(256) pwl_hist_kernel(const RowSource<T> S, const int axis, const T lo, const T inv_range, const int inside_only,
+                                                       const T* __restrict__ brk, const int* __restrict__ count, const int cap,
+                                                       double* __restrict__ hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* hw = reinterpret_cast<double*>(smem_raw);          // [cap + 1] sum of weights
+  double* hs = hw + (cap + 1);                               // [cap + 1] sum of weights times s
+  T* b = reinterpret_cast<T*>(hs + (cap + 1));               // [cap] breakpoints
+  const int nb = *count;
+  for (int i = threadIdx.x; i <= cap; i += blockDim.x) hw[i] = hs[i] = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) b[i] = brk[i];
+  __syncthreads();
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
+    const T q = S.pos[r * S.stride_row + (axis && S.ncols > 1 ? S.stride_col : 0)];
+    const T s = (q - lo) * inv_range;
+    T w = S.w != nullptr ? S.w[r] : T(1);
+    if (inside_only && !(s >= T(0) && s <= T(1))) w = T(0);
+    if (w == T(0)) continue;
+    int p = 0, len = nb;
+    while (len > 0) {
+      const int half = len >> 1;
+      const bool right = b[p + half] < s;
+      p = right ? p + half + 1 : p;
+      len = right ? len - half - 1 : half;
+    }
+    atomicAdd(&hw[p], (double)w);
+    atomicAdd(&hs[p], (double)w * (double)s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= cap; i += blockDim.x) {
+    if (hw[i] != 0.0) {
+      atomicAdd(&hist[i], hw[i]);
+      atomicAdd(&hist[cap + 1 + i], hs[i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pwl_rows_kernel(const double* __restrict__ hist, const int cap, const T lo, const T inv_range,
+                                                       T* __restrict__ rows, T* __restrict__ row_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > cap) return;
+  const double n = hist[i], sw = hist[cap + 1 + i];
+  const double sbar = n != 0.0 ? sw / n : 0.0;
+  const T x = (T)((double)lo + sbar / (double)inv_range);
+  rows[2 * i] = x;
+  rows[2 * i + 1] = x;
+  row_w[i] = (T)n;
+}
+
+template <typename T>
+cudaError_t launch_pwl_compress(const RowSource<T>& S, int axis, T lo, T inv_range, int inside_only, const T* brk, const int* count, int cap,
+                                double* hist, T* rows, T* row_w, cudaStream_t st, int* launches) {
+  cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(double) * 2 * (size_t)(cap + 1), st);
+  if (e != cudaSuccess) return e;
+  const size_t sm = sizeof(double) * 2 * (size_t)(cap + 1) + sizeof(T) * (size_t)cap + 16;
+  auto kern = pwl_hist_kernel<T>;
+  if (sm > 48 * 1024 - 64) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  int64_t blocks = (S.n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, 256, sm, st>>>(S, axis, lo, inv_range, inside_only, brk, count, cap, hist);
+  pwl_rows_kernel<T><<<(cap + 1 + 255) / 256, 256, 0, st>>>(hist, cap, lo, inv_range, rows, row_w);
+  *launches += 2;
+  return cudaGetLastError();
+}
+template cudaError_t launch_pwl_compress<float>(const RowSource<float>&, int, float, float, int, const float*, const int*, int, double*, float*,
+                                                float*, cudaStream_t, int*);
+template cudaError_t launch_pwl_compress<double>(const RowSource<double>&, int, double, double, int, const double*, const int*, int, double*,
+                                                 double*, double*, cudaStream_t, int*);
+
 #define PV_INST(T)                                                                                               \
   template cudaError_t launch_moments_basis<T>(const RowSource<T>&, const BasisParams<T>&, double*, double*,     \
                                                double*, double*, cudaStream_t, int*);                            \

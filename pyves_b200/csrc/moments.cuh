@@ -54,6 +54,13 @@ cudaError_t launch_cov_tc(const RowSource<float>& S, const BasisParams<float>& B
 void cov_tc_set_max_rows(int64_t rows);   // rows one CTA accumulates in FP32 before its partial goes to the FP64 sum (tuning)
 constexpr int kMaxSmForScratch = 160;
 bool no_tensor_cores();
+// ReLU NNBasis1D: every parameter gradient dV/dtheta is AFFINE in the input on each piece of the piecewise-linear V (bias.cuh,
+// BiasPwl1D), so sum_r w_r dV/dtheta(s_r) = sum over the pieces p of n_p dV/dtheta(mean_p): the rows are binned into the pieces
+// (n_p = sum of weights, S_p = sum of weights times s), and the parameter-gradient kernel runs on cap + 1 pseudo rows instead
+// of n.  hist: 2 (cap + 1) doubles; rows: 2 (cap + 1) T (two columns, both the coordinate); row_w: cap + 1 T.  Stream ordered.
+template <typename T>
+cudaError_t launch_pwl_compress(const RowSource<T>& S, int axis, T lo, T inv_range, int inside_only, const T* brk, const int* count, int cap,
+                                double* hist, T* rows, T* row_w, cudaStream_t st, int* launches);
 void set_tiled_first_moments(bool v);   // tuning / test switch: register-tiled first moments of large 2D bases (default on)
 void set_no_tensor_cores(bool v);   // tuning / test switch: force the CUDA-core covariance
 

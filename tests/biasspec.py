@@ -78,6 +78,9 @@ def oracle_inside(spec, pos):
     if k == "pathcv":
         s, _, _, _ = pathcv.path_cv(pos, spec["x_i"], spec["y_i"], spec["lam"])
         return (2 * s - 1 >= -1) & (2 * s - 1 <= 1)
+    if k == "mlp":                                   # NNBasis1D: scaled coordinate in [0, 1] (the support of the target)
+        s = (pos[:, AX[spec["axis"]]] - spec["min"]) / (spec["max"] - spec["min"])
+        return (s >= 0) & (s <= 1)
     raise KeyError(k)
 
 

@@ -636,6 +636,45 @@ def test_moments_inside_domain(case):
         e.close()
 
 
+@pytest.mark.parametrize("sizes", [[48, 48, 48], [128, 128], [30, 32, 28]], ids=["48x3", "128x2", "30_32_28"])
+def test_moments_relu_mlp_through_the_pieces(sizes):
+    """Parameter-gradient moments of a ReLU NNBasis1D through the pieces of the piecewise-linear network (pyves_set_tuning 8; the FP32
+    default for large ensembles): dV/dtheta is affine in the input on every piece, so binning the rows and running the gradient
+    kernel on one pseudo row per piece gives the same sums as the per-row pass -- against the FP64 oracle, with and without row
+    weights, with the in-box restriction, FP32 and FP64."""
+    rng = np.random.default_rng(zlib.crc32(str(sizes).encode()))
+    spec = rng_spec("mlp", rng, sizes=sizes)
+    n = 5003
+    pos = np.stack([rng.uniform(-0.2, 1.2, n) * (spec["max"] - spec["min"]) + spec["min"], rng.uniform(-2.5, 2.5, n)], 1)
+    w = rng.uniform(0, 2, n)
+    fr = biasspec.oracle_basis(spec, pos)
+    from oracle import ves
+    for prec, tol, dt in PREC:
+        e = biasspec.make_ensemble(n, 2, 0, prec, potentials.DOUBLE_WELL_2D, None, spec)
+        tpos = torch.tensor(pos, dtype=dt, device=DEV)
+        e.set_state(tpos.T.contiguous(), None)
+        p_dev = pos.astype(e.np_dtype).astype(np.float64)
+        inside = biasspec.oracle_inside(spec, p_dev)
+        for variant in (8, 6):
+            e.set_tuning(variant)
+            for domain in (False, True):
+                e.set_moment_domain(domain)
+                for weights in (None, w):
+                    tws = None if weights is None else torch.tensor(weights, dtype=dt, device=DEV)
+                    wm = (inside.astype(np.float64) if domain else np.ones(n)) * (1.0 if weights is None else weights)
+                    sw_r, sf_r, _ = ves.moments(fr, wm)
+                    sw, sf, _ = e.moments(row_weights=tws)
+                    assert abs(float(sw.cpu()[0]) - sw_r) / sw_r < (1e-12 if prec == "fp64" and variant == 6 else 1e-6)
+                    scale = np.maximum(np.abs(fr).T @ wm, 1.0)
+                    err = np.max(np.abs(sf.cpu().numpy() - sf_r) / scale)
+                    # FP32: a row within rounding of a switch point of the second layer can fall on the other side, and dV/dW2[j][i]
+                    # jumps there by wout_j h_i -- for a parameter only a few rows feed, one such row is 2e-3 of the sum in the
+                    # per-row FP32 kernel (measured, tools/diag/nn_moments_diag.py); the pieces come from FP64 breakpoints: 3e-5
+                    bound = 1e-6 if prec == "fp64" else (tol if variant == 8 else 5e-3)
+                    assert err < bound, (sizes, prec, variant, domain, err)
+        e.close()
+
+
 def test_moments_mlp_rejects_covariance():
     rng = np.random.default_rng(0)
     e = biasspec.make_ensemble(8, 2, 0, "fp32", potentials.DOUBLE_WELL_2D, None, rng_spec("mlp", rng, sizes=[4, 4]))
