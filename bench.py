@@ -516,6 +516,11 @@ def config_legs(args, rank, world, local, dev, peak):
         if "tc_kernel" in kernel:
             K = int(name.split("_")[1].split("x")[0]) if name.startswith("cfg5_") else args.basis
             extra["tensor"] = tensor_roofline(K, n_rank * stride / (kms * 1e-3))["tensor"]
+        elif "BiasPwl1D" in kernel:
+            flops_note = ("%d flop per walker-step is the algorithmic work of evaluating the network (SURVEY 8(d)); this kernel does not "
+                          "evaluate it -- for a ReLU net of one input dV/ds is piecewise constant and is looked up by a binary search in "
+                          "shared memory -- so the FP32 fraction is not a bound here (it exceeds 1)" % flops)
+            extra["roofline_note"] = flops_note
         elif "tc_relu_kernel" in kernel:
             ex = 2.0 * 2.0 * 96 * 48                  # 2 MMAs (mask x hi, mask x lo) x 2 N K flops per walker-step, N = 2 H, K = H
             extra["tensor"] = {"executed_flops_per_walker_step": ex, "achieved": ex * n_rank * stride / (kms * 1e-3) * 1e-12, "unit": "TFLOP/s"}
@@ -551,7 +556,11 @@ def config_legs(args, rank, world, local, dev, peak):
                                      beta, "Adam", {"lr": 1e-3}, target_update_every=0, gradient_average='running')
     updater_leg("cfg4", "configs[3]: Szabo-Berezhkovskii + NNBasis1D [48,48,48] (ReLU), Adam 1e-3, running-average gradients, uniform target, "
                 "10^6 walkers per GPU", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII, (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000,
-                1000000 * world, args.stride, 2, "langevin2d_tc_relu_kernel<48, 5> (48 x 48 layer on the tensor cores, 0/1 mask operand against W2 diag(u) over W2 diag(c))", LEG_FLOPS["cfg4"], "weak")
+                1000000 * world, args.stride, 2, "langevin2d_kernel<SzaboBerezhkovskii, BiasPwl1D> (ReLU net compiled to its piecewise-constant dV/ds: "
+                "binary search in shared memory; parameter-gradient moments through the pieces)", LEG_FLOPS["cfg4"], "weak")
+    updater_leg("cfg4_tensor_cores", "configs[3] with the network itself evaluated every step, 48 x 48 layer on the tensor cores (pyves_set_tuning 7)", nn_bias,
+                _lib.POT_SZABO_BEREZHKOVSKII, (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000, 1000000 * world, args.stride, 2,
+                "langevin2d_tc_relu_kernel<48, 5> (0/1 mask operand against W2 diag(u) over W2 diag(c))", LEG_FLOPS["cfg4"], "weak", variant=7)
     updater_leg("cfg4_cuda_cores", "configs[3] with the step kernel forced onto the CUDA cores (pyves_set_tuning 6)", nn_bias, _lib.POT_SZABO_BEREZHKOVSKII,
                 (2.2, 4.0, 4.04, 4.84), (-4, 4, -4, 4), 1000000, rank * 1000000, 1000000 * world, args.stride, 2,
                 "langevin2d_kernel<SzaboBerezhkovskii, Mlp<48>> (CUDA cores, FFMA2 input sweep)", LEG_FLOPS["cfg4"], "weak", variant=6)

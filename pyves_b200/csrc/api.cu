@@ -66,6 +66,8 @@ struct pyves_ctx {
   void* pwl_brk = nullptr;         // ReLU NNBasis1D compiled to a piecewise-constant dV/ds (BiasPwl1D): breakpoints, slopes, count
   void* pwl_slope = nullptr;
   int* pwl_count = nullptr;
+  int* pwl_grid = nullptr;         // bucket grid of the breakpoints (kPwlBuckets + 1 ints) and its {origin, buckets per unit}
+  void* pwl_grid_map = nullptr;
   int pwl_cap = 0;
   bool pwl_valid = false;
   double* pwl_hist = nullptr;      // moments through the pieces: histogram, pseudo rows, their weights
@@ -267,13 +269,17 @@ int refresh_pwl(pyves_ctx* h, cudaStream_t st) {
     CU(cudaMalloc(&h->pwl_slope, (size_t)(cap + 1) * h->esz));
     h->pwl_cap = cap;
   }
-  if (!h->pwl_count) CU(cudaMalloc(reinterpret_cast<void**>(&h->pwl_count), sizeof(int)));
+  if (!h->pwl_count) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->pwl_count), sizeof(int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->pwl_grid), sizeof(int) * (kPwlBuckets + 1)));
+    CU(cudaMalloc(&h->pwl_grid_map, 2 * sizeof(double)));
+  }
   if (h->prec == PYVES_F64) {
     CU(launch_mlp_pwl_build<double>(static_cast<const double*>(h->mlp_packed_dev), h->mlp_H, h->mlp_width, static_cast<double*>(h->pwl_brk),
-                                    static_cast<double*>(h->pwl_slope), h->pwl_count, st));
+                                    static_cast<double*>(h->pwl_slope), h->pwl_count, h->pwl_grid, static_cast<double*>(h->pwl_grid_map), st));
   } else {
     CU(launch_mlp_pwl_build<float>(static_cast<const float*>(h->mlp_packed_dev), h->mlp_H, h->mlp_width, static_cast<float*>(h->pwl_brk),
-                                   static_cast<float*>(h->pwl_slope), h->pwl_count, st));
+                                   static_cast<float*>(h->pwl_slope), h->pwl_count, h->pwl_grid, static_cast<float*>(h->pwl_grid_map), st));
   }
   g_launches++;
   h->pwl_valid = true;
@@ -289,6 +295,8 @@ template <typename T> PwlParams<T> pwl_params(const pyves_ctx* h) {
   P.brk = static_cast<const T*>(h->pwl_brk);
   P.slope = static_cast<const T*>(h->pwl_slope);
   P.count = h->pwl_count;
+  P.grid = h->pwl_grid;
+  P.grid_map = static_cast<const T*>(h->pwl_grid_map);
   return P;
 }
 
@@ -774,7 +782,7 @@ int pyves_destroy(pyves_t* h) {
   if (!h) return PYVES_OK;
   DeviceGuard g(h->device);
   void* ptrs[] = {h->pos, h->vel, h->l2_w_dev, h->l2_wt_dev, h->l1_wt_dev, h->l1_w64_dev, h->mlp_theta_dev, h->mlp_packed_dev, h->pc_path_dev,
-                  h->scratch, h->stage, h->fail_dev, h->tc_img, h->pwl_brk, h->pwl_slope, h->pwl_count, h->pwl_hist, h->pwl_rows, h->pwl_row_w};
+                  h->scratch, h->stage, h->fail_dev, h->tc_img, h->pwl_brk, h->pwl_slope, h->pwl_count, h->pwl_hist, h->pwl_rows, h->pwl_row_w, h->pwl_grid, h->pwl_grid_map};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;

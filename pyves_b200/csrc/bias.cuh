@@ -558,6 +558,8 @@ template <typename T, int H, int ACT> struct BiasMlp {
 // the sorted breakpoints and the slope of every piece (FP64 sums, exact up to the rounding of the breakpoints) whenever they
 // change; the step kernel's bias force is then ONE binary search in shared memory -- no matmul, no activations, no tensor core.
 // Step kernels only (forces); energies and parameter gradients go through the network itself (BiasMlp, moments_mlp2_kernel).
+constexpr int kPwlBuckets = 2048;   // uniform grid over [first, last breakpoint]: where the binary search starts
+
 template <typename T> struct PwlParams {
   int axis;
   T lo, inv_range;
@@ -565,30 +567,40 @@ template <typename T> struct PwlParams {
   const T* brk;        // device: breakpoints in the scaled coordinate, ascending
   const T* slope;      // device: dV/ds on the pieces: slope[k] for brk[k-1] < s <= brk[k]
   const int* count;    // device: number of breakpoints
+  const int* grid;     // device: grid[b] = number of breakpoints below the lower edge of bucket b (kPwlBuckets + 1 entries)
+  const T* grid_map;   // device: {origin, buckets per unit of s}
 };
 
 template <typename T> struct BiasPwl1D {
   using Params = PwlParams<T>;
-  static size_t smem_bytes(const Params& P) { return (size_t)(2 * P.cap + 1) * sizeof(T) + 16; }
+  static size_t smem_bytes(const Params& P) { return (size_t)(2 * P.cap + 1) * sizeof(T) + (size_t)(kPwlBuckets + 1) * sizeof(int) + 32; }
   static PV_DEV void stage(const Params& P, void* smem) {
     T* d = reinterpret_cast<T*>(smem);
+    int* g = reinterpret_cast<int*>(d + 2 * P.cap + 1);
     const int n = *P.count;
     for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = P.brk[i];
     for (int i = threadIdx.x; i <= n; i += blockDim.x) d[P.cap + i] = P.slope[i];
+    for (int i = threadIdx.x; i <= kPwlBuckets; i += blockDim.x) g[i] = P.grid[i];
   }
   template <bool WANT_E> static PV_DEV void grad(const Params& P, const void* smem, T x, T y, T& e, T& gx, T& gy) {
     const T s = ((P.axis ? y : x) - P.lo) * P.inv_range;
     const T* brk = reinterpret_cast<const T*>(smem);
-    int lo = 0, len = *P.count;                     // number of breakpoints below s (branch-free halving)
+    const int* g = reinterpret_cast<const int*>(brk + 2 * P.cap + 1);
+    // number of breakpoints below s: the bucket of s (one bucket of margin on either side against rounding at the edges)
+    // bounds it from both sides, a branch-free halving finishes inside -- usually zero to two probes instead of twelve
+    const T t = (s - P.grid_map[0]) * P.grid_map[1];
+    int b = (int)Math<T>::min(Math<T>::max(t, T(0)), T(kPwlBuckets - 1));
+    int lo = g[b > 0 ? b - 1 : 0];
+    int len = g[b + 2 <= kPwlBuckets ? b + 2 : kPwlBuckets] - lo;
     while (len > 0) {
       const int half = len >> 1;
       const bool right = brk[lo + half] < s;
       lo = right ? lo + half + 1 : lo;
       len = right ? len - half - 1 : half;
     }
-    const T g = brk[P.cap + lo] * P.inv_range;
-    gx += P.axis ? T(0) : g;
-    gy += P.axis ? g : T(0);
+    const T gr = brk[P.cap + lo] * P.inv_range;
+    gx += P.axis ? T(0) : gr;
+    gy += P.axis ? gr : T(0);
   }
 };
 

@@ -491,9 +491,37 @@ int mlp_pwl_capacity(int H, int width) {
   return width + 1;
 }
 
+// grid[b] = number of breakpoints below the lower edge of bucket b of a uniform grid over [brk[0], brk[n - 1]] (block-wide; brk was
+// written by this block and a barrier separates the writes from these reads); grid[kPwlBuckets] = n
+template <typename T> PV_DEV void pwl_grid(const T* brk, int n, int* grid, T* grid_map) {
+  const T g0 = n > 0 ? brk[0] : T(0);
+  const T width = n > 1 ? brk[n - 1] - brk[0] : T(0);
+  const T per = width > T(0) ? T(kPwlBuckets) / width : T(0);
+  if (threadIdx.x == 0) {
+    grid_map[0] = g0;
+    grid_map[1] = per;
+  }
+  for (int b = threadIdx.x; b <= kPwlBuckets; b += blockDim.x) {
+    int lo = 0, len = n;
+    if (b == kPwlBuckets || per == T(0)) {
+      lo = b == 0 ? 0 : n;
+    } else {
+      const T edge = g0 + T(b) / per;
+      while (len > 0) {
+        const int half = len >> 1;
+        const bool right = brk[lo + half] < edge;
+        lo = right ? lo + half + 1 : lo;
+        len = right ? len - half - 1 : half;
+      }
+    }
+    grid[b] = lo;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kPwlThreads) mlp_pwl_build_kernel(const T* __restrict__ packed, const int H, const int width,
-                                                                   T* __restrict__ brk, T* __restrict__ slope, int* __restrict__ count) {
+                                                                   T* __restrict__ brk, T* __restrict__ slope, int* __restrict__ count,
+                                                                   int* __restrict__ grid, T* __restrict__ grid_map) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n1 = H > 0 ? H : width;                   // first-layer units
   const int n2 = H > 0 ? H : 0;                       // second-layer units
@@ -548,6 +576,8 @@ __global__ void __launch_bounds__(kPwlThreads) mlp_pwl_build_kernel(const T* __r
       if (r < M) brk[r] = (T)tau[r];
     }
     if (tid == 0) *count = M;
+    __syncthreads();
+    pwl_grid(brk, M, grid, grid_map);
     return;
   }
   // ---- second layer on every interval of the first
@@ -629,10 +659,12 @@ __global__ void __launch_bounds__(kPwlThreads) mlp_pwl_build_kernel(const T* __r
     slope[pidx] = (T)g;
     if (has_hi) brk[pidx] = (T)hi;
   }
+  __syncthreads();
+  pwl_grid(brk, pieces - 1, grid, grid_map);
 }
 
 template <typename T>
-cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, cudaStream_t st) {
+cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, int* grid, T* grid_map, cudaStream_t st) {
   const int n1 = H > 0 ? H : width, n2 = H > 0 ? H : 0;
   if (n1 < 1 || n1 > kPwlMaxUnits) return cudaErrorInvalidValue;
   const size_t sm = sizeof(double) * (kPwlMaxUnits + 3 * (size_t)(n1 + 1) * n2) + sizeof(int) * (2 * (size_t)n1 + 8);
@@ -641,10 +673,10 @@ cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* s
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
-  kern<<<1, kPwlThreads, sm, st>>>(packed, H, width, brk, slope, count);
+  kern<<<1, kPwlThreads, sm, st>>>(packed, H, width, brk, slope, count, grid, grid_map);
   return cudaGetLastError();
 }
-template cudaError_t launch_mlp_pwl_build<float>(const float*, int, int, float*, float*, int*, cudaStream_t);
-template cudaError_t launch_mlp_pwl_build<double>(const double*, int, int, double*, double*, int*, cudaStream_t);
+template cudaError_t launch_mlp_pwl_build<float>(const float*, int, int, float*, float*, int*, int*, float*, cudaStream_t);
+template cudaError_t launch_mlp_pwl_build<double>(const double*, int, int, double*, double*, int*, int*, double*, cudaStream_t);
 
 }  // namespace pv

@@ -52,7 +52,7 @@ cudaError_t launch_mlp_pack(const double* theta64, const MlpPackPlan& Q, T* thet
 // the piecewise-constant derivative dV/ds that BiasPwl1D evaluates: brk[count] ascending, slope[count + 1], count <= mlp_pwl_capacity.
 int mlp_pwl_capacity(int H, int width);
 template <typename T>
-cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, cudaStream_t st);
+cudaError_t launch_mlp_pwl_build(const T* packed, int H, int width, T* brk, T* slope, int* count, int* grid, T* grid_map, cudaStream_t st);
 
 // PE = U + V_bias (+1000 z^2), KE = m/2 |v + dt/2 F/m|^2 (ves/langevin_dynamics.py:227-228)
 template <typename T>
