@@ -244,7 +244,10 @@ const char* pyves_comm_last_error(void);
 
 /* kernel-variant selector for tuning runs (-1 = default table; 99 = force the general step kernel; 7 / 6 = the 2D Legendre
  * contraction of the step kernel on the tensor cores for every size <= 64 x 64 / on the CUDA cores for every size (default:
- * tensor cores for every FP32 2D Legendre basis up to 64 x 64 except the static 8 x 8 double-well kernel); 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed
+ * tensor cores for every FP32 2D Legendre basis up to 64 x 64 except the static 8 x 8 double-well kernel); for ReLU NNBasis1D biases
+ * with two / three hidden layers -1 = the piecewise-constant dV/ds table on FP32 handles (and, for ensembles much larger than the table,
+ * parameter-gradient moments through its pieces), 8 = the table on any handle and for any number of rows, 7 / 6 = the network itself
+ * evaluated every step on the tensor cores / CUDA cores; 98 / 97 = process-wide: covariance on CUDA cores only / tensor cores allowed
  * again; 96 / 95 = process-wide: first moments of 2D bases beyond 16 x 16 with the one-function-per-thread kernel / the register-tiled
  * kernel again; 1000 + k = process-wide: rows the tensor-core covariance accumulates in TMEM between two drains = 2^k) */
 int pyves_set_tuning(pyves_t* h, int variant);
