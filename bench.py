@@ -309,10 +309,9 @@ def run_ours(args):
             for c in range(nch):
                 streams[c].wait_stream(main)                     # the coefficient hand-over was enqueued on the main stream
                 with torch.cuda.stream(streams[c]):
-                    subs[c].set_state(hp[c], hv[c], async_copy=True)          # H2D of this chunk's inputs
-                    subs[c].step(args.stride)
-                    subs[c].moments(out=mom[c])
-                    subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)    # D2H of this chunk's walkers
+                    # pyves_iterate_pinned: H2D of this chunk's walkers from pinned memory, the steps, the chunk's moments, D2H of
+                    # the walkers back into the pinned buffers -- one C call, all enqueued on this chunk's stream
+                    subs[c].iterate_pinned(hp[c], hv[c], args.stride, mom[c])
             for c in range(nch):
                 main.wait_stream(streams[c])
             sw = sum(m[0] for m in mom)

@@ -131,6 +131,14 @@ int pyves_init_velocities(pyves_t* h, void* stream);
  * update, state held in registers for the whole launch.  injected_noise: NULL = Philox, or
  * a device array [nsteps][dims][n] of N(0,1) draws (parity tests). */
 int pyves_step(pyves_t* h, int64_t nsteps, const void* injected_noise, void* stream);
+/* One iteration between two coefficient updates with HOST buffers, every operation enqueued on `stream` (no synchronisation): the walker
+ * state from PINNED host memory (pos_in / vel_in, SoA [dims][n] of the handle's element type), nsteps steps, the basis moments of the
+ * handle's walkers into the device buffers sum_w[1] / sum_wf[K], the walker state back to the pinned buffers pos_out / vel_out (which may
+ * be the input buffers).  The four calls of set_state(on_host = 2) -> step -> moments -> get_state(on_host = 2) in one: what a caller
+ * that keeps its ensemble on the host does every iteration (the reference moves its one particle through
+ * context.setPositions / step / getState, ves/langevin_dynamics.py:60-76,188,201). */
+int pyves_iterate_pinned(pyves_t* h, const void* pos_in, const void* vel_in, int64_t nsteps, double* sum_w, double* sum_wf,
+                         void* pos_out, void* vel_out, void* stream);
 /* same, recording positions of walkers [0, n_rec) before every `every`-th step (frame t is
  * written before step t, as :180-188 does) into traj_out (device) [n_frames][dims][n_rec],
  * n_frames = ceil(nsteps / every). */

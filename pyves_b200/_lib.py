@@ -61,6 +61,7 @@ SIGNATURES = {
     "pyves_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _dp, _ip, _vp, _vp, _i, _vp]),
     "pyves_set_tuning": (_i, [_vp, _i]),
     "pyves_step_wave_walkers": (_i, [_vp, _c.POINTER(_i64)]),
+    "pyves_iterate_pinned": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pyves_set_moment_domain": (_i, [_vp, _i]),
     "pyves_averaged_sgd_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _i64, _vp, _vp, _vp]),
     "pyves_set_bias_legendre2d_device": (_i, [_vp, _i, _i, _dp, _vp, _vp]),
@@ -332,6 +333,18 @@ class Ensemble:
 
     def set_tuning(self, variant):
         self._ck(self.lib.pyves_set_tuning(self.h, variant))
+
+    def iterate_pinned(self, pos, vel, nsteps, out, stream=None):
+        """One iteration with HOST buffers, everything enqueued on the stream (no synchronisation): the walker state from the PINNED
+        numpy arrays ``pos`` / ``vel`` ([dims, n], the handle's dtype, C-contiguous), ``nsteps`` steps, the basis moments into the CUDA
+        tensors ``out = (sum_w, sum_wf)``, the walker state back into ``pos`` / ``vel``.  One C call instead of set_state(async) /
+        step / moments / get_state(async); synchronise the stream before reading the arrays."""
+        for a in (pos, vel):
+            if not (isinstance(a, np.ndarray) and a.dtype == self.np_dtype and a.flags["C_CONTIGUOUS"] and a.shape == (self.dims, self.n)):
+                raise ValueError("iterate_pinned needs C-contiguous numpy arrays [dims, n] of the handle's dtype")
+        st = self.stream if stream is None else stream
+        self._ck(self.lib.pyves_iterate_pinned(self.h, pos.ctypes.data, vel.ctypes.data, int(nsteps), out[0].data_ptr(), out[1].data_ptr(),
+                                               pos.ctypes.data, vel.ctypes.data, st))
 
     def wave_walkers(self):
         """Walkers one full wave of this handle's step kernel advances (0: no granularity worth respecting).  Chunked

@@ -75,6 +75,7 @@ struct pyves_ctx {
   void* pwl_row_w = nullptr;
   int pwl_hist_cap = 0;
   void* tc_img = nullptr;          // operand image of the tensor-core Legendre step kernel (langevin2d_tc_scratch_bytes())
+  bool tc_img_valid = false;       // built from the current 2D coefficients (reset by every pyves_set_bias_legendre2d*)
   int mlp_H = -1;                   // -1: no fast functor; 0: streamed; 32/48/64: one matmul
   int mlp_width = 0, mlp_linear = 0;
   double mlp_bout = 0, mlp_u0 = 0;
@@ -478,12 +479,28 @@ template <typename T> int run_general(pyves_ctx* h, const StepArgs<T>& A, cudaSt
 
 // tuning variant 7: the 2D Legendre contraction on the tensor cores (langevin_tc.cu); returns 1 when it did not apply
 template <typename T> int run_tc(pyves_ctx*, const StepArgs<T>&, cudaStream_t) { return 1; }
-template <> int run_tc<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream_t st) {
+// builds the operand image of the folded coefficient matrices from the handle's current 2D coefficients (FP32 handles, bases <= 64 x 64)
+int refresh_tc_img(pyves_ctx* h, cudaStream_t st) {
+  if (h->prec != PYVES_F32) return PYVES_OK;
   if (!h->tc_img) CU(cudaMalloc(&h->tc_img, langevin2d_tc_scratch_bytes()));
+  const cudaError_t rc = langevin2d_tc_prepare(l2_params<float>(h), h->tc_img, st);
+  if (rc == cudaErrorNotSupported) return PYVES_OK;
+  if (rc != cudaSuccess) return fail(h, PYVES_ECUDA, std::string("langevin2d_tc_prepare: ") + cudaGetErrorString(rc));
+  g_launches++;
+  h->tc_img_valid = true;
+  return PYVES_OK;
+}
+
+template <> int run_tc<float>(pyves_ctx* h, const StepArgs<float>& A, cudaStream_t st) {
+  if (!h->tc_img_valid) {
+    const int rc0 = refresh_tc_img(h, st);
+    if (rc0) return rc0;
+    if (!h->tc_img_valid) return 1;
+  }
   const cudaError_t rc = launch_langevin2d_tc(A, integrator_params<float>(h), pot_params<float>(h), l2_params<float>(h), make_keys(h->seed), h->tc_img, st);
   if (rc == cudaErrorNotSupported) return 1;
   if (rc != cudaSuccess) return fail(h, PYVES_ECUDA, std::string("launch_langevin2d_tc: ") + cudaGetErrorString(rc));
-  g_launches += 2;   // tc_weight_prep_kernel + langevin2d_tc_kernel
+  g_launches++;
   return PYVES_OK;
 }
 
@@ -730,6 +747,7 @@ template <typename T> static int set_l2_device(pyves_ctx* h, const double* w_dev
   }
   CU(launch_convert_weights2d<T>(w_dev, kx, ky, static_cast<T*>(h->l2_w_dev), static_cast<T*>(h->l2_wt_dev), st));
   g_launches++;
+  h->tc_img_valid = false;
   return PYVES_OK;
 }
 
@@ -881,6 +899,19 @@ int pyves_averaged_sgd_step(int device, int K, const double* sum_w, const double
   return PYVES_OK;
 }
 
+int pyves_iterate_pinned(pyves_t* h, const void* pos_in, const void* vel_in, int64_t nsteps, double* sum_w, double* sum_wf, void* pos_out,
+                         void* vel_out, void* stream) {
+  if (!h) return PYVES_EINVAL;
+  if (!pos_in || !vel_in || !sum_w || !sum_wf || !pos_out || !vel_out) return fail(h, PYVES_EINVAL, "iterate_pinned: NULL buffer");
+  int rc = pyves_set_state(h, pos_in, vel_in, 2, stream);
+  if (rc) return rc;
+  rc = pyves_step(h, nsteps, nullptr, stream);
+  if (rc) return rc;
+  rc = pyves_moments(h, nullptr, 0, 0, nullptr, sum_w, sum_wf, nullptr, 0, stream);
+  if (rc) return rc;
+  return pyves_get_state(h, pos_out, vel_out, 2, stream);
+}
+
 int pyves_step_wave_walkers(pyves_t* h, int64_t* walkers) {
   if (!h || !walkers) return PYVES_EINVAL;
   *walkers = 0;
@@ -990,6 +1021,7 @@ int pyves_set_bias_legendre2d(pyves_t* h, int deg_x, int deg_y, const double* mm
   if (rc) return rc;
   h->l2_dev_mode = false;
   h->l2_dev_count = 0;           // upload() reallocated l2_w_dev
+  h->tc_img_valid = false;
   h->bias_kind = PYVES_BIAS_LEGENDRE_2D;
   return PYVES_OK;
 }
@@ -1059,6 +1091,21 @@ int pyves_set_bias_like(pyves_t* h, const pyves_t* leader, void* stream) {
     std::memcpy(h->l2_mm, leader->l2_mm, sizeof(h->l2_mm));
     h->l2_dev_mode = true;
     h->l2_w.clear();
+    // the operand image of the tensor-core step kernel: built ONCE by the leader, copied to every follower (a follower that built
+    // its own in front of its step kernel would wait for an SM that the previous shard's step kernel still holds)
+    h->tc_img_valid = false;
+    if (h->prec == PYVES_F32) {
+      pyves_ctx* L = const_cast<pyves_ctx*>(leader);
+      if (!L->tc_img_valid) {
+        const int rc = refresh_tc_img(L, st);
+        if (rc) return rc;
+      }
+      if (L->tc_img_valid) {
+        if (!h->tc_img) CU(cudaMalloc(&h->tc_img, langevin2d_tc_scratch_bytes()));
+        CU(cudaMemcpyAsync(h->tc_img, L->tc_img, langevin2d_tc_scratch_bytes(), cudaMemcpyDeviceToDevice, st));
+        h->tc_img_valid = true;
+      }
+    }
   }
   h->const_tag = leader->const_tag;   // same content: a launch of either handle finds the __constant__ array up to date
   h->bias_kind = leader->bias_kind;

@@ -369,9 +369,10 @@ langevin_general_kernel(const StepArgs<T> A, const IntegratorParams<T> I, const 
 template <typename T> cudaError_t upload_static_weights(const T* dev_src, int n, cudaStream_t st);
 
 // experimental tensor-core step kernel for the 2D Legendre bias (langevin_tc.cu); cudaErrorNotSupported when it does not apply
-// `scratch`: device buffer of langevin2d_tc_scratch_bytes() bytes owned by the caller (the operand image of the folded coefficient
-// matrices, rebuilt by a one-block kernel on `st` at every launch, so coefficients updated on the device are picked up)
+// `scratch`: device buffer of langevin2d_tc_scratch_bytes() bytes owned by the caller: the operand image of the folded coefficient
+// matrices, built by langevin2d_tc_prepare (a one-block kernel on `st`) whenever the coefficients change and read by every launch
 size_t langevin2d_tc_scratch_bytes();
+cudaError_t langevin2d_tc_prepare(const Legendre2DSmemParams<float>& BP, void* scratch, cudaStream_t st);
 int langevin2d_tc_walkers_per_cta(int kx, int ky);     // of the shape the launcher picks (one CTA per SM)
 int langevin2d_tc_mlp_walkers_per_cta(int H, int act);
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,

@@ -617,6 +617,7 @@ langevin2d_tc_kernel(const StepArgs<float> A, const IntegratorParams<float> I, c
 template <int KXP, int KYP, int G, int WPT, class POT = PotGeneric<float>>
 cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,
                       const Legendre2DSmemParams<float>& BP, const RngKeys& K, unsigned char* img, cudaStream_t st) {
+  if (img == nullptr) return cudaErrorInvalidValue;
   auto kern = A.noise != nullptr ? langevin2d_tc_kernel<KXP, KYP, G, WPT, true, POT> : langevin2d_tc_kernel<KXP, KYP, G, WPT, false, POT>;
   const size_t smem = sizeof(TcSmem<KYP, G, WPT>) + 1024;
   static_assert(sizeof(TcSmem<KYP, G, WPT>) + 1024 <= 227 * 1024, "operand tiles do not fit the shared memory of an SM");
@@ -629,7 +630,6 @@ cudaError_t launch_tc(const StepArgs<float>& A, const IntegratorParams<float>& I
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kGT * G, smem);
   TcGrid GR;
   const unsigned grid = tc_deal_sets(A.n, G * WPT, WPT, resident, GR);
-  tc_weight_prep_kernel<<<1, 1024, 0, st>>>(BP, KXP, img);
   kern<<<grid, kGT * G, smem, st>>>(A, I, PP, BP, K, img, GR);
   return cudaGetLastError();
 }
@@ -1154,6 +1154,14 @@ int langevin2d_tc_mlp_walkers_per_cta(int H, int act) {
     case 64: return kGT * (relu ? 4 : 3);
     default: return 0;
   }
+}
+
+// the operand image of the folded coefficient matrices (see tc_weight_prep_kernel), rebuilt whenever the coefficients change
+cudaError_t langevin2d_tc_prepare(const Legendre2DSmemParams<float>& BP, void* scratch, cudaStream_t st) {
+  if (BP.kx > 64 || BP.ky > 64 || BP.kx < 1 || BP.ky < 1 || scratch == nullptr) return cudaErrorNotSupported;
+  const int KXP = BP.kx <= 16 ? 16 : BP.kx <= 32 ? 32 : 64;
+  tc_weight_prep_kernel<<<1, 1024, 0, st>>>(BP, KXP, static_cast<unsigned char*>(scratch));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_langevin2d_tc(const StepArgs<float>& A, const IntegratorParams<float>& I, const PotParams<float>& PP,

@@ -392,10 +392,13 @@ def test_chunked_handles_async_copies_match_single_handle():
         for c in range(nch):
             streams[c].wait_stream(main)
             with torch.cuda.stream(streams[c]):
-                subs[c].set_state(hp[c], hv[c], async_copy=True)
-                subs[c].step(stride)
-                subs[c].moments(out=mom[c])
-                subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)
+                if c % 2:                                   # the same four operations as one C call (pyves_iterate_pinned)
+                    subs[c].iterate_pinned(hp[c], hv[c], stride, mom[c])
+                else:
+                    subs[c].set_state(hp[c], hv[c], async_copy=True)
+                    subs[c].step(stride)
+                    subs[c].moments(out=mom[c])
+                    subs[c].get_state(out=(hp[c], hv[c]), async_copy=True)
         for c in range(nch):
             main.wait_stream(streams[c])
         upd.update(sum(m[0] for m in mom), sum(m[1] for m in mom))
