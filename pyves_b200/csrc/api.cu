@@ -69,7 +69,8 @@ struct pyves_ctx {
   int* pwl_grid = nullptr;         // bucket grid of the breakpoints (kPwlBuckets + 1 ints) and its {origin, buckets per unit}
   void* pwl_grid_map = nullptr;
   int pwl_cap = 0;
-  bool pwl_valid = false;
+  bool pwl_valid = false;          // the handle's bias is a ReLU net this applies to
+  bool pwl_stale = true;           // the table does not reflect the current parameters yet (built on first use, ensure_pwl)
   double* pwl_hist = nullptr;      // moments through the pieces: histogram, pseudo rows, their weights
   void* pwl_rows = nullptr;
   void* pwl_row_w = nullptr;
@@ -254,13 +255,21 @@ template <typename T, int KX, int KY> Legendre2DStaticTCParams<T, KX, KY> l2_sta
   return P;
 }
 
-// ReLU nets with two or three hidden layers: compile the packed parameters into the piecewise-constant dV/ds of BiasPwl1D
-// (stream ordered after the pack / upload that precedes it).  Anything else leaves pwl_valid false.
-int refresh_pwl(pyves_ctx* h, cudaStream_t st) {
+// ReLU nets with two or three hidden layers can be compiled into the piecewise-constant dV/ds of BiasPwl1D.  refresh_pwl (called by
+// the parameter setters) only decides whether that applies and marks the table stale; ensure_pwl builds it on the stream of the first
+// step / moments call that wants it -- an FP64 evaluator handle that never asks never pays for it.
+int refresh_pwl(pyves_ctx* h, cudaStream_t) {
   h->pwl_valid = false;
+  h->pwl_stale = true;
   if (h->mlp_act != PYVES_ACT_RELU || h->mlp_linear || h->mlp_H < 0) return PYVES_OK;
   const int n1 = h->mlp_H > 0 ? h->mlp_H : h->mlp_width;
   if (n1 < 1 || n1 > 128) return PYVES_OK;
+  h->pwl_valid = true;
+  return PYVES_OK;
+}
+
+int ensure_pwl(pyves_ctx* h, cudaStream_t st) {
+  if (!h->pwl_valid || !h->pwl_stale) return PYVES_OK;
   const int cap = mlp_pwl_capacity(h->mlp_H, h->mlp_width);
   if (cap > h->pwl_cap) {
     if (h->pwl_brk) cudaFree(h->pwl_brk);
@@ -283,7 +292,7 @@ int refresh_pwl(pyves_ctx* h, cudaStream_t st) {
                                    static_cast<float*>(h->pwl_slope), h->pwl_count, h->pwl_grid, static_cast<float*>(h->pwl_grid_map), st));
   }
   g_launches++;
-  h->pwl_valid = true;
+  h->pwl_stale = false;
   return PYVES_OK;
 }
 
@@ -605,6 +614,7 @@ int do_step(pyves_ctx* h, int64_t nsteps, const void* noise, void* traj, int64_t
       // ReLU nets with two / three hidden layers, FP32 default: dV/ds is piecewise constant in the one input -- a binary search
       // (variant 8 forces it for FP64 handles too; 6 / 7 keep the CUDA-core / tensor-core evaluation of the network)
       if (h->pwl_valid && ((h->variant == -1 && sizeof(T) == 4) || h->variant == 8)) {
+        { const int rc = ensure_pwl(h, st); if (rc) return rc; }
         if (pk == PYVES_POT_SZABO_BEREZHKOVSKII) return run_fast<T, SB, BiasPwl1D<T>, 2, 1>(h, A, pwl_params<T>(h), st);
         return run_fast<T, GP, BiasPwl1D<T>, 2, 1>(h, A, pwl_params<T>(h), st);
       }
@@ -675,8 +685,9 @@ static int moments_impl(pyves_ctx* h, const void* pos, int64_t n, int ncols, con
     M.inside_only = h->mom_inside;
     // ReLU nets: rows binned into the pieces of the piecewise-linear network, gradients on one pseudo row per piece (moments.cuh);
     // FP32 default for ensembles much larger than the table, variant 8 always
-    const int cap = h->pwl_cap;
+    const int cap = h->pwl_valid ? mlp_pwl_capacity(h->mlp_H, h->mlp_width) : 0;
     if (h->pwl_valid && S.ncols <= 2 && (h->variant == 8 || (h->variant == -1 && sizeof(T) == 4 && S.n >= 8 * (int64_t)(cap + 1)))) {
+      { const int rc = ensure_pwl(h, st); if (rc) return rc; }
       if (h->pwl_hist_cap < cap) {
         if (h->pwl_hist) cudaFree(h->pwl_hist);
         if (h->pwl_rows) cudaFree(h->pwl_rows);
