@@ -424,3 +424,26 @@ def test_trajectory_reader_formats(tmp_path):
     assert TrajectoryReader(str(f)).read_traj(skip=2)[1].shape == (2, 3)
     with pytest.raises(ValueError, match="Invalid format"):
         TrajectoryReader(str(tmp_path / "missing.dat"), format='tx').read_traj()
+
+
+def test_relu_nnbasis1d_is_piecewise_linear_in_its_input():
+    """The two facts the piecewise-constant NN paths of the CUDA side rest on (csrc/bias.cuh BiasPwl1D, csrc/moments.cu pwl_hist_kernel),
+    checked on the CPU against the network itself (oracle/mlp.py): dV/ds looked up in the compiled table equals the derivative of the
+    network, and parameter-gradient sums over rows equal the sums over one pseudo row per piece."""
+    from oracle import mlp, pwl
+    rng = np.random.default_rng(12)
+    for sizes in ([16], [7, 9], [48, 48, 48], [10, 12, 8, 6]):
+        theta = rng.standard_normal(mlp.n_params(sizes)) * 0.5
+        brk, slope = pwl.compile_pwl(theta, sizes)
+        assert np.all(np.diff(brk) >= 0) and len(slope) == len(brk) + 1
+        s = rng.uniform(-1.5, 2.5, 4000)
+        if len(brk):                                   # stay clear of the switch points (the derivative jumps there)
+            s = s[np.min(np.abs(s[:, None] - brk[None, :]), axis=1) > 1e-9]
+        _, dV = mlp.forward(s, theta, sizes, mlp.ACT_RELU)
+        scale = max(1.0, float(np.max(np.abs(dV))))
+        assert np.max(np.abs(pwl.slope_at(s, brk, slope) - dV)) < 1e-10 * scale, sizes
+        w = rng.uniform(0, 2, s.size)
+        ref = mlp.param_grad(s, theta, sizes, mlp.ACT_RELU, w)
+        got, rows = pwl.param_grad_through_pieces(s, theta, sizes, w)
+        assert rows <= len(brk) + 1
+        assert np.max(np.abs(got - ref)) < 1e-9 * max(1.0, float(np.max(np.abs(ref)))), sizes
