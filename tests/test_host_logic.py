@@ -447,3 +447,26 @@ def test_relu_nnbasis1d_is_piecewise_linear_in_its_input():
         got, rows = pwl.param_grad_through_pieces(s, theta, sizes, w)
         assert rows <= len(brk) + 1
         assert np.max(np.abs(got - ref)) < 1e-9 * max(1.0, float(np.max(np.abs(ref)))), sizes
+
+
+def test_folded_legendre_derivatives_and_monic_recursion():
+    """The two rewrites of the tensor-core Legendre step kernel (csrc/langevin_tc.cu), checked on the CPU against the recursion of
+    oracle/legendre.py: forces from Legendre VALUES only through the folded matrices WA / WB, and the scaled monic recursion."""
+    from oracle import legendre, legendre_fold as lf
+    rng = np.random.default_rng(3)
+    s = np.concatenate([rng.uniform(-1, 1, 500), [-1.0, 1.0, 0.0]])
+    cc, d, kappa = lf.monic_table(64)
+    assert set(np.unique(d)) <= {0, 1} and kappa.min() > 0.70 and kappa.max() < 1.42
+    P, _ = legendre.legendre_table(s, 63)
+    q = lf.monic_values(s, 64)
+    assert np.max(np.abs(q)) < 1.42 and np.max(np.abs(kappa[:, None] * q - P)) < 1e-12
+    for kx, ky in ((16, 16), (64, 64), (5, 11), (17, 3), (1, 50), (2, 1)):
+        w = rng.standard_normal((kx, ky))
+        sx, sy = rng.uniform(-1, 1, 300), rng.uniform(-1, 1, 300)
+        Px, dPx = legendre.legendre_table(sx, kx - 1)
+        Py, dPy = legendre.legendre_table(sy, ky - 1)
+        gx_ref = np.sum(dPx * (w @ Py), axis=0)
+        gy_ref = np.sum(Px * (w @ dPy), axis=0)
+        gx, gy = lf.gradient_folded(sx, sy, w)
+        scale = max(1.0, float(np.max(np.abs(gx_ref))), float(np.max(np.abs(gy_ref))))
+        assert np.max(np.abs(gx - gx_ref)) < 1e-10 * scale and np.max(np.abs(gy - gy_ref)) < 1e-10 * scale, (kx, ky)
